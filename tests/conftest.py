@@ -1,0 +1,26 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+@pytest.fixture(scope="session")
+def hn():
+    """The product package (directory name has hyphens, so it is imported by path)."""
+    return importlib.import_module("nerf-3dtalker-code_b200")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import headnerf_oracle
+    return headnerf_oracle

@@ -1,0 +1,116 @@
+"""Pins oracle/headnerf_oracle.py against the REAL reference (imported from /root/reference).
+
+Runs only where the reference tree exists (the build container); skipped on the GPU box, where the
+committed fixtures under tests/golden/ (outputs of the real reference) take over (test_golden.py).
+Bar: bit-equality in fp32 on CPU for every intermediate the path defines."""
+import pytest
+import torch
+
+from oracle import headnerf_oracle as O
+from oracle import ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present")
+
+
+def _opts(fs, S, hidden=None, ns=None):
+    o = O.OracleOptions(featmap_size=fs, pred_img_size=S)
+    if hidden:
+        o.mlp_hidden_nchannels = hidden
+    if ns:
+        o.num_sample_coarse = ns
+    return o
+
+
+def _hook_features(net):
+    taps = {}
+    net.calc_color_func.register_forward_hook(lambda m, i, o: taps.update(F=o[0], bg_alpha=o[1], depth=o[2], w=o[3]))
+    net.fg_CD_predictor.register_forward_hook(lambda m, i, o: taps.update(feat=o[0], density=o[1]))
+    return taps
+
+
+@pytest.mark.parametrize("fs,S,B,mode", [(8, 32, 2, "test"), (8, 64, 1, "train"), (16, 64, 1, "test")])
+def test_forward_bit_equal(fs, S, B, mode):
+    torch.manual_seed(0)
+    opt_ref, net = ref_import.build(fs, S)
+    net.eval()
+    opt = _opts(fs, S)
+    assert list(net.state_dict().keys()) == list(O.state_dict_shapes(opt).keys())
+    for k, v in net.state_dict().items():
+        assert tuple(v.shape) == O.state_dict_shapes(opt)[k], k
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    inp = O.synthetic_inputs(opt, B, seed=3)
+    taps = _hook_features(net)
+    with torch.no_grad():
+        torch.manual_seed(11)
+        ref = net(mode, inp["batch_xy"], None, inp["audiostyle"], None, inp["shape_code"], inp["appea_code"],
+                  inp["batch_Rmats"], inp["batch_Tvecs"], inp["batch_inv_inmats"])
+        torch.manual_seed(11)          # same global RNG stream -> same jitter (utils.py:77)
+        got, r = O.headnerf_forward(sd, opt, mode, inp["batch_xy"], inp["audiostyle"], inp["shape_code"],
+                                    inp["appea_code"], inp["batch_Rmats"], inp["batch_Tvecs"], inp["batch_inv_inmats"])
+    for k in ("feat", "density", "F", "bg_alpha", "depth", "w"):
+        assert torch.equal(taps[k], r[k]), k
+    for k in ("merge_img", "bg_img"):
+        assert torch.equal(ref["coarse_dict"][k], got["coarse_dict"][k]), k
+
+
+def test_explicit_jitter_matches_rng_jitter():
+    opt = _opts(8, 32)
+    sd = O.formula_state_dict(opt)
+    inp = O.synthetic_inputs(opt, 1, seed=5)
+    args = (inp["batch_xy"], inp["audiostyle"], inp["shape_code"], inp["appea_code"],
+            inp["batch_Rmats"], inp["batch_Tvecs"], inp["batch_inv_inmats"])
+    torch.manual_seed(7)
+    a = O.render_features(sd, opt, "train", *args)
+    torch.manual_seed(7)
+    t_rand = torch.rand(1, 64, 65)
+    b = O.render_features(sd, opt, "train", *args, t_rand=t_rand)
+    assert torch.equal(a["F"], b["F"])
+
+
+def test_backward_matches_reference():
+    """Gradients of the restatement equal the reference's autograd on every leaf (fp64, tight)."""
+    torch.manual_seed(0)
+    _, net = ref_import.build(8, 32)
+    net = net.double()
+    opt = _opts(8, 32)
+    inp = O.synthetic_inputs(opt, 2, seed=9, dtype=torch.float64)
+    leaves = ["shape_code", "appea_code", "audiostyle", "batch_Rmats", "batch_Tvecs"]
+
+    def run(fn_is_ref):
+        x = {k: v.clone().requires_grad_(k in leaves) for k, v in inp.items()}
+        if fn_is_ref:
+            net.zero_grad()
+            out = net("test", x["batch_xy"], None, x["audiostyle"], None, x["shape_code"], x["appea_code"],
+                      x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"])
+            params = dict(net.named_parameters())
+        else:
+            params = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(".f"))
+                      for k, v in net.state_dict().items()}
+            out, _ = O.headnerf_forward(params, opt, "test", x["batch_xy"], x["audiostyle"], x["shape_code"],
+                                        x["appea_code"], x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"])
+        img = out["coarse_dict"]["merge_img"]
+        tgt = torch.linspace(0, 1, img.numel(), dtype=img.dtype).view_as(img)
+        ((img - tgt) ** 2).mean().backward()
+        g = {k: x[k].grad for k in leaves}
+        g.update({k: p.grad for k, p in params.items() if p.grad is not None})
+        return g
+
+    gr, go = run(True), run(False)
+    assert set(gr) == set(go)
+    for k in gr:
+        assert torch.allclose(gr[k], go[k], rtol=1e-9, atol=1e-14), k
+
+
+def test_init_seed_parity(hn=None):
+    """The drop-in's constructor draws the same parameters as the reference under the same seed."""
+    import importlib
+    hn = importlib.import_module("nerf-3dtalker-code_b200")
+    torch.manual_seed(123)
+    _, ref = ref_import.build(8, 32)
+    torch.manual_seed(123)
+    mine = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": 8, "featmap_nc": 256, "pred_img_size": 32}),
+                          include_vd=False, hier_sampling=False)
+    sr, sm = ref.state_dict(), mine.state_dict()
+    assert list(sr.keys()) == list(sm.keys())
+    for k in sr:
+        assert torch.equal(sr[k], sm[k]), k
