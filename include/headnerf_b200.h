@@ -1,0 +1,216 @@
+/* headnerf_b200.h — C ABI of libheadnerf_b200.so: the sm_100a implementation of the HeadNeRF rendering
+ * hot path (ray sampling -> positional encoding -> fg_CD_predictor MLP -> alpha compositing).
+ *
+ * The reference (NeRF-3DTalker) is pure Python/PyTorch and has no FFI of its own; each entry point
+ * below replaces the reference code cited beside it (paths relative to the reference root) and is
+ * bound from Python with ctypes (see INTEGRATION.md and nerf-3dtalker-code_b200/_lib.py).
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the caller owns all memory (inputs, outputs, saved-for-backward, workspace); the library never
+ *    allocates, never synchronises, and launches on the stream passed as `stream` (a cudaStream_t);
+ *  - every function returns 0 on success, a negative HN_E_* code on a bad argument, or a positive
+ *    cudaError_t value; hn_last_error() returns a thread-local human-readable message;
+ *  - samples are indexed m = (b*n_rays + r)*n_samples + s; M = B*n_rays*n_samples must be a multiple
+ *    of 128 and n_samples one of 32/64/128 (whole rays per 128-sample tile, tiles never straddle items);
+ *  - "image" buffers hold half-precision operand blocks of 128 rows x 64 columns = 16 KiB in the
+ *    tensor-core SWIZZLE_128B layout (csrc/hn_tc.cuh); block (slot, tile, kb) of a saved tensor lives at
+ *    byte ((slot_base + kb) * n_tiles + tile) * 16384.
+ */
+#ifndef HEADNERF_B200_H_
+#define HEADNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HN_ABI_VERSION 1
+
+/* error codes (negative = argument / configuration errors) */
+#define HN_OK 0
+#define HN_E_BADARG (-1)      /* null pointer, non-positive size, misaligned buffer                */
+#define HN_E_UNSUPPORTED (-2) /* dimensions outside what the sm_100a kernels are specialised for    */
+#define HN_E_PROTOCOL (-3)    /* a kernel's internal pipeline timed out (reported via status word)  */
+
+/* Fixed architecture of fg_CD_predictor (NetWorks/models.py:29-59, HeadNeRFOptions.py:20-29). */
+#define HN_HIDDEN 384     /* mlp_hidden_nchannels                              */
+#define HN_FEAT 256       /* featmap_nc                                        */
+#define HN_RGB1 192       /* HIDDEN/2, output of RGB_layer_1                   */
+#define HN_PE 63          /* 3 + 2*3*10 positional-encoding channels           */
+#define HN_PE_PAD 64
+#define HN_TILE 128       /* samples per tile                                  */
+
+/* Per-batch-item effective biases (latent codes folded in): one row of
+ * HN_BIAS_STRIDE floats per batch item, laid out as
+ *   [0,3072)    FeaExt_module_0..7   (8 x 384)
+ *   [3072,3456) RGB_layer_0          (384)
+ *   [3456,3648) RGB_layer_1          (192)
+ *   [3648,3904) RGB_layer_2          (256)
+ *   [3904]      density_module bias  (1)            rest: padding                                    */
+#define HN_BIAS_OFF_R0 3072
+#define HN_BIAS_OFF_R1 3456
+#define HN_BIAS_OFF_R2 3648
+#define HN_BIAS_OFF_DENSITY 3904
+#define HN_BIAS_STRIDE 3920
+
+/* Saved-activation slots (forward -> backward), in units of 64-column blocks. */
+#define HN_SLOT_PE 0      /* 1 block : positional encoding (63 ch + zero pad)                        */
+#define HN_SLOT_H0 1      /* 8 x 6 blocks : outputs of FeaExt_module_0..7 (post-ReLU)                */
+#define HN_SLOT_R0 49     /* 6 blocks : output of RGB_layer_0 (no activation)                        */
+#define HN_SLOT_X 55      /* 3 blocks : output of RGB_layer_1 (post-ReLU)                            */
+#define HN_ACT_BLOCKS 58
+/* Gradient slots written by hn_mlp_bwd_data, read by hn_mlp_bwd_weights (pre-activation gradients). */
+#define HN_GSLOT_Z0 0     /* 8 x 6 blocks : dL/d(pre-act) of FeaExt_module_0..7                      */
+#define HN_GSLOT_R0 48    /* 6 blocks : RGB_layer_0                                                  */
+#define HN_GSLOT_R1 54    /* 3 blocks : RGB_layer_1                                                  */
+#define HN_GSLOT_DENS 57  /* 1 block  : density head, column 0 = dL/d(pre-ReLU density), rest zero    */
+#define HN_GRAD_BLOCKS 59 /* + 1 never-written pad block (rows of it only reach ignored outputs)      */
+/* ReLU sign masks: 9 masked layers (FeaExt 0..7: 12 words/sample, RGB_layer_1: 6 words/sample). */
+#define HN_MASK_WORDS 104 /* 8*12 + 6 uint32 per sample, padded so a row is a multiple of 16 bytes      */
+
+int hn_abi_version(void);
+const char* hn_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight packing.  Replaces nothing in the reference (cuDNN consumes the fp32 [out,in,1,1] tensors
+ * directly, NetWorks/models.py:32-59); produces the half-precision operand images the kernels stream.
+ * `w` holds 12 device pointers to the fp32 state-dict tensors in this order:
+ *   FeaExt_module_0..7.weight, density_module.weight, RGB_layer_0.weight, RGB_layer_1.weight,
+ *   RGB_layer_2.weight,   with row strides (= in_channels) in `ld`.  Column blocks that multiply
+ * per-item constants (shape/audio/appearance codes) are NOT packed: they are folded into the bias.
+ * `pe_col`/`h_col` give the column offset of the PE block and of the hidden block inside layers 0/5
+ * and RGB_layer_1 (reference concat orders).                                           */
+typedef struct {
+    const float* w[12];
+    int ld[12];
+    int l5_hidden_col;   /* column of the h block in FeaExt_module_5.weight (242 without gaze)        */
+} hn_weights_t;
+
+size_t hn_packed_weights_bytes(void);
+int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray generation + stratified sampling (standalone form).   NetWorks/utils.py:64-161
+ * Outputs are per sample, sample-major.  Any output pointer may be NULL.                            */
+typedef struct {
+    int B, n_rays, n_samples;
+    float world_z1, world_z2;
+    const float* xy;        /* [B,2,n_rays]  (reference layout)                                      */
+    const float* Rmats;     /* [B,3,3] camera-to-world rotation                                      */
+    const float* Tvecs;     /* [B,3]   camera-to-world translation                                   */
+    const float* inv_inmats;/* [B,3,3]                                                               */
+    const float* t_rand;    /* [B,n_rays,n_samples+1] uniform draws, or NULL for mode "test"          */
+} hn_camera_t;
+
+int hn_sample_rays(const hn_camera_t* cam, float* pts /*[M,3]*/, float* zvals /*[M]*/, float* z_dists /*[M]*/,
+                   float* ray_d /*[B*n_rays,3]*/, float* ray_l /*[B*n_rays]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused sampling + positional encoding + MLP forward.
+ * NetWorks/utils.py:43-51,147-161 ; NetWorks/HeadNeRFNet.py:139-152,84-95 ; NetWorks/models.py:62-87  */
+typedef struct {
+    hn_camera_t cam;
+    const float* bias;        /* [B, HN_BIAS_STRIDE] effective biases                                 */
+    const float* w_density;   /* [384] fp32 density_module.weight                                     */
+    const void* packed;       /* from hn_pack_weights                                                 */
+    float* feat;              /* [M,256] out (NULL allowed when `xbar` is set)                        */
+    float* sigma;             /* [M] out: relu(density)                                               */
+    float* delta;             /* [M] out: z_dists                                                     */
+    float* zvals;             /* [M] out or NULL                                                      */
+    void* act;                /* [HN_ACT_BLOCKS, n_tiles, 16 KiB] out or NULL (no backward)            */
+    uint32_t* masks;          /* [M, HN_MASK_WORDS] out or NULL                                       */
+    int* status;              /* device int, zero-initialised by caller; nonzero = pipeline fault     */
+} hn_mlp_fwd_t;
+
+int hn_mlp_fwd(const hn_mlp_fwd_t* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Alpha compositing, forward and backward.                  NetWorks/utils.py:273-309
+ * feat is sample-major [M,C]; one warp per ray.  C must be a multiple of 128 (<= 256).               */
+typedef struct {
+    int n_rays_total, n_samples, C;
+    const float* feat;   /* [M,C] */
+    const float* sigma;  /* [M]   */
+    const float* delta;  /* [M]   */
+    const float* zvals;  /* [M] or NULL (depth not computed) */
+    float* F;            /* [n_rays_total, C] out */
+    float* bg_alpha;     /* [n_rays_total]    out */
+    float* depth;        /* [n_rays_total]    out or NULL */
+    float* weights;      /* [M]               out or NULL */
+} hn_composite_fwd_t;
+
+int hn_composite_fwd(const hn_composite_fwd_t* a, void* stream);
+
+typedef struct {
+    int n_rays_total, n_samples, C;
+    const float* feat; const float* sigma; const float* delta; const float* zvals;
+    const float* gF;        /* [n_rays_total, C] */
+    const float* g_bg;      /* [n_rays_total]    */
+    const float* g_depth;   /* [n_rays_total] or NULL */
+    float* dfeat;           /* [M,C] fp32 out, or NULL                                               */
+    void* dfeat_image;      /* half-precision image out [C/64, n_tiles, 16 KiB], scaled by *grad_scale, or NULL */
+    const float* grad_scale;/* device scalar (power of two) used for dfeat_image                      */
+    float* dsigma;          /* [M] out  (w.r.t. the post-ReLU density)                                */
+    float* ddelta;          /* [M] out or NULL                                                        */
+} hn_composite_bwd_t;
+
+int hn_composite_bwd(const hn_composite_bwd_t* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MLP backward, data path: dL/dfeat, dL/dsigma -> pre-activation gradients of every layer (saved as
+ * images for the weight pass), dL/d(positional encoding) reduced to per-ray camera-side gradients.
+ * Autograd of NetWorks/models.py:62-87 and NetWorks/utils.py:43-51,80-86.                            */
+typedef struct {
+    hn_camera_t cam;
+    const void* packed;
+    const float* w_density;
+    const void* dfeat_image;  /* from hn_composite_bwd                                                */
+    const float* dsigma;      /* [M] fp32, unscaled                                                   */
+    const float* ddelta;      /* [M] fp32, unscaled, or NULL                                          */
+    const float* sigma;       /* [M] saved forward output (ReLU mask of the density head)             */
+    const float* grad_scale;  /* device scalar                                                        */
+    const uint32_t* masks;    /* saved by hn_mlp_fwd                                                  */
+    const void* act;          /* saved by hn_mlp_fwd (PE block is re-used for the sampling gradient)   */
+    void* grads;              /* [HN_GRAD_BLOCKS, n_tiles, 16 KiB] out                                 */
+    float* g_ray_o;           /* [B*n_rays,3] out or NULL: dL/d ray origin                             */
+    float* g_ray_v;           /* [B*n_rays,3] out or NULL: dL/d (ray_d * ray_l)                        */
+    float* g_ray_l;           /* [B*n_rays]   out or NULL: dL/d ray_l through z_dists                  */
+    int* status;
+} hn_mlp_bwd_data_t;
+
+int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream);
+
+/* MLP backward, weight path: contraction over all samples of (pre-activation gradient)^T x (layer input).
+ * Accumulates (atomically, caller zero-initialises) into fp32 gradient tensors shaped like the
+ * reference state dict, and into d(bias) [B, HN_BIAS_STRIDE].                                         */
+typedef struct {
+    int B, n_rays, n_samples;
+    const void* act;          /* saved by hn_mlp_fwd                                                   */
+    const void* grads;        /* saved by hn_mlp_bwd_data                                              */
+    const void* dfeat_image;  /* from hn_composite_bwd (pre-activation gradient of RGB_layer_2)        */
+    const float* grad_scale;
+    float* dw[12];            /* same order / leading dimensions as hn_weights_t; NULL entries skipped; */
+    int ld[12];               /* all NULL = only the bias gradients of the latent-folded layers         */
+    int l5_hidden_col;
+    float* dbias;             /* [B, HN_BIAS_STRIDE]                                                  */
+    void* items_workspace;    /* device scratch for the work-item table, hn_wgrad_workspace_bytes(B)   */
+    size_t items_workspace_bytes;
+    int* status;
+} hn_mlp_bwd_weights_t;
+
+size_t hn_wgrad_workspace_bytes(int B);
+int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream);
+
+/* Bytes of the saved-for-backward buffers for M samples. */
+size_t hn_act_bytes(int64_t M);
+size_t hn_grads_bytes(int64_t M);
+size_t hn_mask_bytes(int64_t M);
+size_t hn_dfeat_image_bytes(int64_t M);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEADNERF_B200_H_ */

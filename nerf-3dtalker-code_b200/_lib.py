@@ -1,0 +1,107 @@
+"""ctypes binding of libheadnerf_b200.so — the C ABI declared in include/headnerf_b200.h.
+
+There is deliberately no fallback: if the shared library is missing or a call fails, this raises.
+The structures below mirror the header field for field."""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libheadnerf_b200.so")
+
+HIDDEN, FEAT, RGB1, PE, TILE = 384, 256, 192, 63, 128
+BIAS_OFF_R0, BIAS_OFF_R1, BIAS_OFF_R2, BIAS_OFF_DENSITY, BIAS_STRIDE = 3072, 3456, 3648, 3904, 3920
+ACT_BLOCKS, GRAD_BLOCKS, MASK_WORDS = 58, 59, 104
+
+_p = C.c_void_p
+
+
+class Camera(C.Structure):
+    _fields_ = [("B", C.c_int), ("n_rays", C.c_int), ("n_samples", C.c_int),
+                ("world_z1", C.c_float), ("world_z2", C.c_float),
+                ("xy", _p), ("Rmats", _p), ("Tvecs", _p), ("inv_inmats", _p), ("t_rand", _p)]
+
+
+class Weights(C.Structure):
+    _fields_ = [("w", _p * 12), ("ld", C.c_int * 12), ("l5_hidden_col", C.c_int)]
+
+
+class MlpFwd(C.Structure):
+    _fields_ = [("cam", Camera), ("bias", _p), ("w_density", _p), ("packed", _p), ("feat", _p), ("sigma", _p),
+                ("delta", _p), ("zvals", _p), ("act", _p), ("masks", _p), ("status", _p)]
+
+
+class CompositeFwd(C.Structure):
+    _fields_ = [("n_rays_total", C.c_int), ("n_samples", C.c_int), ("C", C.c_int),
+                ("feat", _p), ("sigma", _p), ("delta", _p), ("zvals", _p),
+                ("F", _p), ("bg_alpha", _p), ("depth", _p), ("weights", _p)]
+
+
+class CompositeBwd(C.Structure):
+    _fields_ = [("n_rays_total", C.c_int), ("n_samples", C.c_int), ("C", C.c_int),
+                ("feat", _p), ("sigma", _p), ("delta", _p), ("zvals", _p),
+                ("gF", _p), ("g_bg", _p), ("g_depth", _p),
+                ("dfeat", _p), ("dfeat_image", _p), ("grad_scale", _p), ("dsigma", _p), ("ddelta", _p)]
+
+
+class MlpBwdData(C.Structure):
+    _fields_ = [("cam", Camera), ("packed", _p), ("w_density", _p), ("dfeat_image", _p), ("dsigma", _p),
+                ("ddelta", _p), ("sigma", _p), ("grad_scale", _p), ("masks", _p), ("act", _p), ("grads", _p),
+                ("g_ray_o", _p), ("g_ray_v", _p), ("g_ray_l", _p), ("status", _p)]
+
+
+class MlpBwdWeights(C.Structure):
+    _fields_ = [("B", C.c_int), ("n_rays", C.c_int), ("n_samples", C.c_int),
+                ("act", _p), ("grads", _p), ("dfeat_image", _p), ("grad_scale", _p),
+                ("dw", _p * 12), ("ld", C.c_int * 12), ("l5_hidden_col", C.c_int), ("dbias", _p),
+                ("items_workspace", _p), ("items_workspace_bytes", C.c_size_t), ("status", _p)]
+
+
+EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pack_weights", "hn_sample_rays",
+           "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
+           "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes"]
+
+_lib = None
+
+
+class HeadNeRFLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library once.  Raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise HeadNeRFLibraryError(
+            f"{LIB_PATH} not found: the CUDA library must be built first "
+            "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.hn_abi_version.restype = C.c_int
+    lib.hn_last_error.restype = C.c_char_p
+    lib.hn_packed_weights_bytes.restype = C.c_size_t
+    for name in ("hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes"):
+        getattr(lib, name).restype = C.c_size_t
+        getattr(lib, name).argtypes = [C.c_int64]
+    lib.hn_wgrad_workspace_bytes.restype = C.c_size_t
+    lib.hn_wgrad_workspace_bytes.argtypes = [C.c_int]
+    lib.hn_pack_weights.argtypes = [C.POINTER(Weights), _p, _p]
+    lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
+    lib.hn_mlp_fwd.argtypes = [C.POINTER(MlpFwd), _p]
+    lib.hn_composite_fwd.argtypes = [C.POINTER(CompositeFwd), _p]
+    lib.hn_composite_bwd.argtypes = [C.POINTER(CompositeBwd), _p]
+    lib.hn_mlp_bwd_data.argtypes = [C.POINTER(MlpBwdData), _p]
+    lib.hn_mlp_bwd_weights.argtypes = [C.POINTER(MlpBwdWeights), _p]
+    for name in ("hn_pack_weights", "hn_sample_rays", "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd",
+                 "hn_mlp_bwd_data", "hn_mlp_bwd_weights"):
+        getattr(lib, name).restype = C.c_int
+    if lib.hn_abi_version() != 1:
+        raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().hn_last_error().decode("utf-8", "replace")
+        raise HeadNeRFLibraryError(f"{what} failed (code {rc}): {msg}")

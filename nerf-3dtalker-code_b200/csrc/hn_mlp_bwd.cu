@@ -1,0 +1,308 @@
+// hn_mlp_bwd.cu — data-gradient chain of fg_CD_predictor for sm_100a (autograd of NetWorks/models.py:62-87,
+// NetWorks/utils.py:43-51,80-86), the mirror image of hn_mlp_fwd.cu.
+//
+// Per 128-sample tile, one persistent CTA:
+//   producer  : bulk-loads the tile's dL/dfeat operand image (written by hn_composite_bwd) into the gradient
+//               buffer, then streams the transposed weight units (W^T) through the smem ring
+//   MMA issuer: dX = dZ * W for RGB_layer_2, _1, _0, FeaExt_module_7..1 (tcgen05, fp16 operands holding
+//               loss-scaled gradients, fp32 accumulate); dL/dPE accumulates in its own 64 TMEM columns
+//               from FeaExt_module_5 and _0
+//   epilogue  : TMEM -> registers -> (+ dsigma x w_density for the density head) -> ReLU mask from the
+//               forward's bit masks -> fp16 -> gradient buffer (next GEMM's A operand) and, for the weight
+//               pass, bulk-stored to HBM as operand images; finally dL/dPE -> dL/dpts (PE backward) ->
+//               per-ray reductions (origin, direction*length, length) for the camera gradients
+// Gradients are carried multiplied by the power-of-two *grad_scale so that fp16 keeps them in range.
+#include <mutex>
+#include "hn_api.h"
+#include "hn_mlp_sched.h"
+#include "hn_sample.cuh"
+#include "hn_tc.cuh"
+
+namespace hn {
+
+__constant__ BwdTables c_bwd[2];          // [0] without dL/dPE, [1] with
+
+constexpr int kBStages = 6;
+constexpr int kBwdThreads = 256;
+constexpr uint32_t kBOffZ = 0;
+constexpr uint32_t kBOffW = 6 * kUnitBytes;
+constexpr uint32_t kBwdSmem = (6 + kBStages) * kUnitBytes + 1024;
+constexpr uint32_t kBTmemCols = 512;
+
+struct BwdShared {
+    uint64_t w_full[kBStages], w_empty[kBStages];
+    uint64_t a_ready[3], in_ready, z_free, acc_full[4], acc_empty[4];
+    uint32_t tmem_base;
+    volatile int abort;
+};
+
+__device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
+    const uint32_t b = smem_u32(bar);
+    if (mbar_try_wait(b, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(b, parity)) {
+        if (*abort_flag) return false;
+        if (clock64() - t0 > 2000000000ll) {
+            *abort_flag = 1;
+            atomicCAS(status, 0, code);
+            return false;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void bsync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum32(float v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bwd_data_t a, const int n_tiles, const int with_pe) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ BwdShared sh;
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const BwdTables& tb = c_bwd[with_pe];
+    const bool saving = (a.grads != nullptr);
+
+    if (tid == 0) {
+        for (int i = 0; i < kBStages; ++i) { mbar_init(smem_u32(&sh.w_full[i]), 1); mbar_init(smem_u32(&sh.w_empty[i]), 1); }
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&sh.a_ready[i]), 128);
+        mbar_init(smem_u32(&sh.in_ready), 1);
+        mbar_init(smem_u32(&sh.z_free), 128);
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.acc_empty[i]), 128); }
+        sh.abort = 0;
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<kBTmemCols>(smem_u32(&sh.tmem_base));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = sh.tmem_base;
+    const int n_units = tb.n_units, n_epis = tb.n_epis;
+
+    if (warp == 0) {
+        // ======================= producer: dL/dfeat image + W^T units =======================
+        if (lane == 0) {
+            uint32_t uc = 0, par_free = 0;
+            const uint8_t* wt = (const uint8_t*)a.packed + (size_t)kFwdUnits * kUnitBytes;
+            const uint8_t* din = (const uint8_t*)a.dfeat_image;
+            for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
+                if (!bwait(&sh.z_free, par_free ^ 1, &sh.abort, a.status, 401)) break;
+                par_free ^= 1;
+                mbar_arrive_expect_tx(smem_u32(&sh.in_ready), 4 * kUnitBytes);
+                for (int kb = 0; kb < 4; ++kb)
+                    bulk_g2s(smem + kBOffZ + kb * kUnitBytes, din + ((size_t)kb * n_tiles + tile) * kUnitBytes, kUnitBytes, smem_u32(&sh.in_ready));
+                for (int u = 0; u < n_units; ++u, ++uc) {
+                    const uint32_t stage = uc % kBStages, par = (uc / kBStages) & 1;
+                    if (!bwait(&sh.w_empty[stage], par ^ 1, &sh.abort, a.status, 402)) break;
+                    const uint32_t bytes = (uint32_t)tb.mma[u].n8 * 8 * 128;
+                    mbar_arrive_expect_tx(smem_u32(&sh.w_full[stage]), bytes);
+                    bulk_g2s(smem + kBOffW + stage * kUnitBytes, wt + (size_t)tb.mma[u].unit * kUnitBytes, bytes, smem_u32(&sh.w_full[stage]));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            uint32_t uc = 0, par_ready = 0, par_in = 0, par_empty = 0;
+            for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
+                for (int u = 0; u < n_units; ++u, ++uc) {
+                    const MmaOp op = tb.mma[u];
+                    bool ok = true;
+                    if (op.wait_src == 5) { ok = bwait(&sh.in_ready, par_in, &sh.abort, a.status, 501); par_in ^= 1; }
+                    else if (op.wait_src) {
+                        const int c = op.wait_src - 1;
+                        ok = bwait(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 502 + c);
+                        par_ready ^= 1u << c;
+                    }
+                    if (ok && op.wait_empty) {
+                        ok = bwait(&sh.acc_empty[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 510 + op.q);
+                        par_empty ^= 1u << op.q;
+                    }
+                    const uint32_t stage = uc % kBStages, par = (uc / kBStages) & 1;
+                    if (ok) ok = bwait(&sh.w_full[stage], par, &sh.abort, a.status, 520);
+                    if (!ok) break;
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem + kBOffZ + op.a_blk * kUnitBytes;
+                    const uint32_t b_addr = smem + kBOffW + stage * kUnitBytes;
+                    const uint32_t idesc = umma_idesc(128, (uint32_t)op.n8 * 8, kF16, kF16, 0, 0);
+                    const uint32_t d_addr = tmem_base + (uint32_t)op.tmem_col8 * 8;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16(d_addr, umma_desc_kmajor(a_addr, ks), umma_desc_kmajor(b_addr, ks), idesc, !(op.first && ks == 0));
+                    umma_commit(smem_u32(&sh.w_empty[stage]));
+                    if (op.commit) umma_commit(smem_u32(&sh.acc_full[op.q]));
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================= epilogue (128 threads, thread = tile row = TMEM lane) =======================
+        const int row = tid - 128;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
+        const int rsw = row & 7;
+        uint32_t par_full = 0;
+        const bool leader = (row == 0);
+        const float scale = __ldg(a.grad_scale);
+        const float inv_scale = 1.0f / scale;
+        for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
+            const size_t m = (size_t)tile * HN_TILE + row;
+            const float dsr = (__ldg(a.sigma + m) > 0.f) ? __ldg(a.dsigma + m) * scale : 0.f;   // d/d(pre-ReLU density), scaled
+            const uint32_t* mask_row = a.masks + m * HN_MASK_WORDS;
+            for (int e = 0; e < n_epis; ++e) {
+                const EpiOp op = tb.epi[e];
+                bwait(&sh.acc_full[op.q], (par_full >> op.q) & 1, &sh.abort, a.status, 600 + e);
+                par_full ^= 1u << op.q;
+                tc_fence_after_sync();
+                if (op.kind == EPI_GRAD_PE) {
+                    // ---- dL/dPE (64 columns, scaled) -> dL/dpts -> per-ray sums
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8, v0);
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8 + 32, v1);
+                    tmem_ld_wait();
+                    tc_fence_before_sync();
+                    mbar_arrive(smem_u32(&sh.acc_empty[op.q]));
+                    const int ns = a.cam.n_samples;
+                    const size_t ray_idx = m / ns;
+                    const int s = (int)(m % ns), r = (int)(ray_idx % a.cam.n_rays), b = (int)(ray_idx / a.cam.n_rays);
+                    const Ray ray = make_ray(a.cam, b, r);
+                    const float e0 = sample_edge(a.cam, ray.oz, b, r, s), e1 = sample_edge(a.cam, ray.oz, b, r, s + 1);
+                    const float p[3] = {__fadd_rn(ray.ox, __fmul_rn(ray.vx, e0)), __fadd_rn(ray.oy, __fmul_rn(ray.vy, e0)),
+                                        __fadd_rn(ray.oz, __fmul_rn(ray.vz, e0))};
+                    auto G = [&](int c) -> float { return __uint_as_float(c < 32 ? v0[c] : v1[c - 32]); };
+                    float dp[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) dp[d] = G(d);
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+                        const float f = (float)(1 << k);
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            float sn, cs;
+                            sincosf(p[d] * f, &sn, &cs);
+                            dp[d] = fmaf(f, G(3 + 6 * k + d) * cs - G(3 + 6 * k + 3 + d) * sn, dp[d]);
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) dp[d] *= inv_scale;
+                    const float dpv = dp[0] * ray.vx + dp[1] * ray.vy + dp[2] * ray.vz;      // through z_s = o_z - const
+                    float red[7] = {dp[0], dp[1], dp[2] + dpv, e0 * dp[0], e0 * dp[1], e0 * dp[2],
+                                    a.ddelta ? (e1 - e0) * __ldg(a.ddelta + m) : 0.f};
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) red[i] = warp_sum32(red[i]);
+                    if (lane == 0 && a.g_ray_o) {
+                        atomicAdd(a.g_ray_o + ray_idx * 3 + 0, red[0]); atomicAdd(a.g_ray_o + ray_idx * 3 + 1, red[1]);
+                        atomicAdd(a.g_ray_o + ray_idx * 3 + 2, red[2]);
+                        atomicAdd(a.g_ray_v + ray_idx * 3 + 0, red[3]); atomicAdd(a.g_ray_v + ray_idx * 3 + 1, red[4]);
+                        atomicAdd(a.g_ray_v + ray_idx * 3 + 2, red[5]);
+                        atomicAdd(a.g_ray_l + ray_idx, red[6]);
+                    }
+                    continue;
+                }
+                if (saving) { if (leader) bulk_wait_read<1>(); bsync(1, 128); }
+                if (saving && op.kind == EPI_GRAD_DENSITY && op.col0 == 0) {
+                    // density head as a one-channel pseudo layer for the weight pass: row = [dsr, 0, ..., 0]
+                    uint8_t* drow = (uint8_t*)a.grads + ((size_t)HN_GSLOT_DENS * n_tiles + tile) * kUnitBytes + row_off;
+                    const uint32_t first = pack_h2(fminf(fmaxf(dsr, -65504.f), 65504.f), 0.f);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4*>(drow + ((c ^ rsw) << 4)) = make_uint4(c == 0 ? first : 0u, 0u, 0u, 0u);
+                }
+                for (int g = 0; g < op.width32; ++g) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8 + g * 32, v);
+                    tmem_ld_wait();
+                    if (g + 1 == op.width32) { tc_fence_before_sync(); mbar_arrive(smem_u32(&sh.acc_empty[op.q])); }
+                    float y[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]);
+                    if (op.kind == EPI_GRAD_DENSITY) {
+                        const float4* wp = reinterpret_cast<const float4*>(a.w_density + op.col0 + g * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 ww = __ldg(wp + i);
+                            y[4 * i + 0] = fmaf(dsr, ww.x, y[4 * i + 0]); y[4 * i + 1] = fmaf(dsr, ww.y, y[4 * i + 1]);
+                            y[4 * i + 2] = fmaf(dsr, ww.z, y[4 * i + 2]); y[4 * i + 3] = fmaf(dsr, ww.w, y[4 * i + 3]);
+                        }
+                    }
+                    if (op.kind != EPI_GRAD_LINEAR) {
+                        const uint32_t mw = __ldg(mask_row + op.mask_word + g);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) y[i] = ((mw >> i) & 1u) ? y[i] : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) y[i] = fminf(fmaxf(y[i], -65504.f), 65504.f);
+                    const int col = g * 32;
+                    const uint32_t blk_addr = smem + kBOffZ + (op.dst_blk + (col >> 6)) * kUnitBytes + row_off;
+                    const int ch0 = (col & 63) >> 3;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        st_shared_v4(blk_addr + (((ch0 + c) ^ rsw) << 4),
+                                     pack_h2(y[8 * c + 0], y[8 * c + 1]), pack_h2(y[8 * c + 2], y[8 * c + 3]),
+                                     pack_h2(y[8 * c + 4], y[8 * c + 5]), pack_h2(y[8 * c + 6], y[8 * c + 7]));
+                }
+                fence_async_smem();
+                if (saving) {
+                    bsync(1, 128);
+                    if (leader && op.save_blk != 0xFFFF) {
+                        const int nblk = (op.width32 + 1) / 2;
+                        for (int k = 0; k < nblk; ++k)
+                            bulk_s2g((uint8_t*)a.grads + ((size_t)(op.save_blk + k) * n_tiles + tile) * kUnitBytes,
+                                     smem + kBOffZ + (op.dst_blk + k) * kUnitBytes, kUnitBytes);
+                        bulk_commit();
+                    }
+                }
+                if (op.ready_idx != 255) mbar_arrive(smem_u32(&sh.a_ready[op.ready_idx]));
+            }
+            // the tile's gradient buffer may now be overwritten by the next tile's dL/dfeat image
+            if (saving && leader) bulk_wait_read<0>();
+            mbar_arrive(smem_u32(&sh.z_free));
+        }
+        if (saving && leader) bulk_wait_all<0>();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_free<kBTmemCols>(tmem_base);
+}
+
+static std::mutex g_bwd_mu;
+static bool g_bwd_ready[64] = {};
+
+}  // namespace hn
+
+extern "C" int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream) {
+    using namespace hn;
+    if (!a || !a->cam.xy || !a->cam.Rmats || !a->cam.Tvecs || !a->cam.inv_inmats || !a->packed || !a->w_density ||
+        !a->dfeat_image || !a->dsigma || !a->sigma || !a->grad_scale || !a->masks || !a->status)
+        return set_error(HN_E_BADARG, "hn_mlp_bwd_data: null pointer");
+    if (int rc = check_geometry(a->cam.B, a->cam.n_rays, a->cam.n_samples, "hn_mlp_bwd_data")) return rc;
+    const bool with_pe = (a->g_ray_o != nullptr);
+    if (with_pe && (!a->g_ray_v || !a->g_ray_l))
+        return set_error(HN_E_BADARG, "hn_mlp_bwd_data: g_ray_o, g_ray_v and g_ray_l must be given together");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_bwd_mu);
+        if (dev < 64 && !g_bwd_ready[dev]) {
+            const HostSchedules& hs = host_schedules();
+            cudaError_t e = cudaMemcpyToSymbol(c_bwd, &hs.bwd_nope, sizeof(BwdTables), 0);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_bwd, &hs.bwd, sizeof(BwdTables), sizeof(BwdTables));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+            if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+            g_bwd_ready[dev] = true;
+        }
+    }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t M = total_samples(a->cam.B, a->cam.n_rays, a->cam.n_samples);
+    const int n_tiles = (int)(M / HN_TILE);
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    mlp_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, with_pe ? 1 : 0);
+    return check_launch("hn_mlp_bwd_data");
+}

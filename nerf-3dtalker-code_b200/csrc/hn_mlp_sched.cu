@@ -1,0 +1,208 @@
+// hn_mlp_sched.cu — host-side generation of the fused-kernel schedules (see hn_mlp_sched.h).
+#include <cassert>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "hn_mlp_sched.h"
+#include "../../include/headnerf_b200.h"
+
+namespace hn {
+namespace {
+
+struct ChainStep {
+    int w_idx;            // weight tensor
+    bool pe_src;          // forward: a PE K-block precedes the activation K-blocks
+    int n_kb;             // K-blocks read from the activation/gradient buffer
+    int n_out;            // output width routed to 128-column chunks
+    EpiKind kind;
+    int bias_off;         // forward only
+    int save_blk;         // first block of the save slot, -1 = none
+    int mask_word;        // first mask word, -1 = none
+    int w_col0;           // column of the first activation K-block in the weight (forward) / of output col 0 (backward)
+    bool l5_hidden;       // w_col0 is relative to the hidden block of FeaExt_module_5
+    int density;          // forward: 1 = accumulate density head in this step's epilogue
+    bool pe_out;          // backward: an extra 64-wide chunk accumulates dL/dPE
+    bool pe_first;        // backward: that chunk overwrites (first contribution of the tile)
+    bool pe_only;         // backward: step has no regular output (FeaExt_module_0)
+    bool no_consumer;     // no later GEMM reads this step's output from shared memory: do not signal a_ready
+};
+
+struct Builder {
+    std::vector<PackOp> pack;
+    std::vector<MmaOp> mma;
+    std::vector<EpiOp> epi;
+    int qc = 0;
+    int n_acc;            // rotating accumulator chunks (4 forward, 3 backward)
+    bool backward;
+
+    void step(const ChainStep& s, bool first_step) {
+        const int nch = s.pe_only ? 0 : (s.n_out + 127) / 128;
+        std::vector<std::vector<int>> groups;
+        if (s.pe_src) groups.push_back({kPeBlk});
+        for (int c = 0; 2 * c < s.n_kb; ++c) {
+            std::vector<int> g{2 * c};
+            if (2 * c + 1 < s.n_kb) g.push_back(2 * c + 1);
+            groups.push_back(g);
+        }
+        const int G = (int)groups.size();
+        const int n_agroups = G - (s.pe_src ? 1 : 0);
+        std::vector<int> q_of(nch);
+        for (int j = 0; j < nch; ++j) q_of[j] = (qc + j) % n_acc;
+        // in-place rule: the chunk that overwrites the K-blocks of the LAST group must complete last
+        std::vector<int> last_order;
+        for (int j = 0; j < nch; ++j) if (j != n_agroups - 1) last_order.push_back(j);
+        if (n_agroups - 1 < nch && n_agroups >= 1) last_order.push_back(n_agroups - 1);
+        std::vector<int> nat_order;
+        for (int j = 0; j < nch; ++j) nat_order.push_back(j);
+
+        for (int g = 0; g < G; ++g) {
+            const bool is_pe_group = s.pe_src && g == 0;
+            // chunk list of this K-group: the dL/dPE chunk (-1) goes FIRST so that no MMA still reads the
+            // group's K-blocks after the regular chunk that overwrites them has been committed
+            std::vector<int> chunks;
+            if (s.pe_out) chunks.push_back(-1);
+            for (int j : ((g == G - 1) ? last_order : nat_order)) chunks.push_back(j);
+            for (size_t ci = 0; ci < chunks.size(); ++ci) {
+                const int j = chunks[ci];
+                const bool pe_chunk = (j < 0);
+                for (size_t kk = 0; kk < groups[g].size(); ++kk) {
+                    const int blk = groups[g][kk];
+                    const int width = pe_chunk ? 64 : std::min(128, s.n_out - 128 * j);
+                    MmaOp m{};
+                    m.a_blk = (uint8_t)blk;
+                    m.n8 = (uint8_t)(width / 8);
+                    m.tmem_col8 = (uint8_t)((pe_chunk ? 384 : q_of[j] * 128) / 8);
+                    m.q = (uint8_t)(pe_chunk ? 3 : q_of[j]);
+                    const bool first_k = (g == 0 && kk == 0);
+                    m.first = pe_chunk ? (uint8_t)(s.pe_first && first_k) : (uint8_t)first_k;
+                    m.wait_empty = pe_chunk ? (uint8_t)(s.pe_first && first_k) : (uint8_t)first_k;
+                    m.commit = (uint8_t)(g == G - 1 && kk + 1 == groups[g].size() && (!pe_chunk || s.pe_only));
+                    // source readiness is waited for once, on the first unit that touches the group
+                    if (ci == 0 && kk == 0) {
+                        if (is_pe_group) m.wait_src = first_step ? 4 : 0;
+                        else if (first_step && backward) m.wait_src = (g == 0) ? 5 : 0;
+                        else m.wait_src = (uint8_t)(1 + blk / 2);
+                    }
+                    mma.push_back(m);
+
+                    PackOp p{};
+                    p.w_idx = (int8_t)s.w_idx;
+                    p.l5_hidden = (int8_t)s.l5_hidden;
+                    if (!backward) {
+                        p.transposed = 0;
+                        p.row0 = (int16_t)(128 * j);
+                        p.valid_r = (int16_t)width;
+                        if (blk == kPeBlk) { p.col0 = 0; p.valid_c = HN_PE; p.l5_hidden = 0; }
+                        else { p.col0 = (int16_t)(s.w_col0 + 64 * blk); p.valid_c = 64; }
+                    } else {
+                        p.transposed = 1;                       // unit(r,c) = W[(row0+c)*ld + col0 + r]
+                        p.row0 = (int16_t)(64 * blk);           // contraction index = layer output channel
+                        p.valid_c = 64;
+                        if (pe_chunk) { p.col0 = 0; p.valid_r = HN_PE; p.l5_hidden = 0; }
+                        else { p.col0 = (int16_t)(s.w_col0 + 128 * j); p.valid_r = (int16_t)width; }
+                    }
+                    pack.push_back(p);
+                }
+            }
+        }
+        // epilogue ops in completion order
+        for (int j : last_order) {
+            EpiOp e{};
+            e.q = (uint8_t)q_of[j];
+            e.tmem_col8 = (uint8_t)(q_of[j] * 128 / 8);
+            e.width32 = (uint8_t)(std::min(128, s.n_out - 128 * j) / 32);
+            e.kind = s.kind;
+            e.dst_blk = (uint8_t)(2 * j);
+            e.ready_idx = (s.kind == EPI_FEAT || s.no_consumer) ? 255 : (uint8_t)j;
+            e.density = (uint8_t)(s.density ? (j == nch - 1 ? 2 : 1) : 0);
+            e.bias_off = (uint16_t)(s.bias_off + 128 * j);
+            e.col0 = (uint16_t)(128 * j);
+            e.save_blk = s.save_blk < 0 ? 0xFFFF : (uint16_t)(s.save_blk + 2 * j);
+            e.mask_word = s.mask_word < 0 ? 0xFFFF : (uint16_t)(s.mask_word + 4 * j);
+            epi.push_back(e);
+        }
+        if (s.pe_only) {
+            EpiOp e{};
+            e.q = 3; e.tmem_col8 = 384 / 8; e.width32 = 2; e.kind = EPI_GRAD_PE; e.ready_idx = 255;
+            e.save_blk = 0xFFFF; e.mask_word = 0xFFFF;
+            epi.push_back(e);
+        }
+        qc += nch;
+    }
+};
+
+HostSchedules* build() {
+    auto* hs = new HostSchedules();
+    memset(hs, 0, sizeof(*hs));
+    {   // ---- forward chain: NetWorks/models.py:69-82
+        Builder b; b.n_acc = 4; b.backward = false;
+        for (int l = 0; l < 8; ++l) {
+            ChainStep s{};
+            s.w_idx = l; s.pe_src = (l == 0 || l == 5); s.n_kb = (l == 0) ? 0 : 6; s.n_out = HN_HIDDEN;
+            s.kind = EPI_HIDDEN; s.bias_off = l * HN_HIDDEN; s.save_blk = HN_SLOT_H0 + 6 * l; s.mask_word = 12 * l;
+            s.w_col0 = 0; s.l5_hidden = (l == 5); s.density = (l == 7);
+            b.step(s, l == 0);
+        }
+        ChainStep r0{}; r0.w_idx = W_R0; r0.n_kb = 6; r0.n_out = HN_HIDDEN; r0.kind = EPI_LINEAR; r0.bias_off = HN_BIAS_OFF_R0;
+        r0.save_blk = HN_SLOT_R0; r0.mask_word = -1; b.step(r0, false);
+        ChainStep r1{}; r1.w_idx = W_R1; r1.n_kb = 6; r1.n_out = HN_RGB1; r1.kind = EPI_HIDDEN; r1.bias_off = HN_BIAS_OFF_R1;
+        r1.save_blk = HN_SLOT_X; r1.mask_word = 96; b.step(r1, false);
+        ChainStep r2{}; r2.w_idx = W_R2; r2.n_kb = 3; r2.n_out = HN_FEAT; r2.kind = EPI_FEAT; r2.bias_off = HN_BIAS_OFF_R2;
+        r2.save_blk = -1; r2.mask_word = -1; b.step(r2, false);
+        assert((int)b.mma.size() == kFwdUnits && (int)b.epi.size() == kFwdEpis);
+        for (size_t u = 0; u < b.mma.size(); ++u) b.mma[u].unit = (uint16_t)u;
+        memcpy(hs->fwd_pack, b.pack.data(), sizeof(PackOp) * kFwdUnits);
+        memcpy(hs->fwd.mma, b.mma.data(), sizeof(MmaOp) * kFwdUnits);
+        memcpy(hs->fwd.epi, b.epi.data(), sizeof(EpiOp) * kFwdEpis);
+    }
+    for (int with_pe = 1; with_pe >= 0; --with_pe) {
+        // ---- data-gradient chain (reverse order); dL/dPE accumulated at FeaExt_module_5 and _0
+        Builder b; b.n_acc = 3; b.backward = true;
+        ChainStep r2{}; r2.w_idx = W_R2; r2.n_kb = 4; r2.n_out = HN_RGB1; r2.kind = EPI_GRAD_MASK; r2.save_blk = HN_GSLOT_R1;
+        r2.mask_word = 96; b.step(r2, true);
+        ChainStep r1{}; r1.w_idx = W_R1; r1.n_kb = 3; r1.n_out = HN_HIDDEN; r1.kind = EPI_GRAD_LINEAR; r1.save_blk = HN_GSLOT_R0;
+        r1.mask_word = -1; b.step(r1, false);
+        ChainStep r0{}; r0.w_idx = W_R0; r0.n_kb = 6; r0.n_out = HN_HIDDEN; r0.kind = EPI_GRAD_DENSITY;
+        r0.save_blk = HN_GSLOT_Z0 + 6 * 7; r0.mask_word = 12 * 7; b.step(r0, false);
+        for (int l = 7; l >= 1; --l) {
+            ChainStep s{};
+            s.w_idx = l; s.n_kb = 6; s.n_out = HN_HIDDEN; s.kind = EPI_GRAD_MASK;
+            s.save_blk = HN_GSLOT_Z0 + 6 * (l - 1); s.mask_word = 12 * (l - 1);
+            s.l5_hidden = (l == 5); s.pe_out = (l == 5) && with_pe; s.pe_first = s.pe_out;
+            s.no_consumer = (l == 1) && !with_pe;
+            b.step(s, false);
+        }
+        if (with_pe) {
+            ChainStep l0{}; l0.w_idx = W_L0; l0.n_kb = 6; l0.n_out = 0; l0.pe_out = true; l0.pe_only = true; l0.kind = EPI_GRAD_PE;
+            l0.save_blk = -1; l0.mask_word = -1; b.step(l0, false);
+        }
+        assert((int)b.mma.size() <= kBwdUnitsMax && (int)b.epi.size() <= kBwdEpisMax);
+        BwdTables& t = with_pe ? hs->bwd : hs->bwd_nope;
+        t.n_units = (int)b.mma.size();
+        t.n_epis = (int)b.epi.size();
+        if (with_pe) {
+            memcpy(hs->bwd_pack, b.pack.data(), sizeof(PackOp) * b.pack.size());
+            for (size_t u = 0; u < b.mma.size(); ++u) b.mma[u].unit = (uint16_t)u;
+        } else {
+            for (size_t u = 0; u < b.mma.size(); ++u) {
+                int found = -1;
+                for (int v = 0; v < hs->bwd.n_units; ++v)
+                    if (!memcmp(&hs->bwd_pack[v], &b.pack[u], sizeof(PackOp))) { found = v; break; }
+                assert(found >= 0);
+                b.mma[u].unit = (uint16_t)found;
+            }
+        }
+        memcpy(t.mma, b.mma.data(), sizeof(MmaOp) * b.mma.size());
+        memcpy(t.epi, b.epi.data(), sizeof(EpiOp) * b.epi.size());
+    }
+    return hs;
+}
+
+}  // namespace
+
+const HostSchedules& host_schedules() {
+    static HostSchedules* hs = build();
+    return *hs;
+}
+
+}  // namespace hn

@@ -1,0 +1,87 @@
+// hn_mlp_sched.h — static schedules of the fused MLP kernels.
+//
+// Every fused kernel (forward chain, data-gradient chain) is an interpreter of three small tables that
+// are generated ONCE on the host from the layer list below and kept in __constant__ memory:
+//   PackOp : which slice of which fp32 state-dict weight goes into weight unit u (16 KiB operand image)
+//   MmaOp  : for weight unit u, in stream order: A-operand block, accumulator, barriers to wait/commit
+//   EpiOp  : for every accumulator chunk, in completion order: bias, activation, destination
+// The weight producer, the MMA issuer and the epilogue warps all walk the same tables, so the three
+// roles cannot drift apart.  fg_CD_predictor layer list: NetWorks/models.py:29-59, forward :62-87.
+#pragma once
+#include <stdint.h>
+
+namespace hn {
+
+// indices into hn_weights_t.w / hn_mlp_bwd_weights_t.dw
+enum { W_L0 = 0, W_L5 = 5, W_L7 = 7, W_DENSITY = 8, W_R0 = 9, W_R1 = 10, W_R2 = 11 };
+
+constexpr int kPeBlk = 6;          // A-operand block id of the positional-encoding block (0..5: activation buffer)
+constexpr int kUnitBytes = 16384;
+
+struct PackOp {                    // unit(r,c) = W[w_idx][(row0 + (T? c : r)) * ld + col0 + (T? r : c)]
+    int8_t w_idx;
+    int8_t transposed;             // data-gradient units hold W^T
+    int8_t l5_hidden;              // add the runtime column of the hidden block of FeaExt_module_5
+    int8_t pad;
+    int16_t row0, col0;
+    int16_t valid_r, valid_c;      // rows/cols of the unit backed by weights (rest is zero)
+};
+
+struct MmaOp {
+    uint8_t a_blk;                 // A operand block (0..5 activation buffer, 6 = PE block)
+    uint8_t n8;                    // MMA N / 8
+    uint8_t tmem_col8;             // accumulator column / 8
+    uint8_t q;                     // accumulator barrier index
+    uint8_t first;                 // 1: overwrite accumulator (first K block of this chunk)
+    uint8_t commit;                // 1: accumulator chunk complete after this unit -> acc_full[q]
+    uint8_t wait_src;              // 0 none, 1..3 a_ready[c-1], 4 pe_ready, 5 in_ready (bwd: input image landed)
+    uint8_t wait_empty;            // 1: wait acc_empty[q] before this unit
+    uint16_t unit;                 // index of the weight unit inside its packed stream
+    uint16_t pad;
+};
+
+enum EpiKind : uint8_t {
+    EPI_HIDDEN = 0,                // y = relu(acc + bias)            -> activation buffer
+    EPI_LINEAR = 1,                // y = acc + bias                  -> activation buffer
+    EPI_FEAT = 2,                  // y = acc + bias                  -> global feat
+    // data-gradient kernel
+    EPI_GRAD_MASK = 3,             // y = acc * relu_mask             -> gradient buffer
+    EPI_GRAD_LINEAR = 4,           // y = acc                         -> gradient buffer
+    EPI_GRAD_DENSITY = 5,          // y = (acc + dsigma*w_density) * relu_mask
+    EPI_GRAD_PE = 6,               // positional-encoding gradient    -> per-ray camera gradients
+};
+
+struct EpiOp {
+    uint8_t q;
+    uint8_t tmem_col8;
+    uint8_t width32;               // columns / 32
+    uint8_t kind;
+    uint8_t dst_blk;               // first activation-buffer block written
+    uint8_t ready_idx;             // a_ready barrier to arrive on, 255 = none
+    uint8_t density;               // fwd: 1 accumulate density dot, 2 = also finish it (last chunk of FeaExt_module_7)
+    uint8_t pad;
+    uint16_t bias_off;             // fwd: offset in the per-item bias row ; bwd: unused
+    uint16_t col0;                 // first logical output column of this chunk
+    uint16_t save_blk;             // first block of the save slot (act / grads buffer), 0xFFFF = none
+    uint16_t mask_word;            // word offset in the per-sample mask row, 0xFFFF = none
+};
+
+constexpr int kFwdUnits = 168;
+constexpr int kFwdEpis = 31;
+constexpr int kBwdUnitsMax = 176;
+constexpr int kBwdEpisMax = 36;
+
+struct FwdTables { MmaOp mma[kFwdUnits]; EpiOp epi[kFwdEpis]; };
+struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_units; int n_epis; };
+
+struct HostSchedules {
+    PackOp fwd_pack[kFwdUnits];
+    FwdTables fwd;
+    PackOp bwd_pack[kBwdUnitsMax];
+    BwdTables bwd;                 // full data-gradient chain incl. dL/dPE (camera gradients)
+    BwdTables bwd_nope;            // same without the dL/dPE chunks; `unit` still indexes the full stream
+};
+
+const HostSchedules& host_schedules();   // built on first use (hn_mlp_sched.cpp part of hn_mlp_pack.cu)
+
+}  // namespace hn

@@ -1,0 +1,296 @@
+// hn_mlp_wgrad.cu — weight gradients of fg_CD_predictor: dW_l = sum over samples of dZ_l^T x X_l, where dZ_l are
+// the (loss-scaled, fp16) pre-activation gradients saved by hn_mlp_bwd_data and X_l the layer inputs saved by
+// hn_mlp_fwd — both already stored as tensor-core operand images, consumed here as MN-major operands
+// (contraction over the 128 sample rows of a block), so nothing is transposed or re-laid-out.
+//
+// Work item = (layer, 128-channel chunk of dZ, batch item, sample split).  A CTA accumulates the item's
+// [128 x K_in] slice of dW in TMEM over all its tiles, plus a 16-column "ones" product that yields the
+// bias gradient (= per-item column sums of dZ, from which the host derives the latent-code and folded
+// weight-column gradients), then flushes once with atomic adds.  The density head rides along as a
+// one-channel pseudo layer (its gradient block is written by hn_mlp_bwd_data).
+#include <mutex>
+#include <vector>
+#include "hn_api.h"
+#include "hn_mlp_sched.h"
+#include "hn_tc.cuh"
+
+namespace hn {
+
+constexpr int kWStages = 3;
+constexpr int kHalfBytes = kUnitBytes / 2;                  // 64 sample rows of a block
+constexpr int kWMaxX = 7;
+constexpr uint32_t kWStageBytes = (2 + kWMaxX) * kHalfBytes;  // 72 KiB
+constexpr uint32_t kWOffOnes = kWStages * kWStageBytes;
+constexpr uint32_t kWgradSmem = kWOffOnes + 2048 + 1024;
+constexpr int kWThreads = 192;                              // warp 0 producer, warp 1 MMA (+TMEM alloc), warps 2..5 flush
+constexpr uint32_t kBiasCol = 448;
+
+struct WItem {
+    int16_t w_idx;            // destination weight (index into dw[]), -1: none
+    int16_t row0;             // first dW row of this chunk
+    int16_t rows;             // valid rows (128, 64 or 1)
+    int16_t n_x;              // number of X blocks (0: bias-only item)
+    int32_t g_blk;            // first block of the dZ chunk (in grads, or in dfeat_image when g_dfeat)
+    int16_t g_dfeat;
+    int16_t bias_off;         // offset in the bias row, -1: none
+    int32_t x_blk[kWMaxX];    // act block ids
+    int16_t x_col[kWMaxX];    // dW column of the block's first column
+    int16_t x_valid[kWMaxX];  // valid columns (64, or 63 for the PE block)
+    int32_t b;                // batch item
+    int32_t tile0, tile1;     // tile range [tile0, tile1)
+};
+
+struct WShared {
+    uint64_t full[kWStages], empty[kWStages], acc_full, acc_empty;
+    uint32_t tmem_base;
+    volatile int abort;
+};
+
+__device__ __forceinline__ bool wwait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
+    const uint32_t b = smem_u32(bar);
+    if (mbar_try_wait(b, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(b, parity)) {
+        if (*abort_flag) return false;
+        if (clock64() - t0 > 2000000000ll) { *abort_flag = 1; atomicCAS(status, 0, code); return false; }
+    }
+    return true;
+}
+
+struct WArgs {
+    const uint8_t* act; const uint8_t* grads; const uint8_t* dfeat_image;
+    const float* grad_scale;
+    float* dw[12]; int ld[12];
+    float* dbias;
+    const WItem* items; int n_items; int n_tiles;
+    int* status;
+};
+
+__global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ WShared sh;
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < kWStages; ++i) { mbar_init(smem_u32(&sh.full[i]), 1); mbar_init(smem_u32(&sh.empty[i]), 1); }
+        mbar_init(smem_u32(&sh.acc_full), 1);
+        mbar_init(smem_u32(&sh.acc_empty), 128);
+        sh.abort = 0;
+        mbar_fence_init();
+    }
+    // "ones" operand: 16 rows x 64 samples of 1.0h (K-major image; every element equal, so swizzling is moot)
+    for (int i = tid; i < 2048 / 4; i += kWThreads)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem + kWOffOnes + i * 4), "r"(0x3C003C00u) : "memory");
+    fence_async_smem();
+    if (warp == 1) tmem_alloc<512>(smem_u32(&sh.tmem_base));
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = sh.tmem_base;
+
+    if (warp == 0) {
+        // ======================= producer =======================
+        if (lane == 0) {
+            uint32_t sc = 0;
+            for (int it = blockIdx.x; it < a.n_items && !sh.abort; it += gridDim.x) {
+                const WItem w = a.items[it];
+                const uint8_t* gsrc = w.g_dfeat ? a.dfeat_image : a.grads;
+                const uint32_t bytes = (2 + w.n_x) * kHalfBytes;
+                for (int tile = w.tile0; tile < w.tile1; ++tile) {
+                    for (int half = 0; half < 2; ++half, ++sc) {
+                        const uint32_t stage = sc % kWStages, par = (sc / kWStages) & 1;
+                        if (!wwait(&sh.empty[stage], par ^ 1, &sh.abort, a.status, 701)) break;
+                        const uint32_t fb = smem_u32(&sh.full[stage]);
+                        mbar_arrive_expect_tx(fb, bytes);
+                        const uint32_t dst = smem + stage * kWStageBytes;
+                        for (int k = 0; k < 2; ++k)
+                            bulk_g2s(dst + k * kHalfBytes, gsrc + ((size_t)(w.g_blk + k) * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
+                        for (int k = 0; k < w.n_x; ++k)
+                            bulk_g2s(dst + (2 + k) * kHalfBytes, a.act + ((size_t)w.x_blk[k] * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            uint32_t sc = 0, n_item = 0;
+            const uint32_t idesc_bias = umma_idesc(128, 16, kF16, kF16, 1, 0);
+            for (int it = blockIdx.x; it < a.n_items && !sh.abort; it += gridDim.x, ++n_item) {
+                const WItem w = a.items[it];
+                bool ok = wwait(&sh.acc_empty, (n_item & 1) ^ 1, &sh.abort, a.status, 710);
+                bool first = true;
+                for (int tile = w.tile0; tile < w.tile1 && ok; ++tile) {
+                    for (int half = 0; half < 2; ++half, ++sc) {
+                        const uint32_t stage = sc % kWStages, par = (sc / kWStages) & 1;
+                        ok = wwait(&sh.full[stage], par, &sh.abort, a.status, 711);
+                        if (!ok) break;
+                        tc_fence_after_sync();
+                        const uint32_t g_addr = smem + stage * kWStageBytes;
+                        const uint32_t x_addr = g_addr + 2 * kHalfBytes;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t ad = umma_desc_mnmajor(g_addr, ks, kHalfBytes);
+                            for (int x0 = 0; x0 < w.n_x; x0 += 4) {
+                                const int nb = min(4, w.n_x - x0);
+                                umma_f16(tmem_base + x0 * 64, ad, umma_desc_mnmajor(x_addr + x0 * kHalfBytes, ks, kHalfBytes),
+                                         umma_idesc(128, nb * 64, kF16, kF16, 1, 1), !(first && ks == 0));
+                            }
+                            umma_f16(tmem_base + kBiasCol, ad, umma_desc_kmajor(smem + kWOffOnes, ks), idesc_bias, !(first && ks == 0));
+                        }
+                        first = false;
+                        umma_commit(smem_u32(&sh.empty[stage]));
+                    }
+                }
+                umma_commit(smem_u32(&sh.acc_full));
+            }
+        }
+    } else {
+        // ======================= flush: TMEM -> atomic adds into dW / dbias =======================
+        const int row = (warp & 3) * 32 + lane;                    // TMEM lane (a warp may only read its own quarter) = dW row in the chunk
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const float inv_scale = 1.0f / __ldg(a.grad_scale);
+        uint32_t n_item = 0;
+        for (int it = blockIdx.x; it < a.n_items && !sh.abort; it += gridDim.x, ++n_item) {
+            const WItem w = a.items[it];
+            wwait(&sh.acc_full, n_item & 1, &sh.abort, a.status, 720);
+            tc_fence_after_sync();
+            const bool row_ok = row < w.rows;
+            for (int k = 0; k < w.n_x; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + k * 64 + h * 32, v);
+                    tmem_ld_wait();
+                    if (row_ok && w.w_idx >= 0 && a.dw[w.w_idx]) {
+                        float* dst = a.dw[w.w_idx] + (size_t)(w.row0 + row) * a.ld[w.w_idx] + w.x_col[k] + h * 32;
+                        const int nvalid = w.x_valid[k] - h * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) atomicAdd(dst + i, __uint_as_float(v[i]) * inv_scale);
+                    }
+                }
+            }
+            {
+                uint32_t v[32];                                   // bias columns (all 16 equal); x32 load stays inside the 512 columns
+                tmem_ld32(tmem_base + lane_base + kBiasCol, v);
+                tmem_ld_wait();
+                if (row_ok && w.bias_off >= 0 && a.dbias)
+                    atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + w.bias_off + row, __uint_as_float(v[0]) * inv_scale);
+            }
+            tc_fence_before_sync();
+            mbar_arrive(smem_u32(&sh.acc_empty));
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_free<512>(tmem_base);
+}
+
+static std::mutex g_w_mu;
+static bool g_w_ready[64] = {};
+
+// host: enumerate work items
+static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, std::vector<WItem>& items) {
+    const int tiles_per_item = (int)(((int64_t)a.n_rays * a.n_samples) / HN_TILE);
+    const bool want_w = false || [&] { for (int i = 0; i < 12; ++i) if (a.dw[i]) return true; return false; }();
+    struct LayerW { int w_idx; int n_out; int g_blk; int g_dfeat; int bias_off; int x_slot; int n_xblk; bool pe; int x_col0; };
+    std::vector<LayerW> layers;
+    for (int l = 0; l < 8; ++l) {
+        LayerW L{l, HN_HIDDEN, HN_GSLOT_Z0 + 6 * l, 0, l * HN_HIDDEN, l == 0 ? -1 : HN_SLOT_H0 + 6 * (l - 1), l == 0 ? 0 : 6,
+                 l == 0 || l == 5, l == 5 ? a.l5_hidden_col : 0};
+        layers.push_back(L);
+    }
+    layers.push_back({W_R0, HN_HIDDEN, HN_GSLOT_R0, 0, HN_BIAS_OFF_R0, HN_SLOT_H0 + 6 * 7, 6, false, 0});
+    layers.push_back({W_R1, HN_RGB1, HN_GSLOT_R1, 0, HN_BIAS_OFF_R1, HN_SLOT_R0, 6, false, 0});
+    layers.push_back({W_R2, HN_FEAT, 0, 1, HN_BIAS_OFF_R2, HN_SLOT_X, 3, false, 0});
+    layers.push_back({W_DENSITY, 1, HN_GSLOT_R1 + 3, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});   // density pseudo layer
+    // how many (layer, chunk) pairs are active -> choose splits so that there are ~2 items per SM
+    int pairs = 0;
+    for (const LayerW& L : layers) {
+        const bool folded = (L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1);
+        if (!want_w && !folded) continue;
+        pairs += (L.n_out + 127) / 128;
+    }
+    if (pairs == 0) return;
+    int splits = (2 * n_sm + pairs * a.B - 1) / (pairs * a.B);
+    if (splits < 1) splits = 1;
+    if (splits > tiles_per_item) splits = tiles_per_item;
+    for (const LayerW& L : layers) {
+        const bool folded = (L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1);
+        if (!want_w && !folded) continue;
+        for (int j = 0; j * 128 < L.n_out; ++j) {
+            for (int b = 0; b < a.B; ++b) {
+                for (int sp = 0; sp < splits; ++sp) {
+                    WItem w{};
+                    w.w_idx = (int16_t)((want_w && a.dw[L.w_idx]) ? L.w_idx : -1);
+                    w.row0 = (int16_t)(128 * j);
+                    w.rows = (int16_t)std::min(128, L.n_out - 128 * j);
+                    w.g_blk = L.g_blk + 2 * j;
+                    w.g_dfeat = (int16_t)L.g_dfeat;
+                    w.bias_off = (int16_t)(L.bias_off + 128 * j);
+                    w.b = b;
+                    w.tile0 = b * tiles_per_item + (int)((int64_t)tiles_per_item * sp / splits);
+                    w.tile1 = b * tiles_per_item + (int)((int64_t)tiles_per_item * (sp + 1) / splits);
+                    int n = 0;
+                    if (w.w_idx >= 0) {
+                        for (int k = 0; k < L.n_xblk; ++k) { w.x_blk[n] = L.x_slot + k; w.x_col[n] = (int16_t)(L.x_col0 + 64 * k); w.x_valid[n] = 64; ++n; }
+                        if (L.pe) { w.x_blk[n] = HN_SLOT_PE; w.x_col[n] = 0; w.x_valid[n] = HN_PE; ++n; }
+                    }
+                    w.n_x = (int16_t)n;
+                    if (w.tile1 > w.tile0) items.push_back(w);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace hn
+
+extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
+    using namespace hn;
+    if (!a || !a->act || !a->grads || !a->dfeat_image || !a->grad_scale || !a->status)
+        return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: null pointer");
+    if (int rc = check_geometry(a->B, a->n_rays, a->n_samples, "hn_mlp_bwd_weights")) return rc;
+    if (!a->items_workspace || a->items_workspace_bytes < hn_wgrad_workspace_bytes(a->B))
+        return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: items workspace missing or too small (hn_wgrad_workspace_bytes)");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_w_mu);
+        if (dev < 64 && !g_w_ready[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
+            if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+            g_w_ready[dev] = true;
+        }
+    }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    std::vector<WItem> items;
+    build_items(*a, n_sm, items);
+    if (items.empty()) return HN_OK;
+    if (items.size() * sizeof(WItem) > a->items_workspace_bytes)
+        return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: items workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the item table is tiny (<100 KiB); pageable -> device copy is stream-ordered and returns after staging
+    cudaError_t e = cudaMemcpyAsync(a->items_workspace, items.data(), items.size() * sizeof(WItem), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+    WArgs k{};
+    k.act = (const uint8_t*)a->act; k.grads = (const uint8_t*)a->grads; k.dfeat_image = (const uint8_t*)a->dfeat_image;
+    k.grad_scale = a->grad_scale;
+    for (int i = 0; i < 12; ++i) { k.dw[i] = a->dw[i]; k.ld[i] = a->ld[i]; }
+    k.dbias = a->dbias;
+    k.items = (const WItem*)a->items_workspace; k.n_items = (int)items.size();
+    k.n_tiles = (int)(total_samples(a->B, a->n_rays, a->n_samples) / HN_TILE);
+    k.status = a->status;
+    const int grid = k.n_items < n_sm ? k.n_items : n_sm;
+    mlp_wgrad_kernel<<<grid, kWThreads, kWgradSmem, st>>>(k);
+    return check_launch("hn_mlp_bwd_weights");
+}
+
+extern "C" size_t hn_wgrad_workspace_bytes(int B) {
+    // upper bound: 35 (layer, chunk) pairs x B x splits, splits chosen so that items <= 2*SMs + pairs*B
+    return (size_t)(35 * (size_t)(B > 0 ? B : 1) + 2 * 160 + 64) * 2 * sizeof(hn::WItem);
+}

@@ -1,0 +1,168 @@
+"""HeadNeRFNet — drop-in for the reference's NetWorks/HeadNeRFNet.py:10-207.
+
+Same constructor, same forward signature, same state-dict keys/shapes (`fg_CD_predictor.*`,
+`neural_render.*`), same seeded initialisation; the rendering hot path (sampling -> positional encoding ->
+fg_CD_predictor -> compositing) runs in libheadnerf_b200.so instead of eager torch ops.  The latent codes
+(shape/expression(+gaze), audio style, appearance) never get broadcast to [B,C,N_r,N_s] (HeadNeRFNet.py:149-152):
+their weight columns are folded into one effective bias row per batch item (three tiny matmuls that stay in
+autograd, so code gradients and the latent weight-column gradients come from the kernel's bias gradient)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+from .neural_renderer import NeuralRenderer
+from .options import BaseOptions
+
+
+class MLPforNeRF(nn.Module):
+    """Parameter container with the reference's layer names and init (NetWorks/models.py:29-59).
+    All layers are 1x1 convolutions = per-sample linear maps; weights stay fp32 [out,in,1,1]."""
+
+    def __init__(self, vp_channels, vd_channels, n_layers=8, h_channel=256, res_nfeat=3):
+        super().__init__()
+        self.vp_channels, self.vd_channels, self.n_layers = vp_channels, vd_channels, n_layers
+        self.h_channel, self.res_nfeat, self.skips = h_channel, res_nfeat, [n_layers // 2]
+
+        def conv(cin, cout, xavier):
+            m = nn.Conv2d(cin, cout, kernel_size=1, stride=1, padding=0)
+            if xavier:
+                nn.init.xavier_uniform_(m.weight.data)
+            return m
+
+        self.add_module("FeaExt_module_0", conv(vp_channels + 64, h_channel, False))
+        for i in range(n_layers - 1):
+            cin = h_channel + vp_channels if i in self.skips else h_channel
+            self.add_module("FeaExt_module_%d" % (i + 1), conv(cin, h_channel, True))
+        self.add_module("density_module", conv(h_channel, 1, True))
+        self.density_module.bias.data[:] = 0.0
+        self.add_module("RGB_layer_0", conv(h_channel, h_channel, True))
+        self.add_module("RGB_layer_1", conv(h_channel + vd_channels, h_channel // 2, False))
+        self.add_module("RGB_layer_2", conv(h_channel // 2, res_nfeat, False))
+
+    def layers(self):
+        names = ["FeaExt_module_%d" % i for i in range(8)] + ["density_module", "RGB_layer_0", "RGB_layer_1", "RGB_layer_2"]
+        return [self._modules[n] for n in names]
+
+    def forward(self, *a, **k):
+        raise RuntimeError("fg_CD_predictor runs inside the fused CUDA render operator; call HeadNeRFNet.forward")
+
+
+class HeadNeRFNet(nn.Module):
+    def __init__(self, opt: BaseOptions, include_vd, hier_sampling, include_gaze=False, eye_gaze_dim=2) -> None:
+        super().__init__()
+        if include_vd:
+            raise NotImplementedError("include_vd=True (view-direction embedding) is not part of the accelerated path; "
+                                      "every caller in the reference passes False (talker_trainer.py:693,699)")
+        if hier_sampling:
+            raise NotImplementedError("hier_sampling=True is dead code in the reference (HeadNeRFNet.py:182-185 passes the "
+                                      "wrong argument count); not supported")
+        self.hier_sampling, self.include_vd = hier_sampling, include_vd
+        self.include_gaze, self.eye_gaze_dim = include_gaze, eye_gaze_dim
+        self.opt = opt
+        self.num_sample_coarse = opt.num_sample_coarse
+        self.mlp_h_channel = opt.mlp_hidden_nchannels
+        self.featmap_size, self.featmap_nc, self.pred_img_size = opt.featmap_size, opt.featmap_nc, opt.pred_img_size
+        if self.mlp_h_channel != L.HIDDEN or self.featmap_nc != L.FEAT:
+            raise NotImplementedError(f"the sm_100a kernels are specialised for mlp_hidden_nchannels={L.HIDDEN}, "
+                                      f"featmap_nc={L.FEAT} (all shipped HeadNeRF checkpoints)")
+        self.vp_n_freqs = 10
+        shape_dims = opt.iden_code_dims + opt.expr_code_dims + (eye_gaze_dim if include_gaze else 0)
+        vp_channels = shape_dims + self.vp_n_freqs * 6 + 3
+        vd_channels = opt.text_code_dims + opt.illu_code_dims
+        self.shape_dims, self.appea_dims = shape_dims, vd_channels
+        self.fg_CD_predictor = MLPforNeRF(vp_channels=vp_channels, vd_channels=vd_channels,
+                                          h_channel=self.mlp_h_channel, res_nfeat=self.featmap_nc)
+        self.neural_render = NeuralRenderer(bg_type=opt.bg_type, feat_nc=self.featmap_nc, out_dim=3, final_actvn=True,
+                                            min_feat=32, featmap_size=self.featmap_size, img_size=self.pred_img_size)
+        self._packed = None
+        self._packed_key = None
+        self.last_meta = None
+
+    # ------------------------------------------------------------------ weights -> kernel operands
+    def _packed_weights(self):
+        ws = [m.weight for m in self.fg_CD_predictor.layers()]
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if self._packed is None or key != self._packed_key:
+            self._packed = ops.pack_weights(ws, L.PE + self.shape_dims, out=self._packed)
+            self._packed_key = key
+        return ws, self._packed
+
+    def _fold_biases(self, shape_code, appea_code, audiostyle):
+        """Effective bias row per batch item: [B, HN_BIAS_STRIDE]."""
+        fg = self.fg_CD_predictor
+        B, S, H = shape_code.shape[0], self.shape_dims, L.HIDDEN
+        lay = fg.layers()
+        w0 = lay[0].weight.flatten(1)
+        w5 = lay[5].weight.flatten(1)
+        wr1 = lay[10].weight.flatten(1)
+        rows = []
+        for i in range(8):
+            b = lay[i].bias.unsqueeze(0).expand(B, H)
+            if i == 0:
+                b = b + F.linear(shape_code, w0[:, L.PE:L.PE + S]) + F.linear(audiostyle, w0[:, L.PE + S:L.PE + S + 64])
+            elif i == 5:
+                b = b + F.linear(shape_code, w5[:, L.PE:L.PE + S])
+            rows.append(b)
+        rows.append(lay[9].bias.unsqueeze(0).expand(B, H))
+        rows.append(lay[10].bias.unsqueeze(0) + F.linear(appea_code, wr1[:, H:]))
+        rows.append(lay[11].bias.unsqueeze(0).expand(B, L.FEAT))
+        rows.append(lay[8].bias.unsqueeze(0).expand(B, 1))
+        rows.append(shape_code.new_zeros(B, L.BIAS_STRIDE - L.BIAS_OFF_DENSITY - 1))
+        return torch.cat(rows, dim=1)
+
+    # ------------------------------------------------------------------ hot path
+    def render_rays(self, mode, batch_xy, audiostyle, shape_code, appea_code, batch_Rmats, batch_Tvecs,
+                    batch_inv_inmats, t_rand=None):
+        """Arbitrary ray sets (no featmap_size constraint): -> F [B,N_r,256], bg_alpha [B,N_r]."""
+        assert mode in ["train", "test"]
+        B, two, n_r = batch_xy.shape
+        assert two == 2
+        if shape_code.shape[1] != self.shape_dims or appea_code.shape[1] != self.appea_dims or audiostyle.shape[1] != 64:
+            raise ValueError("latent code dimensions do not match the network")
+        ns = self.num_sample_coarse
+        pad = 0
+        while ((n_r + pad) * ns) % L.TILE != 0:
+            pad += 1
+        if pad:
+            batch_xy = torch.cat([batch_xy, batch_xy[:, :, -1:].expand(B, 2, pad)], dim=2)
+        if mode == "train" and t_rand is None:
+            # same draw as the reference's rand_like(zvals) (NetWorks/utils.py:77): shape [B,N_r,N_s+1]
+            t_rand = torch.rand(B, n_r, ns + 1, device=batch_xy.device, dtype=torch.float32)
+        if t_rand is not None and pad:
+            t_rand = torch.cat([t_rand, t_rand[:, -1:, :].expand(B, pad, ns + 1)], dim=1)
+        ws, packed = self._packed_weights()
+        bias = self._fold_biases(shape_code.float(), appea_code.float(), audiostyle.float())
+        meta = {"n_samples": ns, "world_z1": self.opt.world_z1, "world_z2": self.opt.world_z2,
+                "l5_hidden_col": L.PE + self.shape_dims, "packed": packed}
+        Fm, bg = ops.RenderFunction.apply(batch_xy.float(), batch_Rmats.float(), batch_Tvecs.float(),
+                                          batch_inv_inmats.float(), t_rand, bias, *ws, meta)
+        self.last_meta = meta
+        Fm, bg = Fm.view(B, n_r + pad, L.FEAT), bg.view(B, n_r + pad)
+        if pad:
+            Fm, bg = Fm[:, :n_r], bg[:, :n_r]
+        return Fm, bg
+
+    def _forward(self, for_train, batch_xy, batch_uv, audiostyle, bg_code, shape_code, appea_code,
+                 batch_Rmats, batch_Tvecs, batch_inv_inmats, dist_expr):
+        batch_size, tv, n_r = batch_xy.size()
+        assert tv == 2
+        assert bg_code is None
+        fs, C = self.featmap_size, self.featmap_nc
+        assert n_r == fs * fs, "HeadNeRFNet.forward renders a full featmap (HeadNeRFNet.py:103-106); use render_rays otherwise"
+        Fm, bg = self.render_rays("train" if for_train else "test", batch_xy, audiostyle, shape_code, appea_code,
+                                  batch_Rmats, batch_Tvecs, batch_inv_inmats)
+        fg_feat = Fm.permute(0, 2, 1).reshape(batch_size, C, fs, fs)
+        bg_alpha = bg.view(batch_size, 1, fs, fs)
+        bg_featmap = self.neural_render.get_bg_featmap()
+        bg_img = self.neural_render(bg_featmap)
+        merge_featmap = fg_feat + bg_alpha * bg_featmap
+        merge_img = self.neural_render(merge_featmap)
+        return {"coarse_dict": {"merge_img": merge_img, "bg_img": bg_img}}
+
+    def forward(self, mode, batch_xy, batch_uv, audiostyle, bg_code, shape_code, appea_code,
+                batch_Rmats, batch_Tvecs, batch_inv_inmats, dist_expr=False, **kwargs):
+        assert mode in ["train", "test"]
+        return self._forward(mode == "train", batch_xy, batch_uv, audiostyle, bg_code, shape_code, appea_code,
+                             batch_Rmats, batch_Tvecs, batch_inv_inmats, dist_expr)

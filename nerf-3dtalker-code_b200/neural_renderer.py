@@ -1,0 +1,74 @@
+"""NeuralRenderer — the consumer of the composited feature map (reference: NetWorks/neural_renderer.py:11-91,
+NetWorks/PixelShuffleUpsample.py:8-45).  Outside the CUDA hot path: kept as plain
+PyTorch modules whose parameter names, shapes and registration order reproduce the reference state dict
+(`neural_render.*` keys) and its seeded initialisation.  The 3x3 binomial blur restates
+kornia.filters.filter2d(normalized=True, border 'reflect') with a depthwise convolution."""
+from math import log2
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Blur(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("f", torch.Tensor([1, 2, 1]))
+
+    def forward(self, x):
+        k = self.f[None, :] * self.f[:, None]
+        k = (k / k.abs().sum()).to(x.dtype)
+        c = x.shape[1]
+        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), k.expand(c, 1, 3, 3), groups=c)
+
+
+class PixelShuffleUpsample(nn.Module):
+    """x -> blur(pixel_shuffle(act(conv2(act(conv1(x)))) + repeat(x, 4)))  : channels kept, resolution x2."""
+
+    def __init__(self, in_feature):
+        super().__init__()
+        self.in_feature = in_feature
+        self.layer_1 = nn.Conv2d(in_feature, in_feature * 2, 1, 1, padding=0)
+        self.layer_2 = nn.Conv2d(in_feature * 2, in_feature * 4, 1, 1, padding=0)
+        self.blur_layer = Blur()
+
+    def forward(self, x):
+        h = F.leaky_relu(self.layer_1(x), 0.2)
+        h = F.leaky_relu(self.layer_2(h), 0.2)
+        h = F.pixel_shuffle(h + x.repeat(1, 4, 1, 1), 2)
+        return self.blur_layer(h)
+
+
+class NeuralRenderer(nn.Module):
+    def __init__(self, bg_type="white", feat_nc=256, out_dim=3, final_actvn=True, min_feat=32,
+                 featmap_size=32, img_size=256, **kwargs):
+        super().__init__()
+        self.bg_type, self.featmap_size, self.final_actvn = bg_type, featmap_size, final_actvn
+        self.n_feat, self.out_dim, self.min_feat = feat_nc, out_dim, min_feat
+        self.n_blocks = int(log2(img_size) - log2(featmap_size))
+        width = lambda i: max(feat_nc // (2 ** i), min_feat)
+        # registration order follows the reference (_make_layer then _build_bg_featmap) for seed parity
+        self.feat_upsample_list = nn.ModuleList([PixelShuffleUpsample(width(i)) for i in range(self.n_blocks)])
+        self.rgb_upsample = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False), Blur())
+        self.feat_2_rgb_list = nn.ModuleList(
+            [nn.Conv2d(feat_nc, out_dim, 1, 1, padding=0)] +
+            [nn.Conv2d(width(i + 1), out_dim, 1, 1, padding=0) for i in range(self.n_blocks)])
+        self.feat_layers = nn.ModuleList(
+            [nn.Conv2d(width(i), width(i + 1), 1, 1, padding=0) for i in range(self.n_blocks)])
+        if bg_type not in ("white", "black"):
+            raise ValueError(f"bg_type must be 'white' or 'black', got {bg_type!r}")
+        fill = torch.ones if bg_type == "white" else torch.zeros
+        self.register_parameter("bg_featmap", nn.Parameter(fill((1, feat_nc, featmap_size, featmap_size), dtype=torch.float32)))
+
+    def get_bg_featmap(self):
+        return self.bg_featmap
+
+    def forward(self, x):
+        rgb = self.rgb_upsample(self.feat_2_rgb_list[0](x))
+        net = x
+        for i in range(self.n_blocks):
+            net = F.leaky_relu(self.feat_layers[i](self.feat_upsample_list[i](net)), 0.2)
+            rgb = rgb + self.feat_2_rgb_list[i + 1](net)
+            if i < self.n_blocks - 1:
+                rgb = self.rgb_upsample(rgb)
+        return torch.sigmoid(rgb) if self.final_actvn else rgb

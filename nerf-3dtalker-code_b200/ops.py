@@ -1,0 +1,326 @@
+"""Host-side operators over the C ABI (include/headnerf_b200.h): thin torch.autograd.Functions that own
+the tensors (inputs, outputs, saved-for-backward) and pass raw device pointers + the current CUDA stream
+to libheadnerf_b200.so.  PyTorch is plumbing here (memory, streams, autograd graph); every FLOP and byte of
+the hot path is moved by the CUDA library.  No fallback: CPU tensors or a missing library raise."""
+import ctypes as C
+import os
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+
+_DEBUG_SYNC = os.environ.get("HN_DEBUG_SYNC", "0") == "1"
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, name, shape=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise L.HeadNeRFLibraryError(f"{name} must be a CUDA tensor: this path has no CPU implementation")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def check_status(status: torch.Tensor, what: str):
+    """Read a kernel status word (synchronises the stream)."""
+    code = int(status.item())
+    if code != 0:
+        raise L.HeadNeRFLibraryError(f"{what}: on-chip pipeline fault, status {code}")
+
+
+def _camera(xy, R, T, Kinv, t_rand, n_samples, z1, z2):
+    B, two, n_rays = xy.shape
+    cam = L.Camera()
+    cam.B, cam.n_rays, cam.n_samples = B, n_rays, n_samples
+    cam.world_z1, cam.world_z2 = float(z1), float(z2)
+    cam.xy, cam.Rmats, cam.Tvecs, cam.inv_inmats = _ptr(xy), _ptr(R), _ptr(T), _ptr(Kinv)
+    cam.t_rand = _ptr(t_rand)
+    return cam
+
+
+def _check_camera(xy, R, T, Kinv, t_rand, n_samples):
+    B, two, n_rays = xy.shape
+    if two != 2:
+        raise ValueError("batch_xy must be [B,2,N_r]")
+    xy = _dev_f32(xy, "batch_xy")
+    R = _dev_f32(R, "batch_Rmats", (B, 3, 3))
+    T = _dev_f32(T.reshape(B, 3), "batch_Tvecs", (B, 3))
+    Kinv = _dev_f32(Kinv, "batch_inv_inmats", (B, 3, 3))
+    if t_rand is not None:
+        t_rand = _dev_f32(t_rand, "t_rand", (B, n_rays, n_samples + 1))
+    return xy, R, T, Kinv, t_rand
+
+
+# ---------------------------------------------------------------------------------------------------
+# a1/a2 standalone sampler (NetWorks/utils.py:64-161) — utility / tests; not differentiable
+# ---------------------------------------------------------------------------------------------------
+def sample_rays(xy, R, T, Kinv, t_rand=None, n_samples=64, world_z1=2.5, world_z2=-3.5):
+    lib = L.load()
+    xy, R, T, Kinv, t_rand = _check_camera(xy, R, T, Kinv, t_rand, n_samples)
+    B, _, n_rays = xy.shape
+    M = B * n_rays * n_samples
+    dev = xy.device
+    pts = torch.empty(M, 3, device=dev)
+    zvals, z_dists = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    ray_d, ray_l = torch.empty(B * n_rays, 3, device=dev), torch.empty(B * n_rays, device=dev)
+    cam = _camera(xy, R, T, Kinv, t_rand, n_samples, world_z1, world_z2)
+    L.check(lib.hn_sample_rays(C.byref(cam), _ptr(pts), _ptr(zvals), _ptr(z_dists), _ptr(ray_d), _ptr(ray_l), _stream()),
+            "hn_sample_rays")
+    return {"pts": pts, "zvals": zvals, "z_dists": z_dists, "ray_d": ray_d, "ray_l": ray_l}
+
+
+# ---------------------------------------------------------------------------------------------------
+# a6 alpha compositing (NetWorks/utils.py:273-309), standalone differentiable form
+# ---------------------------------------------------------------------------------------------------
+def _composite_fwd(feat, sigma, delta, zvals, n_samples, want_depth=False, want_weights=False):
+    lib = L.load()
+    M, Cc = feat.shape
+    R_ = M // n_samples
+    dev = feat.device
+    Fm = torch.empty(R_, Cc, device=dev)
+    bg = torch.empty(R_, device=dev)
+    depth = torch.empty(R_, device=dev) if (want_depth and zvals is not None) else None
+    w = torch.empty(M, device=dev) if want_weights else None
+    a = L.CompositeFwd()
+    a.n_rays_total, a.n_samples, a.C = R_, n_samples, Cc
+    a.feat, a.sigma, a.delta, a.zvals = _ptr(feat), _ptr(sigma), _ptr(delta), _ptr(zvals)
+    a.F, a.bg_alpha, a.depth, a.weights = _ptr(Fm), _ptr(bg), _ptr(depth), _ptr(w)
+    L.check(lib.hn_composite_fwd(C.byref(a), _stream()), "hn_composite_fwd")
+    return Fm, bg, depth, w
+
+
+def _composite_bwd(feat, sigma, delta, zvals, gF, g_bg, g_depth, n_samples, image=False, grad_scale=None, want_ddelta=True):
+    lib = L.load()
+    M, Cc = feat.shape
+    dev = feat.device
+    dfeat = None if image else torch.empty(M, Cc, device=dev)
+    dimg = torch.empty(lib.hn_dfeat_image_bytes(M), dtype=torch.uint8, device=dev) if image else None
+    dsigma = torch.empty(M, device=dev)
+    ddelta = torch.empty(M, device=dev) if want_ddelta else None
+    a = L.CompositeBwd()
+    a.n_rays_total, a.n_samples, a.C = M // n_samples, n_samples, Cc
+    a.feat, a.sigma, a.delta, a.zvals = _ptr(feat), _ptr(sigma), _ptr(delta), _ptr(zvals)
+    a.gF, a.g_bg, a.g_depth = _ptr(gF), _ptr(g_bg), _ptr(g_depth)
+    a.dfeat, a.dfeat_image, a.grad_scale, a.dsigma, a.ddelta = _ptr(dfeat), _ptr(dimg), _ptr(grad_scale), _ptr(dsigma), _ptr(ddelta)
+    L.check(lib.hn_composite_bwd(C.byref(a), _stream()), "hn_composite_bwd")
+    return dfeat, dimg, dsigma, ddelta
+
+
+class CompositeFunction(torch.autograd.Function):
+    """(feat [M,C], sigma [M], delta [M], zvals [M]) -> (F [R,C], bg_alpha [R], depth [R])."""
+
+    @staticmethod
+    def forward(ctx, feat, sigma, delta, zvals, n_samples):
+        feat, sigma, delta = _dev_f32(feat, "feat"), _dev_f32(sigma, "sigma"), _dev_f32(delta, "delta")
+        zvals = _dev_f32(zvals, "zvals") if zvals is not None else None
+        Fm, bg, depth, _ = _composite_fwd(feat, sigma, delta, zvals, n_samples, want_depth=True)
+        ctx.save_for_backward(feat, sigma, delta, zvals)
+        ctx.n_samples = n_samples
+        if depth is None:
+            depth = torch.zeros_like(bg)
+        ctx.mark_non_differentiable(depth) if zvals is None else None
+        return Fm, bg, depth
+
+    @staticmethod
+    def backward(ctx, gF, g_bg, g_depth):
+        feat, sigma, delta, zvals = ctx.saved_tensors
+        g_depth = g_depth.contiguous() if (g_depth is not None and zvals is not None) else None
+        dfeat, _, dsigma, ddelta = _composite_bwd(feat, sigma, delta, zvals, gF.contiguous(), g_bg.contiguous(),
+                                                  g_depth, ctx.n_samples)
+        dz = None
+        if zvals is not None and g_depth is not None and ctx.needs_input_grad[3]:
+            _, _, _, w = _composite_fwd(feat, sigma, delta, zvals, ctx.n_samples, want_weights=True)
+            dz = w * g_depth.repeat_interleave(ctx.n_samples)
+        return dfeat, dsigma, ddelta, dz, None
+
+
+def composite(feat, sigma, delta, zvals=None, n_samples=64):
+    return CompositeFunction.apply(feat, sigma, delta, zvals, n_samples)
+
+
+# ---------------------------------------------------------------------------------------------------
+# weight packing
+# ---------------------------------------------------------------------------------------------------
+def pack_weights(weights12, l5_hidden_col, out=None):
+    """weights12: the 12 fp32 CUDA weight tensors in header order (any [out,in,...] shape) -> packed uint8 buffer."""
+    lib = L.load()
+    ws = [_dev_f32(w.detach(), f"weight[{i}]") for i, w in enumerate(weights12)]
+    n = lib.hn_packed_weights_bytes()
+    if out is None or out.numel() != n or out.device != ws[0].device:
+        out = torch.empty(n, dtype=torch.uint8, device=ws[0].device)
+    a = L.Weights()
+    for i, w in enumerate(ws):
+        a.w[i] = w.data_ptr()
+        a.ld[i] = w.numel() // w.shape[0]
+    a.l5_hidden_col = l5_hidden_col
+    L.check(lib.hn_pack_weights(C.byref(a), _ptr(out), _stream()), "hn_pack_weights")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# the fused render operator: sampling + PE + MLP + compositing, forward and backward
+# ---------------------------------------------------------------------------------------------------
+def ray_params_torch(xy, R, T, Kinv):
+    """Differentiable per-ray quantities (NetWorks/utils.py:147-158): origin o, v = d*l, l.  Used only in
+    backward to chain the kernel's per-ray gradients to R / T / K^-1 (a few hundred floats per ray)."""
+    B, _, n_rays = xy.shape
+    xyz = F.pad(xy, [0, 0, 0, 1, 0, 0], mode="constant", value=1.0)
+    d = R.bmm(Kinv.bmm(xyz))
+    d = d / torch.norm(d, dim=1, keepdim=True)
+    l = -1.0 / d[:, -1:, :]
+    o = T.reshape(B, 3, 1).expand(B, 3, n_rays)
+    return o, d * l, l
+
+
+class RenderFunction(torch.autograd.Function):
+    """inputs : xy [B,2,N_r], R [B,3,3], T [B,3,1], K^-1 [B,3,3], t_rand or None, bias_eff [B,3920],
+                12 weights (header order; [8] is density_module.weight), then non-tensor meta
+       outputs: F [B*N_r, 256], bg_alpha [B*N_r]"""
+
+    @staticmethod
+    def forward(ctx, xy, R, T, Kinv, t_rand, bias_eff, *rest):
+        weights, meta = rest[:12], rest[12]
+        w_density = weights[8].detach()
+        lib = L.load()
+        ns = meta["n_samples"]
+        xy_c, R_c, T_c, K_c, tr_c = _check_camera(xy, R, T, Kinv, t_rand, ns)
+        B, _, n_rays = xy_c.shape
+        bias_c = _dev_f32(bias_eff, "bias_eff", (B, L.BIAS_STRIDE))
+        wd = _dev_f32(w_density.reshape(-1), "w_density", (L.HIDDEN,))
+        M = B * n_rays * ns
+        dev = xy_c.device
+        need_bwd = any(ctx.needs_input_grad)
+        feat = torch.empty(M, L.FEAT, device=dev)
+        sigma, delta = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        act = torch.empty(lib.hn_act_bytes(M), dtype=torch.uint8, device=dev) if need_bwd else None
+        masks = torch.empty(M * L.MASK_WORDS, dtype=torch.int32, device=dev) if need_bwd else None
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        a = L.MlpFwd()
+        a.cam = _camera(xy_c, R_c, T_c, K_c, tr_c, ns, meta["world_z1"], meta["world_z2"])
+        a.bias, a.w_density, a.packed = _ptr(bias_c), _ptr(wd), _ptr(meta["packed"])
+        a.feat, a.sigma, a.delta, a.zvals = _ptr(feat), _ptr(sigma), _ptr(delta), None
+        a.act, a.masks, a.status = _ptr(act), _ptr(masks), _ptr(status)
+        L.check(lib.hn_mlp_fwd(C.byref(a), _stream()), "hn_mlp_fwd")
+        Fm, bg, _, _ = _composite_fwd(feat, sigma, delta, None, ns)
+        if _DEBUG_SYNC:
+            check_status(status, "hn_mlp_fwd")
+        meta["last_status"] = status
+        if need_bwd:
+            ctx.save_for_backward(xy_c, R_c, T_c, K_c, tr_c, wd, feat, sigma, delta, act, masks, *weights)
+            ctx.meta = meta
+            ctx.T_shape = T.shape
+        return Fm, bg
+
+    @staticmethod
+    def backward(ctx, gF, g_bg):
+        lib = L.load()
+        xy, R, T, Kinv, t_rand, wd, feat, sigma, delta, act, masks = ctx.saved_tensors[:11]
+        weights = ctx.saved_tensors[11:]
+        meta = ctx.meta
+        ns = meta["n_samples"]
+        B, _, n_rays = xy.shape
+        M = B * n_rays * ns
+        dev = xy.device
+        need = ctx.needs_input_grad
+        need_cam = need[1] or need[2] or need[3]
+        need_w = any(need[6:18])
+        need_bias = need[5]
+        gF = gF.contiguous().float()
+        g_bg = g_bg.contiguous().float()
+        # power-of-two loss scale so that half-precision gradient operands stay in range
+        gmax = torch.maximum(gF.abs().amax(), g_bg.abs().amax() * 0.0).clamp_min(1e-30)
+        scale = torch.exp2(torch.floor(torch.log2(meta.get("grad_target", 64.0) / gmax))).reshape(1)
+        _, dimg, dsigma, ddelta = _composite_bwd(feat, sigma, delta, None, gF, g_bg, None, ns, image=True,
+                                                 grad_scale=scale, want_ddelta=need_cam)
+        save_grads = need_w or need_bias
+        grads = torch.empty(lib.hn_grads_bytes(M), dtype=torch.uint8, device=dev) if save_grads else None
+        g_o = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
+        g_v = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
+        g_l = torch.zeros(B * n_rays, device=dev) if need_cam else None
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        a = L.MlpBwdData()
+        a.cam = _camera(xy, R, T, Kinv, t_rand, ns, meta["world_z1"], meta["world_z2"])
+        a.packed, a.w_density, a.dfeat_image = _ptr(meta["packed"]), _ptr(wd), _ptr(dimg)
+        a.dsigma, a.ddelta, a.sigma, a.grad_scale = _ptr(dsigma), _ptr(ddelta), _ptr(sigma), _ptr(scale)
+        a.masks, a.act, a.grads = _ptr(masks), _ptr(act), _ptr(grads)
+        a.g_ray_o, a.g_ray_v, a.g_ray_l, a.status = _ptr(g_o), _ptr(g_v), _ptr(g_l), _ptr(status)
+        L.check(lib.hn_mlp_bwd_data(C.byref(a), _stream()), "hn_mlp_bwd_data")
+
+        dws = [None] * 12
+        dbias = None
+        if save_grads:
+            dbias = torch.zeros(B, L.BIAS_STRIDE, device=dev)
+            w = L.MlpBwdWeights()
+            w.B, w.n_rays, w.n_samples = B, n_rays, ns
+            w.act, w.grads, w.dfeat_image, w.grad_scale = _ptr(act), _ptr(grads), _ptr(dimg), _ptr(scale)
+            ws_bytes = lib.hn_wgrad_workspace_bytes(B)
+            wksp = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            w.items_workspace, w.items_workspace_bytes = _ptr(wksp), ws_bytes
+            for i, wt in enumerate(weights):
+                if need_w:
+                    dws[i] = torch.zeros_like(wt)
+                    w.dw[i] = dws[i].data_ptr()
+                else:
+                    w.dw[i] = None
+                w.ld[i] = wt.numel() // wt.shape[0]
+            w.l5_hidden_col = meta["l5_hidden_col"]
+            w.dbias, w.status = _ptr(dbias), _ptr(status)
+            L.check(lib.hn_mlp_bwd_weights(C.byref(w), _stream()), "hn_mlp_bwd_weights")
+        if _DEBUG_SYNC:
+            check_status(status, "hn_mlp_bwd")
+        meta["last_status"] = status
+
+        gR = gT = gK = None
+        if need_cam:
+            with torch.enable_grad():
+                Rr = R.detach().requires_grad_(need[1])
+                Tr = T.detach().requires_grad_(need[2])
+                Kr = Kinv.detach().requires_grad_(need[3])
+                o, v, l = ray_params_torch(xy, Rr, Tr, Kr)
+                outs = [o, v, l]
+                gouts = [g_o.view(B, n_rays, 3).permute(0, 2, 1), g_v.view(B, n_rays, 3).permute(0, 2, 1), g_l.view(B, 1, n_rays)]
+                ins = [t for t, n in ((Rr, need[1]), (Tr, need[2]), (Kr, need[3])) if n]
+                gs = list(torch.autograd.grad(outs, ins, gouts, allow_unused=True))
+            if need[1]:
+                gR = gs.pop(0)
+            if need[2]:
+                gT = gs.pop(0)
+                gT = gT.reshape(ctx.T_shape) if gT is not None else None
+            if need[3]:
+                gK = gs.pop(0)
+        g_weights = [dws[i] if need[6 + i] else None for i in range(12)]
+        return (None, gR, gT, gK, None, dbias if need_bias else None, *g_weights, None)
+
+
+# ---------------------------------------------------------------------------------------------------
+# debugging / test helpers: decode operand images (csrc/hn_tc.cuh layout) back to dense matrices
+# ---------------------------------------------------------------------------------------------------
+def _image_index(device):
+    r = torch.arange(128, device=device).view(128, 1)
+    c = torch.arange(64, device=device).view(1, 64)
+    return ((r // 8) * 512 + (r % 8) * 64 + (((c // 8) ^ (r % 8)) * 8) + (c % 8)).reshape(-1)
+
+
+def decode_image(buf: torch.Tensor, first_block: int, n_blocks: int, n_tiles: int) -> torch.Tensor:
+    """uint8 image buffer [blocks, n_tiles, 16 KiB] -> float32 [n_tiles*128, 64*n_blocks]."""
+    halves = buf.view(torch.float16).view(-1, n_tiles, 8192)
+    idx = _image_index(buf.device)
+    cols = [halves[first_block + k][:, idx].view(n_tiles * 128, 64) for k in range(n_blocks)]
+    return torch.cat(cols, dim=1).float()
+
+
+def decode_masks(masks: torch.Tensor, word0: int, n_cols: int, M: int) -> torch.Tensor:
+    """int32 mask buffer [M, MASK_WORDS] -> bool [M, n_cols]."""
+    w = masks.view(M, L.MASK_WORDS)[:, word0:word0 + (n_cols + 31) // 32].long() & 0xFFFFFFFF
+    bits = (w.unsqueeze(-1) >> torch.arange(32, device=masks.device)) & 1
+    return bits.reshape(M, -1)[:, :n_cols].bool()

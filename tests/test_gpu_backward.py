@@ -1,0 +1,88 @@
+"""GPU parity tests (backward): gradients of the CUDA path through the C ABI vs (a) the oracle's autograd on
+the same inputs (every element, cosine similarity) and (b) the gradients the real reference produced for the
+golden fixtures (input leaves in full, parameters by norm + fixed probes).  Gate: cosine >= 0.999 per leaf."""
+import pytest
+import torch
+
+from oracle import headnerf_oracle as O
+from _util import GOLDEN_CASES, LEAVES, cosine, golden_loss, load_golden, probe_index
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _oracle_grads(g):
+    opt, inp = g["opt"], g["inp"]
+    sd = {k: v.requires_grad_(not k.endswith(".f")) for k, v in O.formula_state_dict(opt, g["variant"]).items()}
+    x = {k: v.clone().requires_grad_(k in LEAVES) for k, v in inp.items()}
+    res, _ = O.headnerf_forward(sd, opt, g["mode"], x["batch_xy"], x["audiostyle"], x["shape_code"], x["appea_code"],
+                                x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"], t_rand=x.get("t_rand"))
+    golden_loss(res["coarse_dict"]["merge_img"]).backward()
+    return {k: x[k].grad for k in LEAVES}, {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+
+def _cuda_grads(hn, g, leaves=LEAVES, param_grads=True):
+    opt = g["opt"]
+    net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": opt.featmap_size, "featmap_nc": 256, "pred_img_size": opt.pred_img_size}),
+                         include_vd=False, hier_sampling=False)
+    net.load_state_dict(O.formula_state_dict(opt, g["variant"]), strict=True)
+    net = net.to(DEV).eval()
+    if not param_grads:
+        for p in net.parameters():
+            p.requires_grad_(False)
+    x = {k: v.to(DEV).requires_grad_(k in leaves) for k, v in g["inp"].items()}
+    B, fs, C = g["B"], opt.featmap_size, 256
+    Fm, bg = net.render_rays(g["mode"], x["batch_xy"], x["audiostyle"], x["shape_code"], x["appea_code"],
+                             x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"], t_rand=x.get("t_rand"))
+    fg = Fm.permute(0, 2, 1).reshape(B, C, fs, fs)
+    merge = fg + bg.view(B, 1, fs, fs) * net.neural_render.get_bg_featmap()
+    img = net.neural_render(merge)
+    golden_loss(img).backward()
+    hn.ops.check_status(net.last_meta["last_status"], "render backward")
+    gl = {k: x[k].grad.cpu() for k in leaves}
+    gp = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
+    return gl, gp
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_gradients_match_oracle_and_reference(hn, name):
+    g = load_golden(name)
+    ol, op = _oracle_grads(g)
+    cl, cp = _cuda_grads(hn, g)
+    worst = ("", 2.0)
+    for k in LEAVES:
+        c_or, c_ref = cosine(cl[k], ol[k]), cosine(cl[k], g["grads"][k])
+        print(f"{name} {k:14s} cos(oracle) {c_or:.6f} cos(reference golden) {c_ref:.6f}  |g| {float(ol[k].norm()):.3e}")
+        worst = min(worst, (k, min(c_or, c_ref)), key=lambda t: t[1])
+    for k, ref in op.items():
+        assert k in cp, f"no gradient for {k}"
+        c = cosine(cp[k], ref)
+        nrm = float(cp[k].double().norm())
+        probe = cosine(cp[k].reshape(-1)[probe_index(ref.numel())], g["pprobe"][k])
+        if "fg_CD_predictor" in k or "bg_featmap" in k:
+            print(f"{name} {k:44s} cos {c:.6f} probe-cos(ref) {probe:.5f} norm ratio(ref) {nrm / max(g['pnorm'][k], 1e-30):.4f}")
+        worst = min(worst, (k, c), key=lambda t: t[1])
+        assert abs(nrm / max(g["pnorm"][k], 1e-30) - 1.0) < 0.02, k
+    assert worst[1] >= 0.999, worst
+
+
+def test_fitting_config_no_weight_grads(hn):
+    """FittingSingleImage_new.py:826-903 shape: grads only to codes and camera, network weights frozen."""
+    g = load_golden("fs16_test_trained")
+    ol, _ = _oracle_grads(g)
+    cl, cp = _cuda_grads(hn, g, param_grads=False)
+    assert not cp
+    for k in LEAVES:
+        c = cosine(cl[k], ol[k])
+        print(f"fitting {k:14s} cos {c:.6f}")
+        assert c >= 0.999, k
+
+
+def test_codes_only(hn):
+    """No camera gradients requested: the data-gradient chain runs without its positional-encoding tail."""
+    g = load_golden("fs8_test_init")
+    ol, _ = _oracle_grads(g)
+    leaves = ["shape_code", "appea_code", "audiostyle"]
+    cl, cp = _cuda_grads(hn, g, leaves=leaves)
+    for k in leaves:
+        assert cosine(cl[k], ol[k]) >= 0.999, k
