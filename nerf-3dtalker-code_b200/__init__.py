@@ -5,6 +5,7 @@ from .options import BaseOptions
 from .neural_renderer import NeuralRenderer, PixelShuffleUpsample, Blur
 from .headnerf_net import HeadNeRFNet, MLPforNeRF
 from . import ops
+from . import dist
 from . import _lib
 from .build import build as build_library
 

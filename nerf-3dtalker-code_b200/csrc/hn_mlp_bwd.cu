@@ -14,46 +14,28 @@
 // Gradients are carried multiplied by the power-of-two *grad_scale so that fp16 keeps them in range.
 #include <mutex>
 #include "hn_api.h"
+#include "hn_mlp_common.cuh"
 #include "hn_mlp_sched.h"
 #include "hn_sample.cuh"
-#include "hn_tc.cuh"
 
 namespace hn {
 
 __constant__ BwdTables c_bwd[2];          // [0] without dL/dPE, [1] with
 
-constexpr int kBStages = 6;
-constexpr int kBwdThreads = 256;
+constexpr int kBStages = 3;                                 // weight ring: 3 stages of two 64-wide K blocks (32 KiB)
+constexpr uint32_t kBStageBytes = 2 * kUnitBytes;
 constexpr uint32_t kBOffZ = 0;
 constexpr uint32_t kBOffW = 6 * kUnitBytes;
-constexpr uint32_t kBwdSmem = (6 + kBStages) * kUnitBytes + 1024;
+constexpr uint32_t kBwdSmem = 6 * kUnitBytes + kBStages * kBStageBytes + 1024;
 constexpr uint32_t kBTmemCols = 512;
 
 struct BwdShared {
     uint64_t w_full[kBStages], w_empty[kBStages];
     uint64_t a_ready[3], in_ready, z_free, acc_full[4], acc_empty[4];
+    float dp_part[2][128][3];
     uint32_t tmem_base;
     volatile int abort;
 };
-
-__device__ __forceinline__ bool bwait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
-    const uint32_t b = smem_u32(bar);
-    if (mbar_try_wait(b, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(b, parity)) {
-        if (*abort_flag) return false;
-        if (clock64() - t0 > 2000000000ll) {
-            *abort_flag = 1;
-            atomicCAS(status, 0, code);
-            return false;
-        }
-    }
-    return true;
-}
-
-__device__ __forceinline__ void bsync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 __device__ __forceinline__ float warp_sum32(float v) {
 #pragma unroll
@@ -61,7 +43,26 @@ __device__ __forceinline__ float warp_sum32(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bwd_data_t a, const int n_tiles, const int with_pe) {
+// PE backward for PE columns [32*H, 32*H+32): partial dL/dpts of one sample.
+// g[i] = dL/dPE[32*H + i] (still loss-scaled); p = sample position.
+template <int H>
+__device__ __forceinline__ void pe_backward_half(const uint32_t (&g)[32], const float (&p)[3], float (&dp)[3]) {
+    dp[0] = dp[1] = dp[2] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = 32 * H + i;
+        const float gi = __uint_as_float(g[i]);
+        if (c < 3) dp[c] += gi;
+        else if (c < 63) {
+            const int k = (c - 3) / 6, t = (c - 3) % 6, d = t % 3;
+            const float f = (float)(1 << k);
+            const float arg = p[d] * f;
+            dp[d] = fmaf(f * gi, (t < 3) ? cosf(arg) : -sinf(arg), dp[d]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_bwd_data_t a, const int n_tiles, const int with_pe) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ BwdShared sh;
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -71,10 +72,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bw
 
     if (tid == 0) {
         for (int i = 0; i < kBStages; ++i) { mbar_init(smem_u32(&sh.w_full[i]), 1); mbar_init(smem_u32(&sh.w_empty[i]), 1); }
-        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&sh.a_ready[i]), 128);
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&sh.a_ready[i]), kEpiWarps);
         mbar_init(smem_u32(&sh.in_ready), 1);
-        mbar_init(smem_u32(&sh.z_free), 128);
-        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.acc_empty[i]), 128); }
+        mbar_init(smem_u32(&sh.z_free), kEpiWarps);
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.acc_empty[i]), kEpiWarps); }
         sh.abort = 0;
         mbar_fence_init();
     }
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bw
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = sh.tmem_base;
-    const int n_units = tb.n_units, n_epis = tb.n_epis;
+    const int n_ops = tb.n_ops, n_epis = tb.n_epis;
 
     if (warp == 0) {
         // ======================= producer: dL/dfeat image + W^T units =======================
@@ -92,17 +93,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bw
             const uint8_t* wt = (const uint8_t*)a.packed + (size_t)kFwdUnits * kUnitBytes;
             const uint8_t* din = (const uint8_t*)a.dfeat_image;
             for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
-                if (!bwait(&sh.z_free, par_free ^ 1, &sh.abort, a.status, 401)) break;
+                if (!wait_or_abort(&sh.z_free, par_free ^ 1, &sh.abort, a.status, 401)) break;
                 par_free ^= 1;
                 mbar_arrive_expect_tx(smem_u32(&sh.in_ready), 4 * kUnitBytes);
                 for (int kb = 0; kb < 4; ++kb)
                     bulk_g2s(smem + kBOffZ + kb * kUnitBytes, din + ((size_t)kb * n_tiles + tile) * kUnitBytes, kUnitBytes, smem_u32(&sh.in_ready));
-                for (int u = 0; u < n_units; ++u, ++uc) {
+                for (int u = 0; u < n_ops; ++u, ++uc) {
                     const uint32_t stage = uc % kBStages, par = (uc / kBStages) & 1;
-                    if (!bwait(&sh.w_empty[stage], par ^ 1, &sh.abort, a.status, 402)) break;
-                    const uint32_t bytes = (uint32_t)tb.mma[u].n8 * 8 * 128;
-                    mbar_arrive_expect_tx(smem_u32(&sh.w_full[stage]), bytes);
-                    bulk_g2s(smem + kBOffW + stage * kUnitBytes, wt + (size_t)tb.mma[u].unit * kUnitBytes, bytes, smem_u32(&sh.w_full[stage]));
+                    if (!wait_or_abort(&sh.w_empty[stage], par ^ 1, &sh.abort, a.status, 402)) break;
+                    const MmaOp op = tb.mma[u];
+                    const uint32_t bytes = (uint32_t)op.n8 * 8 * 128;
+                    const uint32_t fb = smem_u32(&sh.w_full[stage]);
+                    mbar_arrive_expect_tx(fb, bytes * op.nkb);
+                    for (int k = 0; k < op.nkb; ++k)
+                        bulk_g2s(smem + kBOffW + stage * kBStageBytes + k * kUnitBytes, wt + (size_t)(op.unit + k) * kUnitBytes, bytes, fb);
                 }
             }
         }
@@ -111,43 +115,50 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bw
         if (lane == 0) {
             uint32_t uc = 0, par_ready = 0, par_in = 0, par_empty = 0;
             for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
-                for (int u = 0; u < n_units; ++u, ++uc) {
-                    const MmaOp op = tb.mma[u];
+                MmaOp op = tb.mma[0];
+                for (int u = 0; u < n_ops; ++u, ++uc) {
+                    const MmaOp nxt = tb.mma[u + 1 < n_ops ? u + 1 : 0];          // table read off the critical path
                     bool ok = true;
-                    if (op.wait_src == 5) { ok = bwait(&sh.in_ready, par_in, &sh.abort, a.status, 501); par_in ^= 1; }
+                    if (op.wait_src == 5) { ok = wait_or_abort(&sh.in_ready, par_in, &sh.abort, a.status, 501); par_in ^= 1; }
                     else if (op.wait_src) {
                         const int c = op.wait_src - 1;
-                        ok = bwait(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 502 + c);
+                        ok = wait_or_abort(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 502 + c);
                         par_ready ^= 1u << c;
                     }
                     if (ok && op.wait_empty) {
-                        ok = bwait(&sh.acc_empty[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 510 + op.q);
+                        ok = wait_or_abort(&sh.acc_empty[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 510 + op.q);
                         par_empty ^= 1u << op.q;
                     }
                     const uint32_t stage = uc % kBStages, par = (uc / kBStages) & 1;
-                    if (ok) ok = bwait(&sh.w_full[stage], par, &sh.abort, a.status, 520);
+                    if (ok) ok = wait_or_abort(&sh.w_full[stage], par, &sh.abort, a.status, 520);
                     if (!ok) break;
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem + kBOffZ + op.a_blk * kUnitBytes;
-                    const uint32_t b_addr = smem + kBOffW + stage * kUnitBytes;
+                    const uint32_t b_addr = smem + kBOffW + stage * kBStageBytes;
                     const uint32_t idesc = umma_idesc(128, (uint32_t)op.n8 * 8, kF16, kF16, 0, 0);
                     const uint32_t d_addr = tmem_base + (uint32_t)op.tmem_col8 * 8;
+                    for (int k = 0; k < op.nkb; ++k) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_f16(d_addr, umma_desc_kmajor(a_addr, ks), umma_desc_kmajor(b_addr, ks), idesc, !(op.first && ks == 0));
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16(d_addr, umma_desc_kmajor(a_addr + k * kUnitBytes, ks), umma_desc_kmajor(b_addr + k * kUnitBytes, ks), idesc,
+                                     !(op.first && k == 0 && ks == 0));
+                    }
                     umma_commit(smem_u32(&sh.w_empty[stage]));
                     if (op.commit) umma_commit(smem_u32(&sh.acc_full[op.q]));
+                    op = nxt;
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ======================= epilogue (128 threads, thread = tile row = TMEM lane) =======================
-        const int row = tid - 128;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    } else if (warp >= kCtrlWarps) {
+        // ======================= epilogue: 16 warps, 32 rows x 32 columns each =======================
+        const int ew = warp - kCtrlWarps;
+        const int cg = ew >> 2;
+        const int row = (ew & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((ew & 3) * 32) << 16;
         const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
         const int rsw = row & 7;
         uint32_t par_full = 0;
-        const bool leader = (row == 0);
+        const bool leader = (ew == 0 && lane == 0);
         const float scale = __ldg(a.grad_scale);
         const float inv_scale = 1.0f / scale;
         for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
@@ -156,17 +167,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bw
             const uint32_t* mask_row = a.masks + m * HN_MASK_WORDS;
             for (int e = 0; e < n_epis; ++e) {
                 const EpiOp op = tb.epi[e];
-                bwait(&sh.acc_full[op.q], (par_full >> op.q) & 1, &sh.abort, a.status, 600 + e);
+                wait_or_abort(&sh.acc_full[op.q], (par_full >> op.q) & 1, &sh.abort, a.status, 600 + e);
                 par_full ^= 1u << op.q;
                 tc_fence_after_sync();
                 if (op.kind == EPI_GRAD_PE) {
                     // ---- dL/dPE (64 columns, scaled) -> dL/dpts -> per-ray sums
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8, v0);
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8 + 32, v1);
-                    tmem_ld_wait();
-                    tc_fence_before_sync();
-                    mbar_arrive(smem_u32(&sh.acc_empty[op.q]));
                     const int ns = a.cam.n_samples;
                     const size_t ray_idx = m / ns;
                     const int s = (int)(m % ns), r = (int)(ray_idx % a.cam.n_rays), b = (int)(ray_idx / a.cam.n_rays);
@@ -174,55 +179,60 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bw
                     const float e0 = sample_edge(a.cam, ray.oz, b, r, s), e1 = sample_edge(a.cam, ray.oz, b, r, s + 1);
                     const float p[3] = {__fadd_rn(ray.ox, __fmul_rn(ray.vx, e0)), __fadd_rn(ray.oy, __fmul_rn(ray.vy, e0)),
                                         __fadd_rn(ray.oz, __fmul_rn(ray.vz, e0))};
-                    auto G = [&](int c) -> float { return __uint_as_float(c < 32 ? v0[c] : v1[c - 32]); };
-                    float dp[3];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) dp[d] = G(d);
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) {
-                        const float f = (float)(1 << k);
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            float sn, cs;
-                            sincosf(p[d] * f, &sn, &cs);
-                            dp[d] = fmaf(f, G(3 + 6 * k + d) * cs - G(3 + 6 * k + 3 + d) * sn, dp[d]);
-                        }
+                    if (cg < 2) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8 + cg * 32, v);
+                        tmem_ld_wait();
+                        float part[3];
+                        if (cg == 0) pe_backward_half<0>(v, p, part); else pe_backward_half<1>(v, p, part);
+                        sh.dp_part[cg][row][0] = part[0]; sh.dp_part[cg][row][1] = part[1]; sh.dp_part[cg][row][2] = part[2];
                     }
+                    tc_fence_before_sync();
+                    warp_arrive(smem_u32(&sh.acc_empty[op.q]), lane);
+                    named_sync(2, kEpiThreads);
+                    if (cg == 0) {
+                        float dp[3];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) dp[d] *= inv_scale;
-                    const float dpv = dp[0] * ray.vx + dp[1] * ray.vy + dp[2] * ray.vz;      // through z_s = o_z - const
-                    float red[7] = {dp[0], dp[1], dp[2] + dpv, e0 * dp[0], e0 * dp[1], e0 * dp[2],
-                                    a.ddelta ? (e1 - e0) * __ldg(a.ddelta + m) : 0.f};
+                        for (int d = 0; d < 3; ++d) dp[d] = (sh.dp_part[0][row][d] + sh.dp_part[1][row][d]) * inv_scale;
+                        const float dpv = dp[0] * ray.vx + dp[1] * ray.vy + dp[2] * ray.vz;      // through z_s = o_z - const
+                        float red[7] = {dp[0], dp[1], dp[2] + dpv, e0 * dp[0], e0 * dp[1], e0 * dp[2],
+                                        a.ddelta ? (e1 - e0) * __ldg(a.ddelta + m) : 0.f};
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) red[i] = warp_sum32(red[i]);
-                    if (lane == 0 && a.g_ray_o) {
-                        atomicAdd(a.g_ray_o + ray_idx * 3 + 0, red[0]); atomicAdd(a.g_ray_o + ray_idx * 3 + 1, red[1]);
-                        atomicAdd(a.g_ray_o + ray_idx * 3 + 2, red[2]);
-                        atomicAdd(a.g_ray_v + ray_idx * 3 + 0, red[3]); atomicAdd(a.g_ray_v + ray_idx * 3 + 1, red[4]);
-                        atomicAdd(a.g_ray_v + ray_idx * 3 + 2, red[5]);
-                        atomicAdd(a.g_ray_l + ray_idx, red[6]);
+                        for (int i = 0; i < 7; ++i) red[i] = warp_sum32(red[i]);
+                        if (lane == 0 && a.g_ray_o) {
+                            atomicAdd(a.g_ray_o + ray_idx * 3 + 0, red[0]); atomicAdd(a.g_ray_o + ray_idx * 3 + 1, red[1]);
+                            atomicAdd(a.g_ray_o + ray_idx * 3 + 2, red[2]);
+                            atomicAdd(a.g_ray_v + ray_idx * 3 + 0, red[3]); atomicAdd(a.g_ray_v + ray_idx * 3 + 1, red[4]);
+                            atomicAdd(a.g_ray_v + ray_idx * 3 + 2, red[5]);
+                            atomicAdd(a.g_ray_l + ray_idx, red[6]);
+                        }
                     }
                     continue;
                 }
-                if (saving) { if (leader) bulk_wait_read<1>(); bsync(1, 128); }
-                if (saving && op.kind == EPI_GRAD_DENSITY && op.col0 == 0) {
+                const bool active = cg < op.width32;
+                const int col = cg * 32;
+                if (saving) { if (leader) bulk_wait_read<1>(); named_sync(1, kEpiThreads); }
+                if (saving && op.kind == EPI_GRAD_DENSITY && op.col0 == 0 && cg == 0) {
                     // density head as a one-channel pseudo layer for the weight pass: row = [dsr, 0, ..., 0]
                     uint8_t* drow = (uint8_t*)a.grads + ((size_t)HN_GSLOT_DENS * n_tiles + tile) * kUnitBytes + row_off;
-                    const uint32_t first = pack_h2(fminf(fmaxf(dsr, -65504.f), 65504.f), 0.f);
+                    const uint32_t first = pack_sat(dsr, 0.f);
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         *reinterpret_cast<uint4*>(drow + ((c ^ rsw) << 4)) = make_uint4(c == 0 ? first : 0u, 0u, 0u, 0u);
                 }
-                for (int g = 0; g < op.width32; ++g) {
+                float y[32];
+                if (active) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8 + g * 32, v);
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8 + col, v);
                     tmem_ld_wait();
-                    if (g + 1 == op.width32) { tc_fence_before_sync(); mbar_arrive(smem_u32(&sh.acc_empty[op.q])); }
-                    float y[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]);
+                }
+                tc_fence_before_sync();
+                warp_arrive(smem_u32(&sh.acc_empty[op.q]), lane);
+                if (active) {
                     if (op.kind == EPI_GRAD_DENSITY) {
-                        const float4* wp = reinterpret_cast<const float4*>(a.w_density + op.col0 + g * 32);
+                        const float4* wp = reinterpret_cast<const float4*>(a.w_density + op.col0 + col);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float4 ww = __ldg(wp + i);
@@ -231,24 +241,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bw
                         }
                     }
                     if (op.kind != EPI_GRAD_LINEAR) {
-                        const uint32_t mw = __ldg(mask_row + op.mask_word + g);
+                        const uint32_t mw = __ldg(mask_row + op.mask_word + cg);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) y[i] = ((mw >> i) & 1u) ? y[i] : 0.f;
+                        for (int i = 0; i < 32; ++i) y[i] = (mw & (1u << i)) ? y[i] : 0.f;
                     }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) y[i] = fminf(fmaxf(y[i], -65504.f), 65504.f);
-                    const int col = g * 32;
-                    const uint32_t blk_addr = smem + kBOffZ + (op.dst_blk + (col >> 6)) * kUnitBytes + row_off;
-                    const int ch0 = (col & 63) >> 3;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        st_shared_v4(blk_addr + (((ch0 + c) ^ rsw) << 4),
-                                     pack_h2(y[8 * c + 0], y[8 * c + 1]), pack_h2(y[8 * c + 2], y[8 * c + 3]),
-                                     pack_h2(y[8 * c + 4], y[8 * c + 5]), pack_h2(y[8 * c + 6], y[8 * c + 7]));
+                    store_row32<false>(smem + kBOffZ + op.dst_blk * kUnitBytes, row, col, y);
                 }
                 fence_async_smem();
                 if (saving) {
-                    bsync(1, 128);
+                    named_sync(1, kEpiThreads);
                     if (leader && op.save_blk != 0xFFFF) {
                         const int nblk = (op.width32 + 1) / 2;
                         for (int k = 0; k < nblk; ++k)
@@ -257,11 +258,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const hn_mlp_bw
                         bulk_commit();
                     }
                 }
-                if (op.ready_idx != 255) mbar_arrive(smem_u32(&sh.a_ready[op.ready_idx]));
+                if (op.ready_idx != 255) warp_arrive(smem_u32(&sh.a_ready[op.ready_idx]), lane);
             }
             // the tile's gradient buffer may now be overwritten by the next tile's dL/dfeat image
             if (saving && leader) bulk_wait_read<0>();
-            mbar_arrive(smem_u32(&sh.z_free));
+            warp_arrive(smem_u32(&sh.z_free), lane);
         }
         if (saving && leader) bulk_wait_all<0>();
     }
@@ -303,6 +304,6 @@ extern "C" int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream) {
     const int64_t M = total_samples(a->cam.B, a->cam.n_rays, a->cam.n_samples);
     const int n_tiles = (int)(M / HN_TILE);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    mlp_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, with_pe ? 1 : 0);
+    mlp_bwd_kernel<<<grid, kFusedThreads, kBwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, with_pe ? 1 : 0);
     return check_launch("hn_mlp_bwd_data");
 }

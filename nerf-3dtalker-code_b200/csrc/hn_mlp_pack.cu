@@ -48,7 +48,7 @@ static bool g_uploaded[64] = {};
 }  // namespace hn
 
 extern "C" size_t hn_packed_weights_bytes(void) {
-    return (size_t)(hn::kFwdUnits + hn::host_schedules().bwd.n_units) * hn::kUnitBytes;
+    return (size_t)(hn::kFwdUnits + hn::host_schedules().n_bwd_pack_units) * hn::kUnitBytes;
 }
 
 extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream) {
@@ -67,7 +67,7 @@ extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream
         if (dev < 64 && !g_uploaded[dev]) {
             cudaError_t e = cudaMemcpyToSymbol(c_pack, hs.fwd_pack, sizeof(PackOp) * kFwdUnits, 0);
             if (e == cudaSuccess)
-                e = cudaMemcpyToSymbol(c_pack, hs.bwd_pack, sizeof(PackOp) * hs.bwd.n_units, sizeof(PackOp) * kFwdUnits);
+                e = cudaMemcpyToSymbol(c_pack, hs.bwd_pack, sizeof(PackOp) * hs.n_bwd_pack_units, sizeof(PackOp) * kFwdUnits);
             if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
             g_uploaded[dev] = true;
         }
@@ -75,7 +75,7 @@ extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream
     PackArgs a;
     for (int i = 0; i < 12; ++i) { a.w[i] = w->w[i]; a.ld[i] = w->ld[i]; }
     a.l5_hidden_col = w->l5_hidden_col;
-    a.n_units = kFwdUnits + hs.bwd.n_units;
+    a.n_units = kFwdUnits + hs.n_bwd_pack_units;
     pack_kernel<<<a.n_units, 256, 0, (cudaStream_t)stream>>>(a, (uint8_t*)packed);
     return check_launch("hn_pack_weights");
 }

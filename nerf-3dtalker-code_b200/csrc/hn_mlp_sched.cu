@@ -131,6 +131,27 @@ struct Builder {
     }
 };
 
+// Two consecutive weight units that continue the same accumulator chunk over the next K block become one
+// MMA op (one barrier wait / commit per 32 KiB of weights instead of per 16 KiB).
+std::vector<MmaOp> merge_k_pairs(const std::vector<MmaOp>& in) {
+    std::vector<MmaOp> out;
+    for (size_t i = 0; i < in.size(); ++i) {
+        MmaOp m = in[i];
+        m.nkb = 1;
+        if (i + 1 < in.size()) {
+            const MmaOp& n = in[i + 1];
+            if (!m.commit && n.q == m.q && n.tmem_col8 == m.tmem_col8 && n.n8 == m.n8 && n.a_blk == m.a_blk + 1 && m.a_blk != kPeBlk &&
+                !n.first && !n.wait_src && !n.wait_empty && n.unit == m.unit + 1) {
+                m.nkb = 2;
+                m.commit = n.commit;
+                ++i;
+            }
+        }
+        out.push_back(m);
+    }
+    return out;
+}
+
 HostSchedules* build() {
     auto* hs = new HostSchedules();
     memset(hs, 0, sizeof(*hs));
@@ -152,7 +173,11 @@ HostSchedules* build() {
         assert((int)b.mma.size() == kFwdUnits && (int)b.epi.size() == kFwdEpis);
         for (size_t u = 0; u < b.mma.size(); ++u) b.mma[u].unit = (uint16_t)u;
         memcpy(hs->fwd_pack, b.pack.data(), sizeof(PackOp) * kFwdUnits);
-        memcpy(hs->fwd.mma, b.mma.data(), sizeof(MmaOp) * kFwdUnits);
+        std::vector<MmaOp> merged = merge_k_pairs(b.mma);
+        memcpy(hs->fwd.mma, merged.data(), sizeof(MmaOp) * merged.size());
+        hs->fwd.n_ops = (int)merged.size();
+        // the PE block is free once FeaExt_module_5's last chunk has completed: the next tile's PE is produced there
+        hs->fwd.pe_after_epi = 17;
         memcpy(hs->fwd.epi, b.epi.data(), sizeof(EpiOp) * kFwdEpis);
     }
     for (int with_pe = 1; with_pe >= 0; --with_pe) {
@@ -178,21 +203,23 @@ HostSchedules* build() {
         }
         assert((int)b.mma.size() <= kBwdUnitsMax && (int)b.epi.size() <= kBwdEpisMax);
         BwdTables& t = with_pe ? hs->bwd : hs->bwd_nope;
-        t.n_units = (int)b.mma.size();
         t.n_epis = (int)b.epi.size();
+        if (with_pe) hs->n_bwd_pack_units = (int)b.mma.size();
         if (with_pe) {
             memcpy(hs->bwd_pack, b.pack.data(), sizeof(PackOp) * b.pack.size());
             for (size_t u = 0; u < b.mma.size(); ++u) b.mma[u].unit = (uint16_t)u;
         } else {
             for (size_t u = 0; u < b.mma.size(); ++u) {
                 int found = -1;
-                for (int v = 0; v < hs->bwd.n_units; ++v)
+                for (int v = 0; v < hs->n_bwd_pack_units; ++v)
                     if (!memcmp(&hs->bwd_pack[v], &b.pack[u], sizeof(PackOp))) { found = v; break; }
                 assert(found >= 0);
                 b.mma[u].unit = (uint16_t)found;
             }
         }
-        memcpy(t.mma, b.mma.data(), sizeof(MmaOp) * b.mma.size());
+        std::vector<MmaOp> merged = merge_k_pairs(b.mma);
+        memcpy(t.mma, merged.data(), sizeof(MmaOp) * merged.size());
+        t.n_ops = (int)merged.size();
         memcpy(t.epi, b.epi.data(), sizeof(EpiOp) * b.epi.size());
     }
     return hs;

@@ -36,8 +36,9 @@ struct MmaOp {
     uint8_t commit;                // 1: accumulator chunk complete after this unit -> acc_full[q]
     uint8_t wait_src;              // 0 none, 1..3 a_ready[c-1], 4 pe_ready, 5 in_ready (bwd: input image landed)
     uint8_t wait_empty;            // 1: wait acc_empty[q] before this unit
-    uint16_t unit;                 // index of the weight unit inside its packed stream
-    uint16_t pad;
+    uint16_t unit;                 // index of the first weight unit inside its packed stream
+    uint8_t nkb;                   // consecutive 64-wide K blocks (weight units / A blocks) covered by this op: 1 or 2
+    uint8_t pad;
 };
 
 enum EpiKind : uint8_t {
@@ -71,8 +72,8 @@ constexpr int kFwdEpis = 31;
 constexpr int kBwdUnitsMax = 176;
 constexpr int kBwdEpisMax = 36;
 
-struct FwdTables { MmaOp mma[kFwdUnits]; EpiOp epi[kFwdEpis]; };
-struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_units; int n_epis; };
+struct FwdTables { MmaOp mma[kFwdUnits]; EpiOp epi[kFwdEpis]; int n_ops; int pe_after_epi; };
+struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_ops; int n_epis; };
 
 struct HostSchedules {
     PackOp fwd_pack[kFwdUnits];
@@ -80,6 +81,7 @@ struct HostSchedules {
     PackOp bwd_pack[kBwdUnitsMax];
     BwdTables bwd;                 // full data-gradient chain incl. dL/dPE (camera gradients)
     BwdTables bwd_nope;            // same without the dL/dPE chunks; `unit` still indexes the full stream
+    int n_bwd_pack_units;          // weight units in the data-gradient stream (packed after the kFwdUnits forward units)
 };
 
 const HostSchedules& host_schedules();   // built on first use (hn_mlp_sched.cpp part of hn_mlp_pack.cu)

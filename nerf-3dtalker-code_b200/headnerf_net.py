@@ -135,7 +135,8 @@ class HeadNeRFNet(nn.Module):
         ws, packed = self._packed_weights()
         bias = self._fold_biases(shape_code.float(), appea_code.float(), audiostyle.float())
         meta = {"n_samples": ns, "world_z1": self.opt.world_z1, "world_z2": self.opt.world_z2,
-                "l5_hidden_col": L.PE + self.shape_dims, "packed": packed}
+                "l5_hidden_col": L.PE + self.shape_dims, "packed": packed,
+                "grad_target": float(getattr(self, "grad_target", 64.0))}
         Fm, bg = ops.RenderFunction.apply(batch_xy.float(), batch_Rmats.float(), batch_Tvecs.float(),
                                           batch_inv_inmats.float(), t_rand, bias, *ws, meta)
         self.last_meta = meta

@@ -31,9 +31,49 @@ def _dev_f32(t, name, shape=None):
     return t.contiguous()
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of every library launch (used by bench.py): events are recorded on the
+    launching stream around each C-ABI call; durations are read after the caller synchronises."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []          # (name, start_event, end_event)
+        self.launches = 0
+
+    def reset(self):
+        self.records, self.launches = [], 0
+
+    def summary(self):
+        out = {}
+        for name, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            d = out.setdefault(name, {"n": 0, "ms_total": 0.0})
+            d["n"] += 1
+            d["ms_total"] += ms
+        for d in out.values():
+            d["ms_avg"] = d["ms_total"] / d["n"]
+        return out
+
+
+TIMER = KernelTimer()
+
+
+def _call(name, fn, *args):
+    TIMER.launches += 1
+    if TIMER.enabled:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        TIMER.records.append((name, e0, e1))
+    else:
+        rc = fn(*args)
+    L.check(rc, name)
+
+
 def check_status(status: torch.Tensor, what: str):
     """Read a kernel status word (synchronises the stream)."""
-    code = int(status.item())
+    code = int(status[0].item())
     if code != 0:
         raise L.HeadNeRFLibraryError(f"{what}: on-chip pipeline fault, status {code}")
 
@@ -74,8 +114,7 @@ def sample_rays(xy, R, T, Kinv, t_rand=None, n_samples=64, world_z1=2.5, world_z
     zvals, z_dists = torch.empty(M, device=dev), torch.empty(M, device=dev)
     ray_d, ray_l = torch.empty(B * n_rays, 3, device=dev), torch.empty(B * n_rays, device=dev)
     cam = _camera(xy, R, T, Kinv, t_rand, n_samples, world_z1, world_z2)
-    L.check(lib.hn_sample_rays(C.byref(cam), _ptr(pts), _ptr(zvals), _ptr(z_dists), _ptr(ray_d), _ptr(ray_l), _stream()),
-            "hn_sample_rays")
+    _call("hn_sample_rays", lib.hn_sample_rays, C.byref(cam), _ptr(pts), _ptr(zvals), _ptr(z_dists), _ptr(ray_d), _ptr(ray_l), _stream())
     return {"pts": pts, "zvals": zvals, "z_dists": z_dists, "ray_d": ray_d, "ray_l": ray_l}
 
 
@@ -95,7 +134,7 @@ def _composite_fwd(feat, sigma, delta, zvals, n_samples, want_depth=False, want_
     a.n_rays_total, a.n_samples, a.C = R_, n_samples, Cc
     a.feat, a.sigma, a.delta, a.zvals = _ptr(feat), _ptr(sigma), _ptr(delta), _ptr(zvals)
     a.F, a.bg_alpha, a.depth, a.weights = _ptr(Fm), _ptr(bg), _ptr(depth), _ptr(w)
-    L.check(lib.hn_composite_fwd(C.byref(a), _stream()), "hn_composite_fwd")
+    _call("hn_composite_fwd", lib.hn_composite_fwd, C.byref(a), _stream())
     return Fm, bg, depth, w
 
 
@@ -112,7 +151,7 @@ def _composite_bwd(feat, sigma, delta, zvals, gF, g_bg, g_depth, n_samples, imag
     a.feat, a.sigma, a.delta, a.zvals = _ptr(feat), _ptr(sigma), _ptr(delta), _ptr(zvals)
     a.gF, a.g_bg, a.g_depth = _ptr(gF), _ptr(g_bg), _ptr(g_depth)
     a.dfeat, a.dfeat_image, a.grad_scale, a.dsigma, a.ddelta = _ptr(dfeat), _ptr(dimg), _ptr(grad_scale), _ptr(dsigma), _ptr(ddelta)
-    L.check(lib.hn_composite_bwd(C.byref(a), _stream()), "hn_composite_bwd")
+    _call("hn_composite_bwd", lib.hn_composite_bwd, C.byref(a), _stream())
     return dfeat, dimg, dsigma, ddelta
 
 
@@ -163,7 +202,7 @@ def pack_weights(weights12, l5_hidden_col, out=None):
         a.w[i] = w.data_ptr()
         a.ld[i] = w.numel() // w.shape[0]
     a.l5_hidden_col = l5_hidden_col
-    L.check(lib.hn_pack_weights(C.byref(a), _ptr(out), _stream()), "hn_pack_weights")
+    _call("hn_pack_weights", lib.hn_pack_weights, C.byref(a), _ptr(out), _stream())
     return out
 
 
@@ -204,13 +243,13 @@ class RenderFunction(torch.autograd.Function):
         sigma, delta = torch.empty(M, device=dev), torch.empty(M, device=dev)
         act = torch.empty(lib.hn_act_bytes(M), dtype=torch.uint8, device=dev) if need_bwd else None
         masks = torch.empty(M * L.MASK_WORDS, dtype=torch.int32, device=dev) if need_bwd else None
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        status = torch.zeros(32, dtype=torch.int32, device=dev)
         a = L.MlpFwd()
         a.cam = _camera(xy_c, R_c, T_c, K_c, tr_c, ns, meta["world_z1"], meta["world_z2"])
         a.bias, a.w_density, a.packed = _ptr(bias_c), _ptr(wd), _ptr(meta["packed"])
         a.feat, a.sigma, a.delta, a.zvals = _ptr(feat), _ptr(sigma), _ptr(delta), None
         a.act, a.masks, a.status = _ptr(act), _ptr(masks), _ptr(status)
-        L.check(lib.hn_mlp_fwd(C.byref(a), _stream()), "hn_mlp_fwd")
+        _call("hn_mlp_fwd", lib.hn_mlp_fwd, C.byref(a), _stream())
         Fm, bg, _, _ = _composite_fwd(feat, sigma, delta, None, ns)
         if _DEBUG_SYNC:
             check_status(status, "hn_mlp_fwd")
@@ -247,14 +286,14 @@ class RenderFunction(torch.autograd.Function):
         g_o = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
         g_v = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
         g_l = torch.zeros(B * n_rays, device=dev) if need_cam else None
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        status = torch.zeros(32, dtype=torch.int32, device=dev)
         a = L.MlpBwdData()
         a.cam = _camera(xy, R, T, Kinv, t_rand, ns, meta["world_z1"], meta["world_z2"])
         a.packed, a.w_density, a.dfeat_image = _ptr(meta["packed"]), _ptr(wd), _ptr(dimg)
         a.dsigma, a.ddelta, a.sigma, a.grad_scale = _ptr(dsigma), _ptr(ddelta), _ptr(sigma), _ptr(scale)
         a.masks, a.act, a.grads = _ptr(masks), _ptr(act), _ptr(grads)
         a.g_ray_o, a.g_ray_v, a.g_ray_l, a.status = _ptr(g_o), _ptr(g_v), _ptr(g_l), _ptr(status)
-        L.check(lib.hn_mlp_bwd_data(C.byref(a), _stream()), "hn_mlp_bwd_data")
+        _call("hn_mlp_bwd_data", lib.hn_mlp_bwd_data, C.byref(a), _stream())
 
         dws = [None] * 12
         dbias = None
@@ -275,7 +314,7 @@ class RenderFunction(torch.autograd.Function):
                 w.ld[i] = wt.numel() // wt.shape[0]
             w.l5_hidden_col = meta["l5_hidden_col"]
             w.dbias, w.status = _ptr(dbias), _ptr(status)
-            L.check(lib.hn_mlp_bwd_weights(C.byref(w), _stream()), "hn_mlp_bwd_weights")
+            _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream())
         if _DEBUG_SYNC:
             check_status(status, "hn_mlp_bwd")
         meta["last_status"] = status

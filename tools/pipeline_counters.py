@@ -1,0 +1,22 @@
+"""Prints the forward kernel's CTA-0 pipeline counters (cycles) for the Reso64 batch-2 workload."""
+import importlib, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import headnerf_oracle as O
+hn = importlib.import_module("nerf-3dtalker-code_b200")
+dev = "cuda:0"
+opt = O.OracleOptions(featmap_size=64, pred_img_size=512)
+net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": 64, "featmap_nc": 256, "pred_img_size": 512}), False, False).to(dev)
+x = {k: v.to(dev) for k, v in O.synthetic_inputs(opt, 2, seed=0).items()}
+for need_grad in (False, True):
+    xs = {k: v.clone().requires_grad_(need_grad and k == "shape_code") for k, v in x.items()}
+    for _ in range(3):
+        Fm, bg = net.render_rays("test", xs["batch_xy"], xs["audiostyle"], xs["shape_code"], xs["appea_code"], xs["batch_Rmats"], xs["batch_Tvecs"], xs["batch_inv_inmats"])
+    torch.cuda.synchronize()
+    st = net.last_meta["last_status"].cpu()
+    pc = st[2:18].view(torch.int64).tolist()
+    names = ["mma_total", "mma_wait_pe", "mma_wait_a_ready", "mma_wait_acc_empty", "mma_wait_w_full", "epi_total", "epi_wait_acc_full", "epi_pe_work"]
+    tiles = (2 * 4096 * 64 // 128 + 147) // 148
+    print("saving" if need_grad else "inference", "tiles/CTA", tiles, {n: f"{v} ({v / max(pc[0], 1):.2f})" for n, v in zip(names, pc)})
+    print("  per tile cycles:", pc[0] // tiles)
