@@ -1,5 +1,6 @@
 // hn_api.cu — C-ABI plumbing: version, errors, buffer sizes, and the standalone ray sampler.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "hn_api.h"
 #include "hn_sample.cuh"
@@ -24,6 +25,11 @@ int check_geometry(int B, int n_rays, int n_samples, const char* who) {
     if (n_samples != 32 && n_samples != 64 && n_samples != 128) { snprintf(buf, sizeof buf, "%s: n_samples must be 32, 64 or 128 (got %d)", who, n_samples); return set_error(HN_E_UNSUPPORTED, buf); }
     if (((int64_t)n_rays * n_samples) % HN_TILE != 0) { snprintf(buf, sizeof buf, "%s: n_rays*n_samples must be a multiple of %d", who, HN_TILE); return set_error(HN_E_UNSUPPORTED, buf); }
     return HN_OK;
+}
+
+bool use_cta_pairs(int n_tiles) {
+    static const int env = [] { const char* e = getenv("HN_CTA_PAIRS"); return e ? atoi(e) : 0; }();
+    return env != 0 && n_tiles >= 2 && (n_tiles % 2) == 0;
 }
 
 // One thread per sample; NetWorks/utils.py:147-161,64-89.

@@ -31,6 +31,54 @@ __device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, vo
     return true;
 }
 
+// same, for barriers that also receive arrivals from the peer CTA of a pair (cluster-scope acquire)
+template <bool PAIR>
+__device__ __forceinline__ bool wait_or_abort_x(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
+    if (!PAIR) return wait_or_abort(bar, parity, abort_flag, status, code);
+    const uint32_t b = smem_u32(bar);
+    if (mbar_try_wait_cluster(b, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(b, parity)) {
+        if (*abort_flag) return false;
+        if (clock64() - t0 > 2000000000ll) {
+            *abort_flag = 1;
+            atomicCAS(status, 0, code);
+            return false;
+        }
+    }
+    return true;
+}
+
+// one arrival per warp on a barrier that lives in the LEADER CTA (rank 0) of the pair; in single-CTA mode a local arrive
+template <bool PAIR>
+__device__ __forceinline__ void warp_arrive_leader(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) { if (PAIR) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar); }
+}
+
+template <bool PAIR> __device__ __forceinline__ void umma_x(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, bool acc) {
+    if (PAIR) umma_f16_pair(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
+}
+template <bool PAIR> __device__ __forceinline__ void umma_commit_x(uint32_t bar) {
+    if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
+}
+
+// Optional pipeline cycle counters (build with -DHN_PIPE_COUNTERS, read with tools/pipeline_counters.py): the
+// forward kernel's CTA 0 writes, as 64-bit cycle counts, status[2..17] (MMA issuer: total, waits by barrier class,
+// issue, commit) and status[18..29] (epilogue warp 0: total, wait, TMEM load, math+store, sync, next-tile PE).
+#ifdef HN_PIPE_COUNTERS
+#define HN_PC_DECL(v, n) long long v[n] = {0}; const long long v##_start = clock64(); long long v##_t0 = v##_start
+#define HN_PC_T0(v) do { v##_t0 = clock64(); } while (0)
+#define HN_PC_LAP(v, i) do { const long long _t = clock64(); v[i] += _t - v##_t0; v##_t0 = _t; } while (0)
+#define HN_PC_FLUSH(v, n, dst, cond) do { if (cond) { v[0] = clock64() - v##_start; long long* _o = reinterpret_cast<long long*>(dst); \
+                                          for (int _i = 0; _i < n; ++_i) _o[_i] = v[_i]; } } while (0)
+#else
+#define HN_PC_DECL(v, n) do {} while (0)
+#define HN_PC_T0(v) do {} while (0)
+#define HN_PC_LAP(v, i) do {} while (0)
+#define HN_PC_FLUSH(v, n, dst, cond) do {} while (0)
+#endif
+
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -71,12 +119,18 @@ __device__ __forceinline__ void store_row32(uint32_t base, int row, int col0, co
     }
 }
 
-// bit i of the result = (y[i] > 0) (sign-bit funnel shifts: one instruction per element; +0.0 counts as positive)
+// bit i of the result = (y[i] > 0) (sign-bit funnel shifts: one instruction per element; +0.0 counts as positive).
+// Four independent 8-deep chains instead of one 32-deep dependency chain.
 __device__ __forceinline__ uint32_t positive_mask32(const float (&y)[32]) {
-    uint32_t m = 0;
+    uint32_t m[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 32; ++i) m = __funnelshift_l(__float_as_uint(y[i]), m, 1);
-    return ~__brev(m);
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m[c] = __funnelshift_l(__float_as_uint(y[8 * c + i]), m[c], 1);
+    }
+    // m[c] holds the signs of y[8c..8c+7] in its low byte, element 8c at bit 7
+    const uint32_t packed = (m[0] << 24) | ((m[1] & 0xFFu) << 16) | ((m[2] & 0xFFu) << 8) | (m[3] & 0xFFu);
+    return ~__brev(packed);
 }
 
 }  // namespace hn

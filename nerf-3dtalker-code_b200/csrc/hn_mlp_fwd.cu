@@ -27,13 +27,18 @@ constexpr uint32_t kStageBytes = 2 * kUnitBytes;
 constexpr uint32_t kOffA = 0;                               // 6 activation blocks
 constexpr uint32_t kOffPE = 6 * kUnitBytes;                 // 1 PE block
 constexpr uint32_t kOffW = 7 * kUnitBytes;                  // weight ring
-constexpr uint32_t kFwdSmem = 7 * kUnitBytes + kStages * kStageBytes + 1024;
+constexpr uint32_t kOffBias = 7 * kUnitBytes + kStages * kStageBytes;   // this item's effective bias row (15.3 KiB): the ~15 KiB
+                                                                          // of L1 left beside the smem carve-out cannot hold it
+constexpr uint32_t kBiasBytes = HN_BIAS_STRIDE * 4;
+constexpr uint32_t kFwdSmem = kOffBias + kBiasBytes + 1024;
 constexpr uint32_t kTmemCols = 512;
 
 struct FwdShared {
-    uint64_t w_full[kStages], w_empty[kStages];
+    uint64_t w_full[6], w_empty[6], w_peer[6];
     uint64_t a_ready[3], pe_ready, acc_full[4], acc_empty[4];
-    float dens[4][128];
+    uint64_t a_ready_p[3], pe_ready_p, acc_empty_p[4];      // pair mode, leader only: one arrival each, forwarded by the peer CTA
+    float dens[128];                    // density head: the four column groups add their partial dot products here
+    float w_density[HN_HIDDEN];
     uint32_t tmem_base;
     volatile int abort;
 };
@@ -63,24 +68,39 @@ __device__ __forceinline__ void write_pe_part(uint32_t pe_block, int row, const 
                      pack_h2(v[8 * h + 4], v[8 * h + 5]), pack_h2(v[8 * h + 6], v[8 * h + 7]));
 }
 
+// PAIR = true: two CTAs of a cluster (one TPC) process two tiles in lockstep with cta_group::2 MMAs of M = 256; each
+// CTA streams only HALF of every weight unit (its half of the B operand).  Work item w -> tile 2w + rank.
+template <bool PAIR>
 __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_fwd_t a, const int n_tiles, const int tiles_per_item) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ FwdShared sh;
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool saving = (a.act != nullptr);
+    // weight ring geometry: single CTA 3 x 32 KiB (two 64-wide K blocks of 128 rows); pair mode 6 x 16 KiB (this CTA's
+    // half of the rows of both K blocks) - same bytes in flight per CTA, i.e. twice the prefetch depth per weight byte needed
+    constexpr int STAGES = PAIR ? 6 : 3;
+    constexpr uint32_t STAGE_BYTES = PAIR ? kUnitBytes : 2 * kUnitBytes;
+    constexpr uint32_t KB_STRIDE = PAIR ? kUnitBytes / 2 : kUnitBytes;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+    const int work0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int work_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_work = PAIR ? n_tiles / 2 : n_tiles;
 
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&sh.w_full[i]), 1); mbar_init(smem_u32(&sh.w_empty[i]), 1); }
-        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&sh.a_ready[i]), kEpiWarps);
-        mbar_init(smem_u32(&sh.pe_ready), kEpiWarps);
-        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.acc_empty[i]), kEpiWarps); }
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(&sh.w_full[i]), 1); mbar_init(smem_u32(&sh.w_empty[i]), 1); mbar_init(smem_u32(&sh.w_peer[i]), 1);
+        }
+        for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&sh.a_ready[i]), kEpiWarps); mbar_init(smem_u32(&sh.a_ready_p[i]), 1); }
+        mbar_init(smem_u32(&sh.pe_ready), kEpiWarps); mbar_init(smem_u32(&sh.pe_ready_p), 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.acc_empty[i]), kEpiWarps); mbar_init(smem_u32(&sh.acc_empty_p[i]), 1); }
         sh.abort = 0;
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(&sh.tmem_base));
+    if (warp == 2) { if (PAIR) tmem_alloc_pair<kTmemCols>(smem_u32(&sh.tmem_base)); else tmem_alloc<kTmemCols>(smem_u32(&sh.tmem_base)); }
     tc_fence_before_sync();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                               // peer barriers initialised before any remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = sh.tmem_base;
     const int n_ops = c_fwd.n_ops;
@@ -90,56 +110,109 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
         if (lane == 0) {
             uint32_t uc = 0;
             const uint8_t* packed = (const uint8_t*)a.packed;
-            for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
+            for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
                 for (int u = 0; u < n_ops; ++u, ++uc) {
-                    const uint32_t stage = uc % kStages, par = (uc / kStages) & 1;
+                    const uint32_t stage = uc % STAGES, par = (uc / STAGES) & 1;
                     if (!wait_or_abort(&sh.w_empty[stage], par ^ 1, &sh.abort, a.status, 101)) break;
                     const MmaOp op = c_fwd.mma[u];
-                    const uint32_t bytes = (uint32_t)op.n8 * 8 * 128;
+                    // pair mode: this CTA holds rows [rank*N/2, rank*N/2 + N/2) of the unit (its half of the B operand)
+                    const uint32_t bytes = (uint32_t)op.n8 * 8 * 128 / (PAIR ? 2 : 1);
                     const uint32_t fb = smem_u32(&sh.w_full[stage]);
                     mbar_arrive_expect_tx(fb, bytes * op.nkb);
                     for (int k = 0; k < op.nkb; ++k)
-                        bulk_g2s(smem + kOffW + stage * kStageBytes + k * kUnitBytes, packed + (size_t)(op.unit + k) * kUnitBytes, bytes, fb);
+                        bulk_g2s(smem + kOffW + stage * STAGE_BYTES + k * KB_STRIDE,
+                                 packed + (size_t)(op.unit + k) * kUnitBytes + (PAIR ? rank * bytes : 0), bytes, fb);
                 }
             }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        if (PAIR && rank == 1) {
+            // peer CTA: no MMA issue; relay "my half of the weights has landed" to the leader
+            if (lane == 0) {
+                uint32_t uc = 0;
+                for (int w = work0; w < n_work && !sh.abort; w += work_stride)
+                    for (int u = 0; u < n_ops; ++u, ++uc) {
+                        const uint32_t stage = uc % STAGES, par = (uc / STAGES) & 1;
+                        if (!wait_or_abort(&sh.w_full[stage], par, &sh.abort, a.status, 230)) break;
+                        mbar_arrive_cluster(smem_u32(&sh.w_peer[stage]), 0);
+                    }
+            }
+        } else if (lane == 0) {
             uint32_t uc = 0, par_ready = 0, par_pe = 0, par_empty = 0;
-            for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
+            HN_PC_DECL(pc, 8);
+            for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
                 MmaOp op = c_fwd.mma[0];
                 for (int u = 0; u < n_ops; ++u, ++uc) {
                     const MmaOp nxt = c_fwd.mma[u + 1 < n_ops ? u + 1 : 0];       // table read off the critical path
                     bool ok = true;
-                    if (op.wait_src == 4) { ok = wait_or_abort(&sh.pe_ready, par_pe, &sh.abort, a.status, 201); par_pe ^= 1; }
+                    HN_PC_T0(pc);
+                    if (op.wait_src == 4) { ok = wait_or_abort(&sh.pe_ready, par_pe, &sh.abort, a.status, 201);
+                        if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.pe_ready_p, par_pe, &sh.abort, a.status, 241);
+                        par_pe ^= 1; HN_PC_LAP(pc, 1); }
                     else if (op.wait_src) {
                         const int c = op.wait_src - 1;
                         ok = wait_or_abort(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 202 + c);
+                        if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.a_ready_p[c], (par_ready >> c) & 1, &sh.abort, a.status, 242 + c);
                         par_ready ^= 1u << c;
+                        HN_PC_LAP(pc, 2);
                     }
                     if (ok && op.wait_empty) {
                         ok = wait_or_abort(&sh.acc_empty[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 210 + op.q);
+                        if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.acc_empty_p[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 246 + op.q);
                         par_empty ^= 1u << op.q;
+                        HN_PC_LAP(pc, 3);
                     }
-                    const uint32_t stage = uc % kStages, par = (uc / kStages) & 1;
+                    const uint32_t stage = uc % STAGES, par = (uc / STAGES) & 1;
                     if (ok) ok = wait_or_abort(&sh.w_full[stage], par, &sh.abort, a.status, 220);
+                    HN_PC_LAP(pc, 4);
+                    if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.w_peer[stage], par, &sh.abort, a.status, 221);
+                    HN_PC_LAP(pc, 5);
                     if (!ok) break;
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem + (op.a_blk == kPeBlk ? kOffPE : kOffA + op.a_blk * kUnitBytes);
-                    const uint32_t b_addr = smem + kOffW + stage * kStageBytes;
-                    const uint32_t idesc = umma_idesc(128, (uint32_t)op.n8 * 8, kF16, kF16, 0, 0);
+                    const uint32_t b_addr = smem + kOffW + stage * STAGE_BYTES;
+                    const uint32_t idesc = umma_idesc(PAIR ? 256 : 128, (uint32_t)op.n8 * 8, kF16, kF16, 0, 0);
                     const uint32_t d_addr = tmem_base + (uint32_t)op.tmem_col8 * 8;
                     for (int k = 0; k < op.nkb; ++k) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            umma_f16(d_addr, umma_desc_kmajor(a_addr + k * kUnitBytes, ks), umma_desc_kmajor(b_addr + k * kUnitBytes, ks), idesc,
-                                     !(op.first && k == 0 && ks == 0));
+                            umma_x<PAIR>(d_addr, umma_desc_kmajor(a_addr + k * kUnitBytes, ks), umma_desc_kmajor(b_addr + k * KB_STRIDE, ks), idesc,
+                                         !(op.first && k == 0 && ks == 0));
                     }
-                    umma_commit(smem_u32(&sh.w_empty[stage]));
-                    if (op.commit) umma_commit(smem_u32(&sh.acc_full[op.q]));
+                    HN_PC_LAP(pc, 6);
+                    umma_commit_x<PAIR>(smem_u32(&sh.w_empty[stage]));
+                    if (op.commit) umma_commit_x<PAIR>(smem_u32(&sh.acc_full[op.q]));
+                    HN_PC_LAP(pc, 7);
                     op = nxt;
                 }
+            }
+            HN_PC_FLUSH(pc, 8, a.status + 2, blockIdx.x == 0);
+        }
+    } else if (warp == 3) {
+        // ======================= pair mode, peer CTA: barrier forwarder =======================
+        // The peer's epilogue warps arrive on their OWN CTA's barriers (cheap); this thread relays every completed phase
+        // to the leader with a single remote arrive, keeping cluster-scope release traffic off the epilogue's critical path.
+        if (PAIR && rank == 1 && lane == 0) {
+            const int my_tiles = (n_work - work0 + work_stride - 1) / work_stride;
+            uint64_t* local[8] = {&sh.a_ready[0], &sh.a_ready[1], &sh.a_ready[2], &sh.acc_empty[0], &sh.acc_empty[1], &sh.acc_empty[2], &sh.acc_empty[3], &sh.pe_ready};
+            uint64_t* remote[8] = {&sh.a_ready_p[0], &sh.a_ready_p[1], &sh.a_ready_p[2], &sh.acc_empty_p[0], &sh.acc_empty_p[1], &sh.acc_empty_p[2], &sh.acc_empty_p[3], &sh.pe_ready_p};
+            int left[8];
+            for (int i = 0; i < 3; ++i) left[i] = c_fwd.n_ready[i] * my_tiles;
+            for (int i = 0; i < 4; ++i) left[3 + i] = c_fwd.n_empty[i] * my_tiles;
+            left[7] = my_tiles;
+            uint32_t par = 0;
+            int total = 0;
+            for (int i = 0; i < 8; ++i) total += left[i];
+            const long long t0 = clock64();
+            while (total > 0 && !sh.abort) {
+                for (int i = 0; i < 8; ++i) {
+                    if (left[i] > 0 && mbar_try_wait(smem_u32(local[i]), (par >> i) & 1)) {
+                        mbar_arrive_cluster(smem_u32(remote[i]), 0);
+                        par ^= 1u << i; --left[i]; --total;
+                    }
+                }
+                if (clock64() - t0 > 20000000000ll) { sh.abort = 1; atomicCAS(a.status, 0, 260); }
             }
         }
     } else if (warp >= kCtrlWarps) {
@@ -151,6 +224,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
         uint32_t par_full = 0;
         const bool leader = (ew == 0 && lane == 0);
         const int pe_after = c_fwd.pe_after_epi;
+        int cached_b = -1;
+        for (int i = tid - kCtrlWarps * 32; i < HN_HIDDEN; i += kEpiThreads) sh.w_density[i] = __ldg(a.w_density + i);
+        if (tid - kCtrlWarps * 32 < 128) sh.dens[tid - kCtrlWarps * 32] = 0.f;
+        named_sync(3, kEpiThreads);
 
         // sampling + positional encoding of tile `t`: the first GEMM's operand is generated, not loaded
         auto produce_pe = [&](int t) {
@@ -184,18 +261,33 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
             warp_arrive(smem_u32(&sh.pe_ready), lane);
         };
 
-        if ((int)blockIdx.x < n_tiles) produce_pe(blockIdx.x);
-        for (int tile = blockIdx.x; tile < n_tiles && !sh.abort; tile += gridDim.x) {
+        auto tile_of = [&](int w) { return PAIR ? 2 * w + (int)rank : w; };
+        HN_PC_DECL(ec, 6);
+        if (work0 < n_work) produce_pe(tile_of(work0));
+        for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
+            const int tile = tile_of(w);
             const size_t m = (size_t)tile * HN_TILE + row;
             const int b = tile / tiles_per_item;
-            const float* bias_row = a.bias + (size_t)b * HN_BIAS_STRIDE;
+            if (b != cached_b) {                                    // (re)load the item's bias row; epilogue warps run in lockstep
+                named_sync(3, kEpiThreads);
+                const float4* src = reinterpret_cast<const float4*>(a.bias + (size_t)b * HN_BIAS_STRIDE);
+                for (int i = tid - kCtrlWarps * 32; i < HN_BIAS_STRIDE / 4; i += kEpiThreads) {
+                    const float4 v4 = __ldg(src + i);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(smem + kOffBias + i * 16), "f"(v4.x), "f"(v4.y), "f"(v4.z), "f"(v4.w) : "memory");
+                }
+                named_sync(3, kEpiThreads);
+                cached_b = b;
+            }
+            const uint32_t bias_row = smem + kOffBias;
             float dens = 0.f;
             for (int e = 0; e < kFwdEpis; ++e) {
                 const EpiOp op = c_fwd.epi[e];
                 // on a pipeline fault every later wait returns at once; the loop still runs to its end so that all
                 // epilogue threads keep meeting at the same named barriers
+                HN_PC_T0(ec);
                 wait_or_abort(&sh.acc_full[op.q], (par_full >> op.q) & 1, &sh.abort, a.status, 300 + e);
                 par_full ^= 1u << op.q;
+                HN_PC_LAP(ec, 1);
                 tc_fence_after_sync();
                 const bool to_smem = (op.kind != EPI_FEAT);
                 const bool active = cg < op.width32;
@@ -206,16 +298,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                     uint32_t v[32];
                     tmem_ld32(tmem_base + lane_base + (uint32_t)op.tmem_col8 * 8 + col, v);
                     tmem_ld_wait();
-                    const float4* bp = reinterpret_cast<const float4*>(bias_row + op.bias_off + col);
+                    const uint32_t bp = bias_row + (op.bias_off + col) * 4;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 bb = __ldg(bp + i);
+                        float4 bb;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(bp + i * 16));
                         y[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
                         y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
                         y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
                         y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
                     }
                 }
+                HN_PC_LAP(ec, 2);
                 tc_fence_before_sync();
                 warp_arrive(smem_u32(&sh.acc_empty[op.q]), lane);  // accumulator read: hand it back to the MMA issuer
                 if (active) {
@@ -223,10 +317,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                         if (a.masks && op.mask_word != 0xFFFF)
                             a.masks[m * HN_MASK_WORDS + op.mask_word + cg] = positive_mask32(y);
                         if (op.density) {                          // density head on the fp32 activations (models.py:78,83)
-                            const float4* wp = reinterpret_cast<const float4*>(a.w_density + op.col0 + col);
+                            const float4* wp = reinterpret_cast<const float4*>(sh.w_density + op.col0 + col);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float4 ww = __ldg(wp + i);
+                                const float4 ww = wp[i];
                                 dens = fmaf(fmaxf(y[4 * i + 0], 0.f), ww.x, dens); dens = fmaf(fmaxf(y[4 * i + 1], 0.f), ww.y, dens);
                                 dens = fmaf(fmaxf(y[4 * i + 2], 0.f), ww.z, dens); dens = fmaf(fmaxf(y[4 * i + 3], 0.f), ww.w, dens);
                             }
@@ -240,13 +334,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                         for (int i = 0; i < 8; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
                     }
                 }
+                HN_PC_LAP(ec, 3);
                 if (op.density == 2) {                             // combine the four column groups' partial dot products
-                    sh.dens[cg][row] = dens;
+                    atomicAdd(&sh.dens[row], dens);
                     dens = 0.f;
                     named_sync(2, kEpiThreads);
-                    if (cg == 0)
-                        a.sigma[m] = fmaxf(sh.dens[0][row] + sh.dens[1][row] + sh.dens[2][row] + sh.dens[3][row] +
-                                           __ldg(bias_row + HN_BIAS_OFF_DENSITY), 0.f);
+                    if (cg == 0) {
+                        a.sigma[m] = fmaxf(sh.dens[row] + __ldg(a.bias + (size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_DENSITY), 0.f);
+                        sh.dens[row] = 0.f;                        // next use is a whole tile (and many barrier hops) away
+                    }
                 }
                 if (to_smem) {
                     fence_async_smem();
@@ -264,15 +360,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                 }
                 // FeaExt_module_5 (the last reader of the PE block) is done: build the NEXT tile's PE operand now, while
                 // the tensor core still has this tile's remaining layers queued
-                if (e == pe_after && tile + (int)gridDim.x < n_tiles) produce_pe(tile + gridDim.x);
+                HN_PC_LAP(ec, 4);
+                if (e == pe_after && w + work_stride < n_work) produce_pe(tile_of(w + work_stride));
+                HN_PC_LAP(ec, 5);
             }
         }
         if (saving && leader) bulk_wait_all<0>();
+        HN_PC_FLUSH(ec, 6, a.status + 18, blockIdx.x == 0 && leader);
     }
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) tmem_free<kTmemCols>(tmem_base);
+    if (PAIR) cluster_sync_all();                               // the peer may still be reading this CTA's operands / barriers
+    if (warp == 2) { if (PAIR) tmem_free_pair<kTmemCols>(tmem_base); else tmem_free<kTmemCols>(tmem_base); }
 }
 
 static std::mutex g_fwd_mu;
@@ -294,7 +394,8 @@ extern "C" int hn_mlp_fwd(const hn_mlp_fwd_t* a, void* stream) {
         std::lock_guard<std::mutex> lk(g_fwd_mu);
         if (dev < 64 && !g_fwd_ready[dev]) {
             cudaError_t e = cudaMemcpyToSymbol(c_fwd, &host_schedules().fwd, sizeof(FwdTables));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
             if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
             g_fwd_ready[dev] = true;
         }
@@ -304,7 +405,19 @@ extern "C" int hn_mlp_fwd(const hn_mlp_fwd_t* a, void* stream) {
     const int64_t M = total_samples(a->cam.B, a->cam.n_rays, a->cam.n_samples);
     const int n_tiles = (int)(M / HN_TILE);
     const int tiles_per_item = (int)(((int64_t)a->cam.n_rays * a->cam.n_samples) / HN_TILE);
+    if (use_cta_pairs(n_tiles)) {
+        const int n_pairs = (n_tiles / 2) < (n_sm / 2) ? (n_tiles / 2) : (n_sm / 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = kFwdSmem; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_fwd_kernel<true>, *a, n_tiles, tiles_per_item);
+        if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+        return check_launch("hn_mlp_fwd (cta pairs)");
+    }
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    mlp_fwd_kernel<<<grid, kFusedThreads, kFwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, tiles_per_item);
+    mlp_fwd_kernel<false><<<grid, kFusedThreads, kFwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, tiles_per_item);
     return check_launch("hn_mlp_fwd");
 }

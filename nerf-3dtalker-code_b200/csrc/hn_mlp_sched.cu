@@ -178,6 +178,7 @@ HostSchedules* build() {
         hs->fwd.n_ops = (int)merged.size();
         // the PE block is free once FeaExt_module_5's last chunk has completed: the next tile's PE is produced there
         hs->fwd.pe_after_epi = 17;
+        for (const EpiOp& e : b.epi) { if (e.ready_idx != 255) hs->fwd.n_ready[e.ready_idx]++; hs->fwd.n_empty[e.q]++; }
         memcpy(hs->fwd.epi, b.epi.data(), sizeof(EpiOp) * kFwdEpis);
     }
     for (int with_pe = 1; with_pe >= 0; --with_pe) {
@@ -221,6 +222,7 @@ HostSchedules* build() {
         memcpy(t.mma, merged.data(), sizeof(MmaOp) * merged.size());
         t.n_ops = (int)merged.size();
         memcpy(t.epi, b.epi.data(), sizeof(EpiOp) * b.epi.size());
+        for (const EpiOp& e : b.epi) { if (e.ready_idx != 255) t.n_ready[e.ready_idx]++; t.n_empty[e.q]++; }
     }
     return hs;
 }

@@ -72,8 +72,8 @@ constexpr int kFwdEpis = 31;
 constexpr int kBwdUnitsMax = 176;
 constexpr int kBwdEpisMax = 36;
 
-struct FwdTables { MmaOp mma[kFwdUnits]; EpiOp epi[kFwdEpis]; int n_ops; int pe_after_epi; };
-struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_ops; int n_epis; };
+struct FwdTables { MmaOp mma[kFwdUnits]; EpiOp epi[kFwdEpis]; int n_ops; int pe_after_epi; int n_ready[3]; int n_empty[4]; };
+struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_ops; int n_epis; int n_ready[3]; int n_empty[4]; };
 
 struct HostSchedules {
     PackOp fwd_pack[kFwdUnits];

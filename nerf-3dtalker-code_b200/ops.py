@@ -243,7 +243,7 @@ class RenderFunction(torch.autograd.Function):
         sigma, delta = torch.empty(M, device=dev), torch.empty(M, device=dev)
         act = torch.empty(lib.hn_act_bytes(M), dtype=torch.uint8, device=dev) if need_bwd else None
         masks = torch.empty(M * L.MASK_WORDS, dtype=torch.int32, device=dev) if need_bwd else None
-        status = torch.zeros(32, dtype=torch.int32, device=dev)
+        status = torch.zeros(64, dtype=torch.int32, device=dev)
         a = L.MlpFwd()
         a.cam = _camera(xy_c, R_c, T_c, K_c, tr_c, ns, meta["world_z1"], meta["world_z2"])
         a.bias, a.w_density, a.packed = _ptr(bias_c), _ptr(wd), _ptr(meta["packed"])
@@ -286,7 +286,7 @@ class RenderFunction(torch.autograd.Function):
         g_o = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
         g_v = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
         g_l = torch.zeros(B * n_rays, device=dev) if need_cam else None
-        status = torch.zeros(32, dtype=torch.int32, device=dev)
+        status = torch.zeros(64, dtype=torch.int32, device=dev)
         a = L.MlpBwdData()
         a.cam = _camera(xy, R, T, Kinv, t_rand, ns, meta["world_z1"], meta["world_z2"])
         a.packed, a.w_density, a.dfeat_image = _ptr(meta["packed"]), _ptr(wd), _ptr(dimg)

@@ -15,8 +15,11 @@ for need_grad in (False, True):
         Fm, bg = net.render_rays("test", xs["batch_xy"], xs["audiostyle"], xs["shape_code"], xs["appea_code"], xs["batch_Rmats"], xs["batch_Tvecs"], xs["batch_inv_inmats"])
     torch.cuda.synchronize()
     st = net.last_meta["last_status"].cpu()
-    pc = st[2:18].view(torch.int64).tolist()
-    names = ["mma_total", "mma_wait_pe", "mma_wait_a_ready", "mma_wait_acc_empty", "mma_wait_w_full", "epi_total", "epi_wait_acc_full", "epi_pe_work"]
+    mma = st[2:18].view(torch.int64).tolist()
+    epi = st[18:30].view(torch.int64).tolist()
     tiles = (2 * 4096 * 64 // 128 + 147) // 148
-    print("saving" if need_grad else "inference", "tiles/CTA", tiles, {n: f"{v} ({v / max(pc[0], 1):.2f})" for n, v in zip(names, pc)})
-    print("  per tile cycles:", pc[0] // tiles)
+    mn = ["total", "wait_pe", "wait_a_ready", "wait_acc_empty", "wait_w_full", "wait_w_peer", "issue_mma", "commit"]
+    en = ["total", "wait_acc_full", "tmem_ld+bias", "arrive+math+store", "sync+save+a_ready", "next_pe"]
+    print("saving" if need_grad else "inference", "| cycles per tile:", mma[0] // tiles)
+    print("  MMA thread :", {n: f"{v / max(mma[0], 1):.3f}" for n, v in zip(mn, mma)})
+    print("  epilogue w0:", {n: f"{v / max(epi[0], 1):.3f}" for n, v in zip(en, epi)})
