@@ -1,0 +1,64 @@
+"""Multi-process (world_size 2, gloo, CPU) tests of the data-parallel plumbing used at N>1 GPUs: contiguous ray / item
+sharding and the single flat-bucket gradient all-reduce."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, ret):
+    import importlib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    hn = importlib.import_module("nerf-3dtalker-code_b200")
+    r, l, w = hn.dist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+    bucket = hn.dist.GradBucket(lin.parameters())
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lin.parameters())
+    xs = torch.arange(8 * 7, dtype=torch.float32).view(8, 7) / 10.0
+    lo, hi = hn.dist.shard_range(8, rank, world)
+    bucket.zero()
+    lin(xs[lo:hi]).pow(2).sum().backward()                 # accumulates INTO the bucket views
+    flat = bucket.all_reduce(average=False).clone()
+    # reference: single-process gradient over the full batch
+    ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+    ref.load_state_dict(lin.state_dict())
+    ref(xs).pow(2).sum().backward()
+    ref_flat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    ok = torch.allclose(flat, ref_flat, rtol=1e-5, atol=1e-6)
+    mx = hn.dist.max_over_ranks(float(rank + 1), torch.device("cpu"))
+    xy = torch.arange(2 * 2 * 10, dtype=torch.float32).view(2, 2, 10)
+    shard, a, b = hn.dist.shard_rays(xy, rank, world, multiple=2)
+    ret[rank] = (ok, mx, a, b, shard.shape[-1])
+    hn.dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_and_sharding_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] and ret[1][0], "all-reduced flat gradient differs from the single-process gradient"
+    assert ret[0][1] == 2.0 and ret[1][1] == 2.0
+    assert (ret[0][2], ret[0][3], ret[1][2], ret[1][3]) == (0, 6, 6, 10)      # 10 rays = 5 ray pairs -> 3 + 2 pairs
+    assert ret[0][4] + ret[1][4] == 10
+
+
+def test_shard_range_is_a_partition():
+    import importlib
+    hn = importlib.import_module("nerf-3dtalker-code_b200")
+    for n in (1, 2, 7, 8, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [hn.dist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
