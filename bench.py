@@ -165,6 +165,10 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     hn.ops.check_status(net.last_meta["last_status"], "timed region")
 
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return
     peaks = load_peaks()

@@ -278,7 +278,7 @@ class RenderFunction(torch.autograd.Function):
         g_bg = g_bg.contiguous().float()
         # power-of-two loss scale so that half-precision gradient operands stay in range
         gmax = torch.maximum(gF.abs().amax(), g_bg.abs().amax() * 0.0).clamp_min(1e-30)
-        scale = torch.exp2(torch.floor(torch.log2(meta.get("grad_target", 64.0) / gmax))).reshape(1)
+        scale = torch.pow(2.0, torch.floor(torch.log2(meta.get("grad_target", 64.0) / gmax))).reshape(1)
         _, dimg, dsigma, ddelta = _composite_bwd(feat, sigma, delta, None, gF, g_bg, None, ns, image=True,
                                                  grad_scale=scale, want_ddelta=need_cam)
         save_grads = need_w or need_bias
