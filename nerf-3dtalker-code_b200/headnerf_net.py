@@ -114,11 +114,20 @@ class HeadNeRFNet(nn.Module):
 
     # ------------------------------------------------------------------ hot path
     def render_rays(self, mode, batch_xy, audiostyle, shape_code, appea_code, batch_Rmats, batch_Tvecs,
-                    batch_inv_inmats, t_rand=None):
-        """Arbitrary ray sets (no featmap_size constraint): -> F [B,N_r,256], bg_alpha [B,N_r]."""
+                    batch_inv_inmats, t_rand=None, max_chunk_samples=1 << 24):
+        """Arbitrary ray sets (no featmap_size constraint): -> F [B,N_r,256], bg_alpha [B,N_r].
+        Without autograd, rays are processed in chunks of at most `max_chunk_samples` ray*samples so that the per-sample
+        feature tensor ([M,256] fp32) stays bounded: 4M rays x 128 samples would otherwise need 0.5 TB."""
         assert mode in ["train", "test"]
         B, two, n_r = batch_xy.shape
         assert two == 2
+        per_ray = B * self.num_sample_coarse
+        if not torch.is_grad_enabled() and n_r * per_ray > max_chunk_samples and n_r > 2:
+            step = max(2, (max_chunk_samples // per_ray) & ~1)
+            outs = [self.render_rays(mode, batch_xy[:, :, i:i + step].contiguous(), audiostyle, shape_code, appea_code, batch_Rmats,
+                                     batch_Tvecs, batch_inv_inmats, None if t_rand is None else t_rand[:, i:i + step].contiguous(),
+                                     max_chunk_samples) for i in range(0, n_r, step)]
+            return torch.cat([o[0] for o in outs], dim=1), torch.cat([o[1] for o in outs], dim=1)
         if shape_code.shape[1] != self.shape_dims or appea_code.shape[1] != self.appea_dims or audiostyle.shape[1] != 64:
             raise ValueError("latent code dimensions do not match the network")
         ns = self.num_sample_coarse
