@@ -99,23 +99,28 @@ __global__ void __launch_bounds__(kCompThreads) composite_fwd_kernel(hn_composit
     if (lane == 0) a.bg_alpha[ray] = 1.0f - wsum;
 }
 
-// 32 partial values per lane -> lane j receives the sum over lanes of part[j]  (31 shuffles)
-__device__ __forceinline__ float transpose_reduce(float (&part)[32], int lane) {
+// 8 partial values per lane (8 rows) -> the four lanes 4j..4j+3 all receive the full sum of row j  (4+2+1+2 = 9 shuffles).
+// A batch of 8 (instead of 32) rows keeps the register count low enough for 3-4 resident CTAs per SM.
+__device__ __forceinline__ float transpose_reduce8(float (&part)[8], int lane) {
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
+    for (int off = 4; off >= 1; off >>= 1) {              // lane bits 4,3,2 select the row
+        const int lbit = off << 2;
+        const bool up = (lane & lbit) != 0;
 #pragma unroll
         for (int k = 0; k < off; ++k) {
             const float send = up ? part[k] : part[k + off];
             const float keep = up ? part[k + off] : part[k];
-            part[k] = keep + __shfl_xor_sync(kFull, send, off);
+            part[k] = keep + __shfl_xor_sync(kFull, send, lbit);
         }
     }
-    return part[0];
+    float v = part[0];
+    v += __shfl_xor_sync(kFull, v, 2);
+    v += __shfl_xor_sync(kFull, v, 1);
+    return v;
 }
 
 template <int NS, int CV>
-__global__ void __launch_bounds__(kCompThreads) composite_bwd_kernel(hn_composite_bwd_t a, int n_tiles) {
+__global__ void __launch_bounds__(kCompThreads, 3) composite_bwd_kernel(hn_composite_bwd_t a, int n_tiles) {
     constexpr int SPL = NS / 32, C = CV * 128;
     const int lane = threadIdx.x & 31;
     const int ray = blockIdx.x * (kCompThreads / 32) + (threadIdx.x >> 5);
@@ -136,35 +141,43 @@ __global__ void __launch_bounds__(kCompThreads) composite_bwd_kernel(hn_composit
     const float* frow = a.feat + m0 * C + lane * 4;
 #pragma unroll
     for (int i = 0; i < SPL; ++i) {
-        float part[32];
+        float qi = 0.f;
 #pragma unroll
-        for (int ls = 0; ls < 32; ++ls) {
-            const size_t s = i * 32 + ls;
-            const float ws = __shfl_sync(kFull, w[i], ls);
-            float d = 0.f;
+        for (int b8 = 0; b8 < 4; ++b8) {
+            float part[8];
 #pragma unroll
-            for (int k = 0; k < CV; ++k) {
-                const float4 f = ld_stream(frow + s * C + k * 128);
-                d = fmaf(g[k].x, f.x, d); d = fmaf(g[k].y, f.y, d); d = fmaf(g[k].z, f.z, d); d = fmaf(g[k].w, f.w, d);
-                if (a.dfeat) {
-                    float4 o = make_float4(ws * g[k].x, ws * g[k].y, ws * g[k].z, ws * g[k].w);
-                    *reinterpret_cast<float4*>(a.dfeat + (m0 + s) * C + k * 128 + lane * 4) = o;
+            for (int l8 = 0; l8 < 8; ++l8) {
+                const int ls = b8 * 8 + l8;
+                const size_t s = i * 32 + ls;
+                const float ws = __shfl_sync(kFull, w[i], ls);
+                float d = 0.f;
+#pragma unroll
+                for (int k = 0; k < CV; ++k) {
+                    const float4 f = ld_stream(frow + s * C + k * 128);
+                    d = fmaf(g[k].x, f.x, d); d = fmaf(g[k].y, f.y, d); d = fmaf(g[k].z, f.z, d); d = fmaf(g[k].w, f.w, d);
+                    if (a.dfeat) {
+                        float4 o = make_float4(ws * g[k].x, ws * g[k].y, ws * g[k].z, ws * g[k].w);
+                        *reinterpret_cast<float4*>(a.dfeat + (m0 + s) * C + k * 128 + lane * 4) = o;
+                    }
+                    if (a.dfeat_image) {
+                        const float wsc = ws * scale;
+                        const size_t m = m0 + s;
+                        const int kb = (lane >> 4) + 2 * k, col = (lane & 15) * 4;
+                        uint8_t* dst = (uint8_t*)a.dfeat_image + ((size_t)kb * n_tiles + (m >> 7)) * kBlockBytes +
+                                       image_offset((uint32_t)(m & 127), col);
+                        uint2 pk;
+                        pk.x = pack_h2(fminf(fmaxf(wsc * g[k].x, -65504.f), 65504.f), fminf(fmaxf(wsc * g[k].y, -65504.f), 65504.f));
+                        pk.y = pack_h2(fminf(fmaxf(wsc * g[k].z, -65504.f), 65504.f), fminf(fmaxf(wsc * g[k].w, -65504.f), 65504.f));
+                        *reinterpret_cast<uint2*>(dst) = pk;
+                    }
                 }
-                if (a.dfeat_image) {
-                    const float wsc = ws * scale;
-                    const size_t m = m0 + s;
-                    const int kb = (lane >> 4) + 2 * k, col = (lane & 15) * 4;
-                    uint8_t* dst = (uint8_t*)a.dfeat_image + ((size_t)kb * n_tiles + (m >> 7)) * kBlockBytes +
-                                   image_offset((uint32_t)(m & 127), col);
-                    uint2 pk;
-                    pk.x = pack_h2(fminf(fmaxf(wsc * g[k].x, -65504.f), 65504.f), fminf(fmaxf(wsc * g[k].y, -65504.f), 65504.f));
-                    pk.y = pack_h2(fminf(fmaxf(wsc * g[k].z, -65504.f), 65504.f), fminf(fmaxf(wsc * g[k].w, -65504.f), 65504.f));
-                    *reinterpret_cast<uint2*>(dst) = pk;
-                }
+                part[l8] = d;
             }
-            part[ls] = d;
+            const float r = transpose_reduce8(part, lane);           // lanes 4j..4j+3 hold row b8*8 + j
+            const float mine = __shfl_sync(kFull, r, 4 * (lane & 7)); // row b8*8 + (lane % 8)
+            if ((lane >> 3) == b8) qi = mine;
         }
-        q[i] = transpose_reduce(part, lane) - gbg;
+        q[i] = qi - gbg;
         if (a.g_depth && a.zvals) q[i] = fmaf(gdp, __ldg(a.zvals + m0 + i * 32 + lane), q[i]);
     }
 
