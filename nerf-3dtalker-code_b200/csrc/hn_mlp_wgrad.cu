@@ -8,6 +8,7 @@
 // bias gradient (= per-item column sums of dZ, from which the host derives the latent-code and folded
 // weight-column gradients), then flushes once with atomic adds.  The density head rides along as a
 // one-channel pseudo layer (its gradient block is written by hn_mlp_bwd_data).
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include "hn_api.h"
@@ -66,14 +67,21 @@ struct WArgs {
     int* status;
 };
 
+// CL = 1: one CTA per work item.  CL = 3: a cluster of three CTAs works on the three 128-channel chunks of ONE layer over the
+// same samples; every X (layer-input) block is fetched from L2 once per cluster and multicast into all three CTAs' shared
+// memory, which halves the L2->SM traffic that bounds this kernel (~35 B/cycle/SM ingest).
+template <int CL>
 __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ WShared sh;
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
+    const int item0 = (int)blockIdx.x / CL, item_stride = (int)gridDim.x / CL;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
     if (tid == 0) {
-        for (int i = 0; i < kWStages; ++i) { mbar_init(smem_u32(&sh.full[i]), 1); mbar_init(smem_u32(&sh.empty[i]), 1); }
+        for (int i = 0; i < kWStages; ++i) { mbar_init(smem_u32(&sh.full[i]), 1); mbar_init(smem_u32(&sh.empty[i]), CL); }
         mbar_init(smem_u32(&sh.acc_full), 1);
         mbar_init(smem_u32(&sh.acc_empty), 128);
         sh.abort = 0;
@@ -86,6 +94,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
     if (warp == 1) tmem_alloc<512>(smem_u32(&sh.tmem_base));
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                              // peers' barriers exist before any multicast can signal them
     tc_fence_after_sync();
     const uint32_t tmem_base = sh.tmem_base;
 
@@ -93,8 +102,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
         // ======================= producer =======================
         if (lane == 0) {
             uint32_t sc = 0;
-            for (int it = blockIdx.x; it < a.n_items && !sh.abort; it += gridDim.x) {
-                const WItem w = a.items[it];
+            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
+                const WItem w = a.items[it * CL + rank];
                 const uint8_t* gsrc = w.g_dfeat ? a.dfeat_image : a.grads;
                 const uint32_t bytes = (2 + w.n_x) * kHalfBytes;
                 for (int tile = w.tile0; tile < w.tile1; ++tile) {
@@ -106,8 +115,11 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                         const uint32_t dst = smem + stage * kWStageBytes;
                         for (int k = 0; k < 2; ++k)
                             bulk_g2s(dst + k * kHalfBytes, gsrc + ((size_t)(w.g_blk + k) * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
-                        for (int k = 0; k < w.n_x; ++k)
-                            bulk_g2s(dst + (2 + k) * kHalfBytes, a.act + ((size_t)w.x_blk[k] * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
+                        for (int k = 0; k < w.n_x; ++k) {
+                            const uint8_t* xs = a.act + ((size_t)w.x_blk[k] * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes;
+                            if (CL == 1) bulk_g2s(dst + (2 + k) * kHalfBytes, xs, kHalfBytes, fb);
+                            else if (k % CL == (int)rank) bulk_g2s_multicast(dst + (2 + k) * kHalfBytes, xs, kHalfBytes, fb, kMask);
+                        }
                     }
                 }
             }
@@ -117,8 +129,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
         if (lane == 0) {
             uint32_t sc = 0, n_item = 0;
             const uint32_t idesc_bias = umma_idesc(128, 16, kF16, kF16, 1, 0);
-            for (int it = blockIdx.x; it < a.n_items && !sh.abort; it += gridDim.x, ++n_item) {
-                const WItem w = a.items[it];
+            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride, ++n_item) {
+                const WItem w = a.items[it * CL + rank];
                 bool ok = wwait(&sh.acc_empty, (n_item & 1) ^ 1, &sh.abort, a.status, 710);
                 bool first = true;
                 for (int tile = w.tile0; tile < w.tile1 && ok; ++tile) {
@@ -140,7 +152,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                             umma_f16(tmem_base + kBiasCol, ad, umma_desc_kmajor(smem + kWOffOnes, ks), idesc_bias, !(first && ks == 0));
                         }
                         first = false;
-                        umma_commit(smem_u32(&sh.empty[stage]));
+                        if (CL == 1) umma_commit(smem_u32(&sh.empty[stage]));
+                        else umma_commit_multicast(smem_u32(&sh.empty[stage]), kMask);     // a stage is refilled by all peers: all must release it
                     }
                 }
                 umma_commit(smem_u32(&sh.acc_full));
@@ -152,8 +165,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float inv_scale = 1.0f / __ldg(a.grad_scale);
         uint32_t n_item = 0;
-        for (int it = blockIdx.x; it < a.n_items && !sh.abort; it += gridDim.x, ++n_item) {
-            const WItem w = a.items[it];
+        for (int it = item0; it < a.n_items && !sh.abort; it += item_stride, ++n_item) {
+            const WItem w = a.items[it * CL + rank];
             wwait(&sh.acc_full, n_item & 1, &sh.abort, a.status, 720);
             tc_fence_after_sync();
             const bool row_ok = row < w.rows;
@@ -186,44 +199,50 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
 
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                              // peers may still multicast into / signal this CTA
     if (warp == 1) tmem_free<512>(tmem_base);
 }
 
 static std::mutex g_w_mu;
 static bool g_w_ready[64] = {};
 
-// host: enumerate work items
-static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, std::vector<WItem>& items) {
+// host: enumerate work items.  `cluster` = items for the 3-CTA multicast kernel (three consecutive entries = the three
+// 128-channel chunks of one layer over one sample range); `single` = everything else.
+static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters, std::vector<WItem>& cluster, std::vector<WItem>& single) {
     const int tiles_per_item = (int)(((int64_t)a.n_rays * a.n_samples) / HN_TILE);
-    const bool want_w = false || [&] { for (int i = 0; i < 12; ++i) if (a.dw[i]) return true; return false; }();
+    bool want_w = false;
+    for (int i = 0; i < 12; ++i) want_w = want_w || (a.dw[i] != nullptr);
     struct LayerW { int w_idx; int n_out; int g_blk; int g_dfeat; int bias_off; int x_slot; int n_xblk; bool pe; int x_col0; };
     std::vector<LayerW> layers;
-    for (int l = 0; l < 8; ++l) {
-        LayerW L{l, HN_HIDDEN, HN_GSLOT_Z0 + 6 * l, 0, l * HN_HIDDEN, l == 0 ? -1 : HN_SLOT_H0 + 6 * (l - 1), l == 0 ? 0 : 6,
-                 l == 0 || l == 5, l == 5 ? a.l5_hidden_col : 0};
-        layers.push_back(L);
-    }
+    for (int l = 0; l < 8; ++l)
+        layers.push_back({l, HN_HIDDEN, HN_GSLOT_Z0 + 6 * l, 0, l * HN_HIDDEN, l == 0 ? -1 : HN_SLOT_H0 + 6 * (l - 1), l == 0 ? 0 : 6,
+                          l == 0 || l == 5, l == 5 ? a.l5_hidden_col : 0});
     layers.push_back({W_R0, HN_HIDDEN, HN_GSLOT_R0, 0, HN_BIAS_OFF_R0, HN_SLOT_H0 + 6 * 7, 6, false, 0});
     layers.push_back({W_R1, HN_RGB1, HN_GSLOT_R1, 0, HN_BIAS_OFF_R1, HN_SLOT_R0, 6, false, 0});
     layers.push_back({W_R2, HN_FEAT, 0, 1, HN_BIAS_OFF_R2, HN_SLOT_X, 3, false, 0});
-    layers.push_back({W_DENSITY, 1, HN_GSLOT_R1 + 3, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});   // density pseudo layer
-    // how many (layer, chunk) pairs are active -> choose splits so that there are ~2 items per SM
-    int pairs = 0;
+    layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});   // density pseudo layer
+    auto active = [&](const LayerW& L) { return want_w || L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1; };
+    auto clustered = [&](const LayerW& L) { return want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
+    int pairs_single = 0, layers_cluster = 0;
     for (const LayerW& L : layers) {
-        const bool folded = (L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1);
-        if (!want_w && !folded) continue;
-        pairs += (L.n_out + 127) / 128;
+        if (!active(L)) continue;
+        if (clustered(L)) ++layers_cluster; else pairs_single += (L.n_out + 127) / 128;
     }
-    if (pairs == 0) return;
-    int splits = (2 * n_sm + pairs * a.B - 1) / (pairs * a.B);
-    if (splits < 1) splits = 1;
-    if (splits > tiles_per_item) splits = tiles_per_item;
+    auto pick = [&](int units, int workers) {
+        if (units == 0) return 1;
+        int sp = (2 * workers + units * a.B - 1) / (units * a.B);
+        return sp < 1 ? 1 : (sp > tiles_per_item ? tiles_per_item : sp);
+    };
+    const int splits_c = pick(layers_cluster, n_clusters), splits_s = pick(pairs_single, n_sm);
     for (const LayerW& L : layers) {
-        const bool folded = (L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1);
-        if (!want_w && !folded) continue;
-        for (int j = 0; j * 128 < L.n_out; ++j) {
-            for (int b = 0; b < a.B; ++b) {
-                for (int sp = 0; sp < splits; ++sp) {
+        if (!active(L)) continue;
+        const bool cl = clustered(L);
+        const int splits = cl ? splits_c : splits_s;
+        std::vector<WItem>& out = cl ? cluster : single;
+        // cluster items: chunk index innermost (three consecutive entries share layer, item and sample range)
+        for (int b = 0; b < a.B; ++b)
+            for (int sp = 0; sp < splits; ++sp)
+                for (int j = 0; j * 128 < L.n_out; ++j) {
                     WItem w{};
                     w.w_idx = (int16_t)((want_w && a.dw[L.w_idx]) ? L.w_idx : -1);
                     w.row0 = (int16_t)(128 * j);
@@ -240,12 +259,28 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, std::vector<WIt
                         if (L.pe) { w.x_blk[n] = HN_SLOT_PE; w.x_col[n] = 0; w.x_valid[n] = HN_PE; ++n; }
                     }
                     w.n_x = (int16_t)n;
-                    if (w.tile1 > w.tile0) items.push_back(w);
+                    if (w.tile1 > w.tile0) out.push_back(w);
                 }
-            }
-        }
     }
 }
+
+static int launch_wgrad(const WArgs& k, int cl, int grid, cudaStream_t st) {
+    if (cl == 1) {
+        mlp_wgrad_kernel<1><<<grid, kWThreads, kWgradSmem, st>>>(k);
+        return check_launch("hn_mlp_bwd_weights");
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kWThreads); cfg.dynamicSmemBytes = kWgradSmem; cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 3; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_wgrad_kernel<3>, k);
+    if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+    return check_launch("hn_mlp_bwd_weights (3-CTA clusters)");
+}
+
+static int g_w_clusters[64] = {};
 
 }  // namespace hn
 
@@ -261,33 +296,56 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     {
         std::lock_guard<std::mutex> lk(g_w_mu);
         if (dev < 64 && !g_w_ready[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
+            cudaError_t e = cudaFuncSetAttribute(mlp_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
             if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+            // how many 3-CTA clusters can be resident at once (GPC sizes strand a few SMs)
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(3 * 49); cfg.blockDim = dim3(kWThreads); cfg.dynamicSmemBytes = kWgradSmem;
+            cudaLaunchAttribute attr{};
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 3; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            int n = 0;
+            const char* env = getenv("HN_WGRAD_CLUSTERS");
+            if (env && atoi(env) == 0) n = 0;
+            else if (cudaOccupancyMaxActiveClusters(&n, mlp_wgrad_kernel<3>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+            g_w_clusters[dev] = n;
             g_w_ready[dev] = true;
         }
     }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    std::vector<WItem> items;
-    build_items(*a, n_sm, items);
-    if (items.empty()) return HN_OK;
-    if (items.size() * sizeof(WItem) > a->items_workspace_bytes)
+    const int n_clusters = dev < 64 ? g_w_clusters[dev] : 0;
+    std::vector<WItem> cluster, single;
+    build_items(*a, n_sm, n_clusters, cluster, single);
+    if (cluster.empty() && single.empty()) return HN_OK;
+    if ((cluster.size() + single.size()) * sizeof(WItem) > a->items_workspace_bytes)
         return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: items workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    std::vector<WItem> all(cluster);
+    all.insert(all.end(), single.begin(), single.end());
     // the item table is tiny (<100 KiB); pageable -> device copy is stream-ordered and returns after staging
-    cudaError_t e = cudaMemcpyAsync(a->items_workspace, items.data(), items.size() * sizeof(WItem), cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(a->items_workspace, all.data(), all.size() * sizeof(WItem), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
     WArgs k{};
     k.act = (const uint8_t*)a->act; k.grads = (const uint8_t*)a->grads; k.dfeat_image = (const uint8_t*)a->dfeat_image;
     k.grad_scale = a->grad_scale;
     for (int i = 0; i < 12; ++i) { k.dw[i] = a->dw[i]; k.ld[i] = a->ld[i]; }
     k.dbias = a->dbias;
-    k.items = (const WItem*)a->items_workspace; k.n_items = (int)items.size();
     k.n_tiles = (int)(total_samples(a->B, a->n_rays, a->n_samples) / HN_TILE);
     k.status = a->status;
-    const int grid = k.n_items < n_sm ? k.n_items : n_sm;
-    mlp_wgrad_kernel<<<grid, kWThreads, kWgradSmem, st>>>(k);
-    return check_launch("hn_mlp_bwd_weights");
+    if (!cluster.empty()) {
+        k.items = (const WItem*)a->items_workspace; k.n_items = (int)cluster.size() / 3;
+        const int nc = k.n_items < n_clusters ? k.n_items : n_clusters;
+        if (int rc = launch_wgrad(k, 3, 3 * nc, st)) return rc;
+    }
+    if (!single.empty()) {
+        k.items = (const WItem*)a->items_workspace + cluster.size(); k.n_items = (int)single.size();
+        const int grid = k.n_items < n_sm ? k.n_items : n_sm;
+        if (int rc = launch_wgrad(k, 1, grid, st)) return rc;
+    }
+    return HN_OK;
 }
 
 extern "C" size_t hn_wgrad_workspace_bytes(int B) {
