@@ -58,8 +58,8 @@ class KernelTimer:
 TIMER = KernelTimer()
 
 
-def _call(name, fn, *args):
-    TIMER.launches += 1
+def _call(name, fn, *args, kernels=1):
+    TIMER.launches += kernels                  # kernels launched by this library call
     if TIMER.enabled:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -314,7 +314,8 @@ class RenderFunction(torch.autograd.Function):
                 w.ld[i] = wt.numel() // wt.shape[0]
             w.l5_hidden_col = meta["l5_hidden_col"]
             w.dbias, w.status = _ptr(dbias), _ptr(status)
-            _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream())
+            # with weight gradients the library launches two kernels: 3-CTA clusters for the 384-wide layers, then the rest
+            _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=2 if need_w else 1)
         if _DEBUG_SYNC:
             check_status(status, "hn_mlp_bwd")
         meta["last_status"] = status

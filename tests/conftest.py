@@ -16,8 +16,11 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def hn():
-    """The product package (directory name has hyphens, so it is imported by path)."""
-    return importlib.import_module("nerf-3dtalker-code_b200")
+    """The product package (directory name has hyphens, so it is imported by path).  Builds the CUDA library with nvcc
+    if it is missing or stale (the build is a cross-compile: no GPU needed)."""
+    mod = importlib.import_module("nerf-3dtalker-code_b200")
+    mod.build_library()
+    return mod
 
 
 @pytest.fixture(scope="session")
