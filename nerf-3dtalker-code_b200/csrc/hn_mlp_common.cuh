@@ -59,6 +59,9 @@ __device__ __forceinline__ void warp_arrive_leader(uint32_t bar, int lane) {
 template <bool PAIR> __device__ __forceinline__ void umma_x(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, bool acc) {
     if (PAIR) umma_f16_pair(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
 }
+template <bool PAIR> __device__ __forceinline__ void umma_lohi_x(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma_f16_pair_lohi(d, a_lo, b_lo, idesc, acc); else umma_f16_lohi(d, a_lo, b_lo, idesc, acc);
+}
 template <bool PAIR> __device__ __forceinline__ void umma_commit_x(uint32_t bar) {
     if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
 }

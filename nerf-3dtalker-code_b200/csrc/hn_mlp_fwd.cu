@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                         mbar_arrive_cluster(smem_u32(&sh.w_peer[stage]), 0);
                     }
             }
-        } else if (lane == 0) {
+        } else {
+            // the whole warp walks the schedule (uniform control flow keeps descriptors in uniform registers); one
+            // elected lane issues the MMAs and commits
             uint32_t uc = 0, par_ready = 0, par_pe = 0, par_empty = 0;
             HN_PC_DECL(pc, 8);
             for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
@@ -174,15 +176,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                     const uint32_t b_addr = smem + kOffW + stage * STAGE_BYTES;
                     const uint32_t idesc = umma_idesc(PAIR ? 256 : 128, (uint32_t)op.n8 * 8, kF16, kF16, 0, 0);
                     const uint32_t d_addr = tmem_base + (uint32_t)op.tmem_col8 * 8;
-                    for (int k = 0; k < op.nkb; ++k) {
+                    const uint32_t a_lo = desc_lo(a_addr, 16), b_lo = desc_lo(b_addr, 16);
+                    const uint32_t first = op.first, nkb = op.nkb;
+                    if (elect_one()) {
+                        for (uint32_t k = 0; k < nkb; ++k) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_x<PAIR>(d_addr, umma_desc_kmajor(a_addr + k * kUnitBytes, ks), umma_desc_kmajor(b_addr + k * KB_STRIDE, ks), idesc,
-                                         !(op.first && k == 0 && ks == 0));
+                            for (uint32_t ks = 0; ks < 4; ++ks)
+                                umma_lohi_x<PAIR>(d_addr, a_lo + k * (kUnitBytes >> 4) + ks * 2, b_lo + k * (KB_STRIDE >> 4) + ks * 2, idesc,
+                                                  (first && k == 0 && ks == 0) ? 0u : 1u);
+                        }
+                        HN_PC_LAP(pc, 6);
+                        umma_commit_x<PAIR>(smem_u32(&sh.w_empty[stage]));
+                        if (op.commit) umma_commit_x<PAIR>(smem_u32(&sh.acc_full[op.q]));
                     }
-                    HN_PC_LAP(pc, 6);
-                    umma_commit_x<PAIR>(smem_u32(&sh.w_empty[stage]));
-                    if (op.commit) umma_commit_x<PAIR>(smem_u32(&sh.acc_full[op.q]));
+                    __syncwarp();
                     HN_PC_LAP(pc, 7);
                     op = nxt;
                 }

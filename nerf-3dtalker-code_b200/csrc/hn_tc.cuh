@@ -168,6 +168,30 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// Split descriptor form for issue loops: the high word of a SWIZZLE_128B descriptor with SBO = 1024 is a constant, the
+// low word is (address >> 4) | (LBO >> 4) << 16, and stepping K by 16 elements adds 2 (K-major, 32 B) or 128 (MN-major,
+// 2 KiB) to it.  Keeping both words in (uniform) 32-bit registers makes an MMA issue a handful of instructions.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);          // 0x40004040
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a cluster (one TPC) run one MMA of M = 256: CTA r supplies A rows [128r, 128r+128) and B rows
 // [N/2*r, N/2*r+N/2) from the SAME shared-memory offsets, and receives accumulator rows [128r, 128r+128) in its
