@@ -122,6 +122,14 @@ __device__ __forceinline__ void store_row32(uint32_t base, int row, int col0, co
     }
 }
 
+// same, from 16 already packed f16 pairs (columns [col0, col0+32))
+__device__ __forceinline__ void store_row_packed(uint32_t base, int row, int col0, const uint32_t (&p)[16]) {
+    const uint32_t blk = base + (col0 >> 6) * kBlockBytes + (row >> 3) * 1024 + (row & 7) * 128;
+    const int ch0 = (col0 & 63) >> 3, rsw = row & 7;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st_shared_v4(blk + (((ch0 + c) ^ rsw) << 4), p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+}
+
 // bit i of the result = (y[i] > 0) (sign-bit funnel shifts: one instruction per element; +0.0 counts as positive).
 // Four independent 8-deep chains instead of one 32-deep dependency chain.
 __device__ __forceinline__ uint32_t positive_mask32(const float (&y)[32]) {

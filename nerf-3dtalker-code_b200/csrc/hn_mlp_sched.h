@@ -72,7 +72,42 @@ constexpr int kFwdEpis = 31;
 constexpr int kBwdUnitsMax = 176;
 constexpr int kBwdEpisMax = 36;
 
-struct FwdTables { MmaOp mma[kFwdUnits]; EpiOp epi[kFwdEpis]; int n_ops; int pe_after_epi; int n_ready[3]; int n_empty[4]; };
+// ---- forward chain, second generation: the A operand (activations) lives in TENSOR MEMORY.
+// TMEM (512 columns) is managed as eight 64-column slots.  A 128-wide accumulator chunk takes an aligned slot pair;
+// its epilogue packs the 128 fp32 columns to 64 columns of f16 pairs (two 64-wide K blocks of the next GEMM) and
+// stores them into a free slot, or in place over the first slot of its own accumulator.  The slot of every chunk is
+// chosen on the host by a small allocator that knows the only two ordering facts the kernel provides:
+//   (a) tcgen05.mma instructions execute in issue order (a later MMA may overwrite what an earlier one read);
+//   (b) the MMA issuer waits, before chunk n, for the epilogue of chunk n-2 to have drained its accumulator, and
+//       epilogue stores of chunk n are ordered after the accumulator loads of every chunk <= n (per lane quarter).
+// Chunks are computed N-outer (one chunk over all its K blocks, then the next), so the weight units stream in
+// (layer, chunk, K block) order, one 16 KiB unit per ring stage.
+constexpr uint16_t kSrcSmem = 0x8000;   // MmaOp2::a_src flag: K block comes from shared memory (low bits: block index)
+constexpr uint16_t kNoCol = 0xFFFF;
+
+struct MmaOp2 {
+    uint16_t a_src;                // TMEM column of the 32-column A K block, or kSrcSmem | shared-memory block
+    uint16_t acc_col;              // TMEM column of the accumulator chunk
+    uint8_t n8;                    // MMA N / 8
+    uint8_t first;                 // 1: first K block of the chunk (wait for the accumulator, overwrite it)
+    uint8_t commit;                // 1: last K block of the chunk -> acc_full
+    uint8_t wait_src;              // 0 none, 1..3 a_ready[c-1], 4 pe_ready
+};
+
+struct EpiOp2 {
+    uint16_t acc_col;              // TMEM column of the accumulator chunk
+    uint16_t out_col;              // TMEM column of the packed output (64 columns per 128 outputs), kNoCol = none
+    uint8_t width32;               // columns / 32
+    uint8_t kind;
+    uint8_t ready_idx;             // a_ready barrier to arrive on, 255 = none
+    uint8_t density;               // 1 accumulate density dot, 2 = also finish it
+    uint16_t bias_off;
+    uint16_t col0;                 // first logical output column of this chunk
+    uint16_t save_blk;             // first block of the save slot, 0xFFFF = none
+    uint16_t mask_word;            // word offset in the per-sample mask row, 0xFFFF = none
+};
+
+struct FwdTables { MmaOp2 mma[kFwdUnits]; EpiOp2 epi[kFwdEpis]; int n_ops; int pe_after_epi; int n_ready[3]; };
 struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_ops; int n_epis; int n_ready[3]; int n_empty[4]; };
 
 struct HostSchedules {

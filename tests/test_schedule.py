@@ -26,7 +26,7 @@ def dump():
         out = subprocess.run([exe] + ([which] if which != "fwd" else []), check=True, capture_output=True, text=True).stdout
         mma, epi = [], []
         for line in out.splitlines():
-            kv = dict(re.findall(r"(\w+) (-?\d+)", line.split("|")[0]))
+            kv = dict(re.findall(r"(\w+) (-?\d+)", line.replace("|", " ")))
             if line.startswith("U "):
                 mma.append({k: int(v) for k, v in kv.items()})
             elif line.startswith("E "):
@@ -35,7 +35,95 @@ def dump():
     return run
 
 
-@pytest.mark.parametrize("which", ["fwd", "bwd"])
+def _replay_fwd(mma, epi, n_tiles, late):
+    """Replays the forward chain (A operand in tensor memory) against the two ordering facts the kernel provides
+    (MMAs execute in issue order; chunk n's MMAs wait for the accumulator loads of chunk n-2; epilogue stores of chunk n
+    follow the loads of every chunk <= n) with the epilogues running as EARLY or as LATE as those facts allow, tagging
+    every 32-column TMEM block with what was last written there.  Asserts that every MMA reads the K block it expects
+    and every epilogue drains its own, unclobbered accumulator."""
+    tm = {}                                           # 32-column block -> tag
+    n_chunks = len(epi)
+    loads_done = stores_done = 0                      # global epilogue progress (chunk counters)
+    commits = 0
+    ready = [0, 0, 0]; ready_used = [0, 0, 0]
+
+    def epi_load(n):
+        t, e = divmod(n, n_chunks)
+        op = epi[e]
+        for c in range(op["acc_col"], op["acc_col"] + op["width"], 32):
+            assert tm.get(c) == ("acc", n), f"epilogue {e} (tile {t}) finds {tm.get(c)} at column {c}"
+
+    def epi_store(n):
+        t, e = divmod(n, n_chunks)
+        op = epi[e]
+        if op["out_col"] >= 0:
+            for h in range(op["width"] // 64):
+                tm[op["out_col"] + 32 * h] = ("act", n, h)
+        if op["ready"] != 255:
+            ready[op["ready"]] += 1
+
+    def run_epilogues(until_loads, until_stores):
+        nonlocal loads_done, stores_done
+        while loads_done < until_loads or stores_done < until_stores:
+            if stores_done < loads_done:              # a warp stores chunk n before it loads chunk n+1
+                epi_store(stores_done); stores_done += 1
+            else:
+                assert loads_done < commits, "epilogue would wait for an accumulator that is never committed"
+                epi_load(loads_done); loads_done += 1
+
+    for t in range(n_tiles):
+        chunk = t * n_chunks
+        # producer chunk of every a_src column is whatever tag sits there when the layer's first chunk reads it; later
+        # chunks of the same layer must see the very same tags
+        seen = {}
+        for u, m in enumerate(mma):
+            if m["wait_src"] in (1, 2, 3):
+                c = m["wait_src"] - 1
+                ready_used[c] += 1
+                # the MMA issuer blocks until that epilogue has stored: force exactly as much epilogue progress as needed
+                while ready[c] < ready_used[c]:
+                    run_epilogues(min(stores_done + 1, commits), stores_done + 1)
+            if m["first"] and chunk >= 2:
+                run_epilogues(chunk - 1, stores_done)  # accumulator loads of chunk n-2 done
+            if not late:
+                run_epilogues(commits, commits)
+            if not m["smem"]:
+                tag = tm.get(m["a_src"])
+                assert tag is not None and tag[0] == "act", f"MMA unit {u} (tile {t}) reads {tag} at column {m['a_src']}"
+                seen.setdefault((layer_first_of(mma, u), m["a_src"]), tag)
+                assert seen[(layer_first_of(mma, u), m["a_src"])] == tag, f"MMA unit {u}: K block at column {m['a_src']} changed under the layer"
+            for c in range(m["acc_col"], m["acc_col"] + m["n"], 32):
+                tm[c] = ("acc", chunk)
+            if m["commit"]:
+                commits += 1
+                chunk += 1
+    run_epilogues(commits, commits)
+
+
+def layer_first_of(mma, u):
+    """index of the first unit of the layer that unit u belongs to (layers start where a_ready[0] / pe_ready is awaited)"""
+    while not (mma[u]["wait_src"] in (1, 4) and mma[u]["first"]):
+        u -= 1
+    return u
+
+
+@pytest.mark.parametrize("late", [False, True])
+def test_forward_tmem_schedule(dump, late):
+    mma, epi = dump("fwd")
+    assert len(mma) == 168 and len(epi) == 31
+    for c in range(3):
+        arrivals = sum(1 for e in epi if e["ready"] == c)
+        waits = sum(1 for m in mma if m["wait_src"] == 1 + c)
+        assert arrivals == waits, f"a_ready[{c}]: {arrivals} arrivals vs {waits} waits"
+    assert sum(m["commit"] for m in mma) == len(epi) and sum(m["first"] for m in mma) == len(epi)
+    # every layer's K blocks come from the previous layer's chunks in order (chunk j -> K blocks 2j, 2j+1)
+    _replay_fwd(mma, epi, 3, late)
+    # weight units follow the (layer, chunk, K block) stream
+    for u, m in enumerate(mma):
+        assert m["vr"] == m["n"] and m["row0"] % 128 == 0
+
+
+@pytest.mark.parametrize("which", ["bwd"])
 def test_schedule_protocol(dump, which):
     mma, epi = dump(which)
     assert mma and epi

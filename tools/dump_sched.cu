@@ -3,18 +3,38 @@
 #include <cstring>
 #include "../nerf-3dtalker-code_b200/csrc/hn_mlp_sched.h"
 using namespace hn;
+static void print_pack(const PackOp& p) {
+    printf(" | w %d T %d l5 %d row0 %d col0 %d vr %d vc %d\n", p.w_idx, p.transposed, p.l5_hidden, p.row0, p.col0, p.valid_r, p.valid_c);
+}
 int main(int argc, char** argv) {
     const HostSchedules& hs = host_schedules();
     const bool bwd = argc > 1 && !strcmp(argv[1], "bwd");
-    const int nu = bwd ? hs.bwd.n_ops : hs.fwd.n_ops, ne = bwd ? hs.bwd.n_epis : kFwdEpis;
-    const MmaOp* mma = bwd ? hs.bwd.mma : hs.fwd.mma;
-    const EpiOp* epi = bwd ? hs.bwd.epi : hs.fwd.epi;
-    const PackOp* pk = bwd ? hs.bwd_pack : hs.fwd_pack;
+    if (!bwd) {
+        // forward chain: A operand in tensor memory (MmaOp2 / EpiOp2)
+        printf("units %d epis %d pe_after %d\n", hs.fwd.n_ops, kFwdEpis, hs.fwd.pe_after_epi);
+        for (int u = 0; u < hs.fwd.n_ops; ++u) {
+            const MmaOp2& m = hs.fwd.mma[u];
+            printf("U %d smem %d a_src %d acc_col %d n %d first %d commit %d wait_src %d", u, (m.a_src & kSrcSmem) ? 1 : 0, m.a_src & 0x7FFF, m.acc_col,
+                   m.n8 * 8, m.first, m.commit, m.wait_src);
+            print_pack(hs.fwd_pack[u]);
+        }
+        for (int e = 0; e < kFwdEpis; ++e) {
+            const EpiOp2& o = hs.fwd.epi[e];
+            printf("E %d acc_col %d out_col %d width %d kind %d ready %d density %d bias_off %d col0 %d save_blk %d mask_word %d\n", e, o.acc_col,
+                   o.out_col == kNoCol ? -1 : (int)o.out_col, o.width32 * 32, o.kind, o.ready_idx, o.density, o.bias_off, o.col0, o.save_blk, o.mask_word);
+        }
+        return 0;
+    }
+    const int nu = hs.bwd.n_ops, ne = hs.bwd.n_epis;
+    const MmaOp* mma = hs.bwd.mma;
+    const EpiOp* epi = hs.bwd.epi;
+    const PackOp* pk = hs.bwd_pack;
     printf("units %d epis %d\n", nu, ne);
-    for (int u = 0; u < nu; ++u)
-        printf("U %d unit %d nkb %d a_blk %d n %d col %d q %d first %d commit %d wait_src %d wait_empty %d | w %d T %d l5 %d row0 %d col0 %d vr %d vc %d\n",
-               u, mma[u].unit, mma[u].nkb, mma[u].a_blk, mma[u].n8 * 8, mma[u].tmem_col8 * 8, mma[u].q, mma[u].first, mma[u].commit, mma[u].wait_src, mma[u].wait_empty,
-               pk[mma[u].unit].w_idx, pk[mma[u].unit].transposed, pk[mma[u].unit].l5_hidden, pk[mma[u].unit].row0, pk[mma[u].unit].col0, pk[mma[u].unit].valid_r, pk[mma[u].unit].valid_c);
+    for (int u = 0; u < nu; ++u) {
+        printf("U %d unit %d nkb %d a_blk %d n %d col %d q %d first %d commit %d wait_src %d wait_empty %d",
+               u, mma[u].unit, mma[u].nkb, mma[u].a_blk, mma[u].n8 * 8, mma[u].tmem_col8 * 8, mma[u].q, mma[u].first, mma[u].commit, mma[u].wait_src, mma[u].wait_empty);
+        print_pack(pk[mma[u].unit]);
+    }
     for (int e = 0; e < ne; ++e)
         printf("E %d q %d col %d width %d kind %d dst_blk %d ready %d density %d bias_off %d col0 %d save_blk %d mask_word %d\n",
                e, epi[e].q, epi[e].tmem_col8 * 8, epi[e].width32 * 32, epi[e].kind, epi[e].dst_blk, epi[e].ready_idx, epi[e].density,
