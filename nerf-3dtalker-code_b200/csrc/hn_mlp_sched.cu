@@ -144,7 +144,7 @@ struct SlotSim {
 
 struct Fwd2Layer { int w_idx; bool pe; int n_kb; int widths[3]; int n_chunks; EpiKind kind; int bias_off; int save_blk; int mask_word; bool l5_hidden; int density; bool to_tmem; };
 
-struct Chunk2 { int acc_slot; int acc_slots; int out_slot; };
+struct Chunk2 { int acc_slot; int acc_slots; int out_slot; int wait_prev; };
 
 // returns false if `fixed` (when given) violates a hazard rule from the initial state `sim`
 bool run_slots(const std::vector<Fwd2Layer>& layers, SlotSim& sim, int n0, std::vector<Chunk2>& table, bool fixed) {
@@ -188,6 +188,9 @@ bool run_slots(const std::vector<Fwd2Layer>& layers, SlotSim& sim, int n0, std::
             }
             if (c.out_slot >= 0 && !(c.out_slot >= c.acc_slot && c.out_slot < c.acc_slot + need)) {
                 if (!sim.ok_out(c.out_slot, n)) return false;
+                const int wp = (sim.kind[c.out_slot] == 2 && sim.rel_n[c.out_slot] == n - 1) ? 1 : 0;
+                if (fixed && wp && !c.wait_prev) return false;
+                if (!fixed) c.wait_prev = wp;
                 sim.kind[c.out_slot] = 0;
             }
             for (int k = 0; k < need; ++k)
@@ -266,6 +269,7 @@ void build_fwd2(HostSchedules* hs) {
             e.kind = L.kind;
             e.ready_idx = L.to_tmem ? (uint8_t)j : 255;
             e.density = (uint8_t)(L.density ? (j == L.n_chunks - 1 ? 2 : 1) : 0);
+            e.wait_prev = (uint8_t)c.wait_prev;
             e.bias_off = (uint16_t)(L.bias_off + 128 * j);
             e.col0 = (uint16_t)(128 * j);
             e.save_blk = L.save_blk < 0 ? 0xFFFF : (uint16_t)(L.save_blk + 2 * j);

@@ -78,8 +78,10 @@ constexpr int kBwdEpisMax = 36;
 // stores them into a free slot, or in place over the first slot of its own accumulator.  The slot of every chunk is
 // chosen on the host by a small allocator that knows the only two ordering facts the kernel provides:
 //   (a) tcgen05.mma instructions execute in issue order (a later MMA may overwrite what an earlier one read);
-//   (b) the MMA issuer waits, before chunk n, for the epilogue of chunk n-2 to have drained its accumulator, and
-//       epilogue stores of chunk n are ordered after the accumulator loads of every chunk <= n (per lane quarter).
+//   (b) the MMA issuer waits, before chunk n, for the epilogue of chunk n-2 to have drained its accumulator; the
+//       epilogue warps form two groups that take alternate chunks, so the stores of chunk n are ordered after the
+//       accumulator loads of chunk n (own group barrier) and of every chunk <= n-2 (through (a) and acc_full of n);
+//       a store into a slot drained by chunk n-1 (the other group) first waits for that group (EpiOp2::wait_prev).
 // Chunks are computed N-outer (one chunk over all its K blocks, then the next), so the weight units stream in
 // (layer, chunk, K block) order, one 16 KiB unit per ring stage.
 constexpr uint16_t kSrcSmem = 0x8000;   // MmaOp2::a_src flag: K block comes from shared memory (low bits: block index)
@@ -101,6 +103,8 @@ struct EpiOp2 {
     uint8_t kind;
     uint8_t ready_idx;             // a_ready barrier to arrive on, 255 = none
     uint8_t density;               // 1 accumulate density dot, 2 = also finish it
+    uint8_t wait_prev;             // 1: the output slot was drained by chunk n-1: wait for the other group's loads
+    uint8_t pad;
     uint16_t bias_off;
     uint16_t col0;                 // first logical output column of this chunk
     uint16_t save_blk;             // first block of the save slot, 0xFFFF = none

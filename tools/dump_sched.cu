@@ -20,8 +20,8 @@ int main(int argc, char** argv) {
         }
         for (int e = 0; e < kFwdEpis; ++e) {
             const EpiOp2& o = hs.fwd.epi[e];
-            printf("E %d acc_col %d out_col %d width %d kind %d ready %d density %d bias_off %d col0 %d save_blk %d mask_word %d\n", e, o.acc_col,
-                   o.out_col == kNoCol ? -1 : (int)o.out_col, o.width32 * 32, o.kind, o.ready_idx, o.density, o.bias_off, o.col0, o.save_blk, o.mask_word);
+            printf("E %d acc_col %d out_col %d width %d kind %d ready %d density %d wait_prev %d bias_off %d col0 %d save_blk %d mask_word %d\n", e, o.acc_col,
+                   o.out_col == kNoCol ? -1 : (int)o.out_col, o.width32 * 32, o.kind, o.ready_idx, o.density, o.wait_prev, o.bias_off, o.col0, o.save_blk, o.mask_word);
         }
         return 0;
     }

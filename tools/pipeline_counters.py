@@ -16,10 +16,10 @@ for need_grad in (False, True):
     torch.cuda.synchronize()
     st = net.last_meta["last_status"].cpu()
     mma = st[2:18].view(torch.int64).tolist()
-    epi = st[18:30].view(torch.int64).tolist()
+    epi = st[18:50].view(torch.int64).tolist()
     tiles = (2 * 4096 * 64 // 128 + 147) // 148
-    mn = ["total", "wait_pe", "wait_a_ready", "wait_acc_empty", "wait_w_full", "wait_w_peer", "issue_mma", "commit"]
-    en = ["total", "wait_acc_full", "tmem_ld+bias", "arrive+math+store", "sync+save+a_ready", "next_pe"]
+    mn = ["total", "wait_pe", "wait_a_ready", "wait_acc_empty", "wait_w_full", "-", "issue_mma", "commit"]
+    en = ["total", "wait_acc_full", "tmem_ld+bias", "quarter_sync+acc_empty", "wait_stg_free", "feat_store/rest", "a_ready_arrive", "next_pe", "masks", "density+pack", "tmem_st", "stage_st", "tmem_st_wait", "density_fin", "fence+stg_full", "-"]
     print("saving" if need_grad else "inference", "| cycles per tile:", mma[0] // tiles)
     print("  MMA thread :", {n: f"{v / max(mma[0], 1):.3f}" for n, v in zip(mn, mma)})
-    print("  epilogue w0:", {n: f"{v / max(epi[0], 1):.3f}" for n, v in zip(en, epi)})
+    print("  epilogue w0 (cycles/op):", {n: int(v / tiles / 31) for n, v in zip(en, epi)})
