@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libheadnerf_b200.so")
+# HN_LIB_PATH: load an experimental build of the SAME library (profiling variants under build/); never a fallback
+LIB_PATH = os.environ.get("HN_LIB_PATH") or os.path.join(_PKG, "libheadnerf_b200.so")
 
 HIDDEN, FEAT, RGB1, PE, TILE = 384, 256, 192, 63, 128
 BIAS_OFF_R0, BIAS_OFF_R1, BIAS_OFF_R2, BIAS_OFF_DENSITY, BIAS_STRIDE = 3072, 3456, 3648, 3904, 3920

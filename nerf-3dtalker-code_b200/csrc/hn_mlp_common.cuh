@@ -82,6 +82,37 @@ template <bool PAIR> __device__ __forceinline__ void umma_commit_x(uint32_t bar)
 #define HN_PC_FLUSH(v, n, dst, cond) do {} while (0)
 #endif
 
+// Hot-path wait: bounded spin on try_wait only (no clock reads, no flag polling inside the loop).  A try_wait that fails
+// returns after a hardware-defined time of the order of a microsecond, so the bound is several seconds: a protocol bug
+// surfaces as a status code instead of a hung GPU, and a healthy run pays two instructions per wait.
+__device__ __forceinline__ bool wait_spin(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
+    const uint32_t b = smem_u32(bar);
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 24); ++i) {
+        if (mbar_try_wait(b, parity)) return true;
+        if ((i & 1023u) == 1023u && *abort_flag) return false;
+    }
+    *abort_flag = 1;
+    atomicCAS(status, 0, code);
+    return false;
+}
+
+// Wait of a role that expects to wait long (epilogue warps for an accumulator, producers for a free ring stage, the saver):
+// polls with a pause.  Every mbarrier operation of the CTA goes through one synchronisation unit; a dozen warps polling
+// back-to-back keep it saturated and every arrive / try_wait of the MMA issuer queues behind them.
+__device__ __forceinline__ bool wait_backoff(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
+    const uint32_t b = smem_u32(bar);
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 22); ++i) {
+        if (mbar_try_wait(b, parity)) return true;
+        __nanosleep(100);
+        if ((i & 255u) == 255u && *abort_flag) return false;
+    }
+    *abort_flag = 1;
+    atomicCAS(status, 0, code);
+    return false;
+}
+
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

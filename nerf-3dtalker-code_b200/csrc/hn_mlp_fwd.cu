@@ -24,23 +24,36 @@
 
 namespace hn {
 
-__constant__ FwdTables c_fwd;
+// HN_TRACE build (tools/trace_fwd.py): CTA 0 records the SM clock of pipeline events of its third tile into status[64..]
+#ifdef HN_TRACE
+#define HN_TR(cond, slot) do { if ((cond) && blockIdx.x == 0 && tile_k == 2) a.status[64 + (slot)] = (int)clock64(); } while (0)
+#else
+#define HN_TR(cond, slot) do {} while (0)
+#endif
 
-constexpr int kStages = 8;                                  // weight ring: one 16 KiB unit per stage
+__constant__ __align__(16) FwdTables c_fwd;
+
+constexpr int kStages = 4;                                  // weight ring: two consecutive 16 KiB units (32 KiB) per stage
+constexpr uint32_t kStageBytes = 2 * kUnitBytes;
 constexpr uint32_t kOffPE = 0;                              // PE operand block
 constexpr uint32_t kOffW = kUnitBytes;                      // weight ring
-constexpr uint32_t kOffStg = kOffW + kStages * kUnitBytes;  // 2 staging buffers of two blocks (saved activations)
+constexpr uint32_t kOffStg = kOffW + kStages * kStageBytes;  // 2 staging buffers of two blocks (saved activations)
 constexpr uint32_t kOffBias = kOffStg + 4 * kUnitBytes;     // this item's effective bias row
 constexpr uint32_t kBiasBytes = HN_BIAS_STRIDE * 4;
 constexpr uint32_t kOffShared = kOffBias + kBiasBytes;      // barriers and small arrays (FwdShared) close the dynamic region
 constexpr uint32_t kTmemCols = 512;
-constexpr int kGroupWarps = kEpiWarps / 2;                  // two epilogue groups take alternate accumulator chunks
+constexpr int kFwdEpiWarps = 8;                              // two epilogue groups of four warps take alternate accumulator chunks
+constexpr int kGroupWarps = kFwdEpiWarps / 2;
+constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;
+constexpr int kFwdThreads = (kFwdEpiWarps + kCtrlWarps) * 32; // 384 = 12 warps (registers are granted per 4 warps: 13 would cost like 16)
 
 struct FwdShared {
     uint64_t w_full[kStages], w_empty[kStages];
-    uint64_t a_ready[3], pe_ready, pe_free, acc_full[2], acc_empty[2];
-    uint64_t stg_full[2], stg_free[2];  // one staging buffer per epilogue group
-    uint64_t ld_done[2][4], dens_done;  // accumulator loads of a group's chunk k (rotating over 4); density partials of a tile
+    uint64_t a_ready[3], pe_ready, pe_free, pe_consumed, dens_done;
+    // per accumulator chunk n, rotating over 8 (the issuer can run at most a few chunks ahead of the slowest epilogue warp):
+    uint64_t acc_full[8];               //   committed by the MMA issuer
+    uint64_t loaded[8];                 //   all eight epilogue warps have read their part of the accumulator
+    uint64_t stg_full[2], stg_free[2];  // staging buffers of saved chunks, alternating per saved chunk
     alignas(16) float dens[2][128];     // density head: every warp adds its partial dot products here (by tile parity)
     alignas(16) float w_density[HN_HIDDEN];   // read as float4
     uint32_t tmem_base;
@@ -49,36 +62,26 @@ struct FwdShared {
 constexpr uint32_t kFwdSmem = kOffShared + sizeof(FwdShared);
 static_assert(kOffShared % 16 == 0 && kFwdSmem <= 232448, "shared-memory budget (227 KiB per CTA)");
 
-// positional encoding (NetWorks/utils.py:20-51): columns [16*CG, 16*CG+16) of row `row` of the PE operand block.
-// channel order: p(3), then per frequency 2^k: sin(3), cos(3); column 63 is the zero pad of the 64-wide K block.
-template <int CG>
-__device__ __forceinline__ void write_pe_part(uint32_t pe_block, int row, const float (&p)[3]) {
-    float v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        constexpr int c0 = 16 * CG;
-        const int c = c0 + i;
-        if (c < 3) v[i] = p[c];
-        else if (c == 63) v[i] = 0.f;
-        else {
-            const int k = (c - 3) / 6, t = (c - 3) % 6;
-            const float arg = p[t % 3] * (float)(1 << k);
-            v[i] = (t < 3) ? sinf(arg) : cosf(arg);
-        }
-    }
-    const uint32_t row_addr = pe_block + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-        st_shared_v4(row_addr + (((2 * CG + h) ^ (row & 7)) << 4),
-                     pack_h2(v[8 * h + 0], v[8 * h + 1]), pack_h2(v[8 * h + 2], v[8 * h + 3]),
-                     pack_h2(v[8 * h + 4], v[8 * h + 5]), pack_h2(v[8 * h + 6], v[8 * h + 7]));
+// one EpiOp2 (16 bytes) fetched with a single 128-bit constant load and decoded with shifts: the fields stay in registers
+// instead of being re-read from the constant bank wherever they are used
+struct EpiFields {
+    uint32_t acc_col, out_col, bias_off, col0, save_blk, mask_word, width32, kind, ready_idx, density, wait_next, signal_p;
+};
+__device__ __forceinline__ EpiFields load_epi(int e) {
+    const uint4 r = reinterpret_cast<const uint4*>(c_fwd.epi)[e];
+    EpiFields f;
+    f.acc_col = r.x & 0xFFFFu; f.out_col = r.x >> 16;
+    f.bias_off = r.y & 0xFFFFu; f.col0 = r.y >> 16;
+    f.save_blk = r.z & 0xFFFFu; f.mask_word = r.z >> 16;
+    f.width32 = r.w & 0xFFu; f.kind = (r.w >> 8) & 0xFFu; f.ready_idx = (r.w >> 16) & 0xFFu;
+    f.density = (r.w >> 24) & 3u; f.wait_next = (r.w >> 26) & 1u; f.signal_p = (r.w >> 27) & 1u;
+    return f;
 }
 
-// sampling + positional encoding of row `row` of tile `t`: the first GEMM's operand is generated, not loaded.  `part` selects
-// 16 of the 64 PE columns.  Kept out of line: the accurate sin/cos paths need registers and a little local memory that the
-// epilogue loop around the call should not pay for.
-__device__ __noinline__ void produce_pe_part(const hn_camera_t cam, float* delta, float* zvals, uint32_t pe_block, int t, int tiles_per_item,
-                                             int row, int part, bool aux) {
+// Sampling + positional encoding (NetWorks/utils.py:20-51,147-161) of row `row` of tile `t`: the first GEMM's operand is
+// generated, not loaded.  Channel order: p(3), then per frequency 2^k: sin(3), cos(3); column 63 is the zero pad of the
+// 64-wide K block.  One sincosf per (frequency, coordinate).
+__device__ __forceinline__ void produce_pe_row(const hn_camera_t cam, float* delta, float* zvals, uint32_t pe_block, int t, int tiles_per_item, int row) {
     const size_t mm = (size_t)t * HN_TILE + row;
     const int bb = t / tiles_per_item;
     const int ns = cam.n_samples;
@@ -86,239 +89,267 @@ __device__ __noinline__ void produce_pe_part(const hn_camera_t cam, float* delta
     const int s = (int)(mm % ns), r = (int)(ray_idx % cam.n_rays);
     const Ray ray = make_ray(cam, bb, r);
     const Sample q = make_sample(cam, ray, bb, r, s);
-    if (aux) {
-        delta[mm] = q.zdist;
-        if (zvals) zvals[mm] = q.zval;
-    }
+    delta[mm] = q.zdist;
+    if (zvals) zvals[mm] = q.zval;
     const float p[3] = {q.px, q.py, q.pz};
-    switch (part) {
-        case 0: write_pe_part<0>(pe_block, row, p); break;
-        case 1: write_pe_part<1>(pe_block, row, p); break;
-        case 2: write_pe_part<2>(pe_block, row, p); break;
-        default: write_pe_part<3>(pe_block, row, p); break;
-    }
+    float v[64];
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[63] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sincosf(p[d] * (float)(1 << k), &v[3 + 6 * k + d], &v[3 + 6 * k + 3 + d]);
+    const uint32_t row_addr = pe_block + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        st_shared_v4(row_addr + ((c ^ (row & 7)) << 4), pack_h2(v[8 * c + 0], v[8 * c + 1]), pack_h2(v[8 * c + 2], v[8 * c + 3]),
+                     pack_h2(v[8 * c + 4], v[8 * c + 5]), pack_h2(v[8 * c + 6], v[8 * c + 7]));
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_fwd_t a, const int n_tiles, const int tiles_per_item) {
+__global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fwd_t a, const int n_tiles, const int tiles_per_item) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];      // no static shared memory in this kernel: the window starts aligned
     FwdShared& sh = *reinterpret_cast<FwdShared*>(smem_raw + kOffShared);
     const uint32_t smem = smem_u32(smem_raw);
+    // warps 0..7: epilogue (TMEM lane quarter = warp & 3); warps 8..11: control roles.  The warp scheduler favours the
+    // highest warp id of a sub-partition, so the MMA issuer and the producers - short instruction streams that everything
+    // else waits for - sit at the top.
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cw = warp - kFwdEpiWarps;                           // control role: 0 weight producers, 1 MMA issuer, 2 TMEM + positional encoding, 3 saver
     const bool saving = (a.act != nullptr);
     const int work0 = (int)blockIdx.x, work_stride = (int)gridDim.x;
 
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&sh.w_full[i]), 1); mbar_init(smem_u32(&sh.w_empty[i]), 1); }
-        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&sh.a_ready[i]), kGroupWarps);
-        mbar_init(smem_u32(&sh.pe_ready), kEpiWarps); mbar_init(smem_u32(&sh.pe_free), 1);
-        mbar_init(smem_u32(&sh.dens_done), kEpiWarps);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.acc_empty[i]), kGroupWarps);
-            mbar_init(smem_u32(&sh.stg_full[i]), kGroupWarps); mbar_init(smem_u32(&sh.stg_free[i]), 1);
-            for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&sh.ld_done[i][k]), kGroupWarps);
-        }
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&sh.a_ready[i]), kFwdEpiWarps);
+        mbar_init(smem_u32(&sh.pe_ready), 1); mbar_init(smem_u32(&sh.pe_free), 1); mbar_init(smem_u32(&sh.pe_consumed), kFwdEpiWarps);
+        mbar_init(smem_u32(&sh.dens_done), kFwdEpiWarps);
+        for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.loaded[i]), kFwdEpiWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&sh.stg_full[i]), kFwdEpiWarps); mbar_init(smem_u32(&sh.stg_free[i]), 1); }
         sh.abort = 0;
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(&sh.tmem_base));
+    if (cw == 2) tmem_alloc<kTmemCols>(smem_u32(&sh.tmem_base));
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = sh.tmem_base;
-    const int n_ops = c_fwd.n_ops;
+    const int n_stages = c_fwd.n_stages;
 
-    if (warp == 0 || warp == 2 || (warp == 3 && !saving)) {
-        // ======================= weight producers (lane 0 of warps 0, 2 and - when nothing is saved - 3) =======================
-        if (lane == 0) {
-            const uint32_t P = saving ? 2u : 3u, p = warp == 0 ? 0u : (uint32_t)(warp - 1);
-            uint32_t uc = 0;
+    if (cw == 0) {
+        // ======================= weight producers: three lanes of one warp, each with its own copies in flight =======================
+        if (lane < 3) {
+            const uint32_t P = 3u, p = (uint32_t)lane;
+            uint32_t pc = 0;                                         // stage (unit pair) counter
             const uint8_t* packed = (const uint8_t*)a.packed;
             for (int w = work0; w < n_tiles && !sh.abort; w += work_stride) {
-                for (int u = 0; u < n_ops; ++u, ++uc) {
-                    if (uc % P != p) continue;
-                    const uint32_t stage = uc % kStages, par = (uc / kStages) & 1;
-                    if (!wait_or_abort(&sh.w_empty[stage], par ^ 1, &sh.abort, a.status, 101)) break;
-                    const uint32_t bytes = (uint32_t)c_fwd.mma[u].n8 * 8 * 128;
+                for (int st = 0; st < n_stages; ++st, ++pc) {
+                    if (pc % P != p) continue;
+                    const uint32_t stage = pc % kStages, par = (pc / kStages) & 1;
+                    if (!wait_spin(&sh.w_empty[stage], par ^ 1, &sh.abort, a.status, 101)) break;
                     const uint32_t fb = smem_u32(&sh.w_full[stage]);
-                    mbar_arrive_expect_tx(fb, bytes);
-                    bulk_g2s(smem + kOffW + stage * kUnitBytes, packed + (size_t)u * kUnitBytes, bytes, fb);
+                    mbar_arrive_expect_tx(fb, kStageBytes);
+                    // one 32 KiB copy per stage: a thread's bulk copies complete one after the other at ~700 cycles apiece
+                    // whatever their size, so bigger copies are what buys bandwidth
+                    bulk_g2s(smem + kOffW + stage * kStageBytes, packed + (size_t)st * kStageBytes, kStageBytes, fb);
                 }
             }
         }
-    } else if (warp == 3) {
+    } else if (cw == 3) {
+        if (!saving) { /* nothing to save */ } else
         // ======================= saver: staged activation chunks + the PE block -> HBM operand images =======================
         if (lane == 0) {
-            uint32_t use0 = 0, use1 = 0, par_pe = 0, base_n = 0;
-            for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, base_n += kFwdEpis) {
+            uint32_t sidx = 0, par_pe = 0;                           // saved chunks so far: buffer = sidx & 1, its use = sidx >> 1
+            for (int w = work0; w < n_tiles && !sh.abort; w += work_stride) {
                 const int tile = w;
-                if (!wait_or_abort(&sh.pe_ready, par_pe, &sh.abort, a.status, 150)) break;
+                if (!wait_spin(&sh.pe_ready, par_pe, &sh.abort, a.status, 150)) break;
                 par_pe ^= 1;
                 bulk_s2g((uint8_t*)a.act + ((size_t)HN_SLOT_PE * n_tiles + tile) * kUnitBytes, smem + kOffPE, kUnitBytes);
                 bulk_commit();
                 bulk_wait_read<0>();
                 mbar_arrive(smem_u32(&sh.pe_free));
                 for (int e = 0; e < kFwdEpis; ++e) {
-                    const EpiOp2 op = c_fwd.epi[e];
+                    const EpiFields op = load_epi(e);
                     if (op.save_blk == 0xFFFF) continue;
-                    const uint32_t sg = (base_n + e) & 1;             // staging buffer = epilogue group of the chunk
-                    if (!wait_or_abort(&sh.stg_full[sg], (sg ? use1 : use0) & 1, &sh.abort, a.status, 151)) break;
-                    if (sg) ++use1; else ++use0;
+                    const uint32_t sb = sidx & 1;
+                    if (!wait_spin(&sh.stg_full[sb], (sidx >> 1) & 1, &sh.abort, a.status, 151)) break;
+                    ++sidx;
                     const int nblk = (op.width32 + 1) / 2;
                     for (int k = 0; k < nblk; ++k)
                         bulk_s2g((uint8_t*)a.act + ((size_t)(op.save_blk + k) * n_tiles + tile) * kUnitBytes,
-                                 smem + kOffStg + (sg * 2 + k) * kUnitBytes, kUnitBytes);
+                                 smem + kOffStg + (sb * 2 + k) * kUnitBytes, kUnitBytes);
                     bulk_commit();
                     bulk_wait_read<0>();                               // the buffer is free as soon as the engine has read it
-                    mbar_arrive(smem_u32(&sh.stg_free[sg]));
+                    mbar_arrive(smem_u32(&sh.stg_free[sb]));
                 }
             }
             bulk_wait_all<0>();
         }
-    } else if (warp == 1) {
+    } else if (cw == 1) {
         // ======================= MMA issuer =======================
         // the whole warp walks the schedule (uniform control flow keeps descriptors in uniform registers); one
         // elected lane issues the MMAs and commits
-        uint32_t uc = 0, par_ready = 0, par_pe = 0, chunk_n = 0;
-        HN_PC_DECL(pc, 8);
-        for (int w = work0; w < n_tiles && !sh.abort; w += work_stride) {
-            MmaOp2 op = c_fwd.mma[0];
-            for (int u = 0; u < n_ops; ++u, ++uc) {
-                const MmaOp2 nxt = c_fwd.mma[u + 1 < n_ops ? u + 1 : 0];         // table read off the critical path
+        uint32_t pc = 0, par_ready = 0, par_pe = 0, base_n = 0;
+        int tile_k = 0;
+        HN_PC_DECL(pcn, 8);
+        // The issuer shares its scheduler with four epilogue warps and gets only a fraction of the issue slots, so its
+        // instruction stream per MMA is what bounds the tensor pipe: a stage is one 128-bit table word, four MMAs of N = 256
+        // (or eight of N = 128), one release; the NEXT stage's weight barrier is queried before its answer is needed.
+        bool pre = mbar_try_wait(smem_u32(&sh.w_full[0]), 0);
+        const uint4* table = reinterpret_cast<const uint4*>(c_fwd.stage);
+        uint4 cur = table[0];
+        for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, base_n += kFwdEpis, ++tile_k) {
+            const uint32_t hx = (uint32_t)(tile_k & 1) << 8;           // odd tiles: the TMEM halves swap roles
+            for (int st = 0; st < n_stages; ++st, ++pc) {
+                const uint4 nxt = table[st + 1 < n_stages ? st + 1 : 0];           // table read off the critical path
+                const uint32_t stage = pc % kStages, par = (pc / kStages) & 1;
+                const uint32_t a0 = cur.x & 0xFFFFu, a1 = cur.x >> 16, acc = cur.y & 0xFFFFu, n8 = (cur.y >> 16) & 0xFFu, first = cur.y >> 24;
+                const uint32_t commit = cur.z & 0xFFu, chunk = (cur.z >> 8) & 0xFFu;
                 bool ok = true;
-                HN_PC_T0(pc);
-                if (op.wait_src == 4) { ok = wait_or_abort(&sh.pe_ready, par_pe, &sh.abort, a.status, 201); par_pe ^= 1; HN_PC_LAP(pc, 1); }
-                else if (op.wait_src) {
-                    const int c = op.wait_src - 1;
-                    ok = wait_or_abort(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 202 + c);
-                    par_ready ^= 1u << c;
-                    HN_PC_LAP(pc, 2);
+                HN_TR(lane == 0, st * 4 + 0);
+                if (cur.z >> 16) {                                     // rare: an input slot or chunk 0's accumulator must be awaited
+                    const uint32_t wait_src = (cur.z >> 16) & 0xFFu;
+                    if (wait_src == 4) { ok = wait_spin(&sh.pe_ready, par_pe, &sh.abort, a.status, 201); par_pe ^= 1; }
+                    else if (wait_src) {
+                        const int c = (int)wait_src - 1;
+                        ok = wait_spin(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 202 + c);
+                        par_ready ^= 1u << c;
+                    }
+                    if (ok && (cur.z >> 24)) {                         // chunk 2 reuses chunk 0's accumulator: all of it must have been read
+                        const uint32_t np = base_n + chunk - 2;
+                        ok = wait_spin(&sh.loaded[np & 7], (np >> 3) & 1, &sh.abort, a.status, 210);
+                    }
                 }
-                // accumulator of chunk n: released by the epilogue of chunk n-2 (the first two chunks find fresh barriers)
-                if (ok && op.first) ok = wait_or_abort(&sh.acc_empty[chunk_n & 1], ((chunk_n >> 1) & 1) ^ 1, &sh.abort, a.status, 210);
-                HN_PC_LAP(pc, 3);
-                const uint32_t stage = uc % kStages, par = (uc / kStages) & 1;
-                if (ok) ok = wait_or_abort(&sh.w_full[stage], par, &sh.abort, a.status, 220);
-                HN_PC_LAP(pc, 4);
+                HN_TR(lane == 0, st * 4 + 1);
+                if (ok && !pre) ok = wait_spin(&sh.w_full[stage], par, &sh.abort, a.status, 220);
+                HN_TR(lane == 0, st * 4 + 2);
                 if (!ok) break;
                 tc_fence_after_sync();
-                const uint32_t idesc = umma_idesc(128, (uint32_t)op.n8 * 8, kF16, kF16, 0, 0);
-                const uint32_t d_addr = tmem_base + op.acc_col;
-                const uint32_t b_lo = desc_lo(smem + kOffW + stage * kUnitBytes, 16);
-                const uint32_t first = op.first;
-                if (op.a_src & kSrcSmem) {
-                    const uint32_t a_lo = desc_lo(smem + kOffPE + (op.a_src & 0x7FFFu) * kUnitBytes, 16);
+                const uint32_t b_lo = desc_lo(smem + kOffW + stage * kStageBytes, 16);
+                const uint32_t idesc = umma_idesc(128, n8 * 8, kF16, kF16, 0, 0);
+                const uint32_t d = tmem_base + (acc ^ hx);
+                const uint32_t acc0 = first ? 0u : 1u;
+                const uint32_t n0 = base_n + chunk, n1 = n0 + 1;
+                const uint32_t full0 = smem_u32(&sh.acc_full[n0 & 7]), full1 = smem_u32(&sh.acc_full[n1 & 7]);
+                if (a0 & kSrcSmem) {
+                    const uint32_t a_lo = desc_lo(smem + kOffPE + (a0 & 0x7FFFu) * kUnitBytes, 16);
                     if (elect_one()) {
 #pragma unroll
-                        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_lohi(d_addr, a_lo + ks * 2, b_lo + ks * 2, idesc, (first && ks == 0) ? 0u : 1u);
+                        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_lohi(d, a_lo + ks * 2, b_lo + ks * 2, idesc, ks == 0 ? acc0 : 1u);
+                        if (a1 != kSrcNone) {                          // (both K blocks of a stage come from the same kind of source)
+#pragma unroll
+                            for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_lohi(d, a_lo + ks * 2, b_lo + (kUnitBytes >> 4) + ks * 2, idesc, 1u);
+                        }
+                        if (commit) umma_commit(full0);
+                        if (commit == 2) umma_commit(full1);
+                        umma_commit(smem_u32(&sh.w_empty[stage]));
                     }
                 } else {
-                    const uint32_t a_t = tmem_base + op.a_src;
+                    const uint32_t a_t0 = tmem_base + (a0 ^ hx), a_t1 = tmem_base + (a1 ^ hx);
                     if (elect_one()) {
 #pragma unroll
-                        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ts_lo(d_addr, a_t + ks * 8, b_lo + ks * 2, idesc, (first && ks == 0) ? 0u : 1u);
+                        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ts_lo(d, a_t0 + ks * 8, b_lo + ks * 2, idesc, ks == 0 ? acc0 : 1u);
+                        if (a1 != kSrcNone) {
+#pragma unroll
+                            for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ts_lo(d, a_t1 + ks * 8, b_lo + (kUnitBytes >> 4) + ks * 2, idesc, 1u);
+                        }
+                        if (commit) umma_commit(full0);
+                        if (commit == 2) umma_commit(full1);
+                        umma_commit(smem_u32(&sh.w_empty[stage]));
                     }
                 }
-                HN_PC_LAP(pc, 6);
-                if (elect_one()) {
-                    umma_commit(smem_u32(&sh.w_empty[stage]));
-                    if (op.commit) umma_commit(smem_u32(&sh.acc_full[chunk_n & 1]));
-                }
                 __syncwarp();
-                HN_PC_LAP(pc, 7);
-                chunk_n += op.commit;
-                op = nxt;
+                // ask for the next stage's weights now; the answer is consumed at the top of the next iteration
+                pre = mbar_try_wait(smem_u32(&sh.w_full[(pc + 1) % kStages]), ((pc + 1) / kStages) & 1);
+                HN_TR(lane == 0, st * 4 + 3);
+                cur = nxt;
             }
         }
-        HN_PC_FLUSH(pc, 8, a.status + 2, blockIdx.x == 0 && lane == 0);
-    } else {
-        // ======================= PE producers + epilogue =======================
-        // Two groups of 8 warps take alternate accumulator chunks (group = chunk index & 1), so one group's TMEM loads /
-        // conversions / stores overlap the other's.  Inside a group: warp = (TMEM lane quarter, column half); a warp drains
-        // 32 rows x 64 columns of its chunk as two 32-column pieces.
-        const int ew = warp - kCtrlWarps;
-        const int g = ew >> 3, quarter = ew & 3, half = (ew >> 2) & 1;
-        const int row = quarter * 32 + lane;                        // tile row = TMEM lane
-        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        const int qbar = 4 + g * 4 + quarter;                       // named barrier of the two warps sharing (group, quarter)
-        uint32_t base_n = 0, use_n = 0, pe_n = 0, tile_i = 0;       // first chunk index of the tile; staged chunks of this group
-        const int pe_after = c_fwd.pe_after_epi;
-        int cached_b = -1;
-        for (int i = tid - kCtrlWarps * 32; i < HN_HIDDEN; i += kEpiThreads) sh.w_density[i] = __ldg(a.w_density + i);
-        if (tid - kCtrlWarps * 32 < 256) (&sh.dens[0][0])[tid - kCtrlWarps * 32] = 0.f;
-        named_sync(3, kEpiThreads);
-
-        // each group writes 32 of the 64 PE columns of the next tile (16 per warp half)
-        auto produce_pe = [&](int t) {
-            // the previous tile's PE block must have been read by the saver's bulk store (its MMAs are long done)
-            if (saving) wait_or_abort(&sh.pe_free, (pe_n & 1) ^ 1, &sh.abort, a.status, 160);
-            ++pe_n;
-            produce_pe_part(a.cam, a.delta, a.zvals, smem + kOffPE, t, tiles_per_item, row, 2 * g + half, g == 0 && half == 0);
+        HN_PC_FLUSH(pcn, 8, a.status + 2, blockIdx.x == 0 && lane == 0);
+    } else if (cw == 2) {
+        // ======================= PE warp: sampling + positional encoding of the NEXT tile, off everybody's critical path =======================
+        // four rows per lane; the PE block is free once FeaExt_module_5's last chunk has been committed (its MMAs were the last
+        // readers) and - when activations are saved - the saver's bulk store has read it
+        uint32_t k = 0;
+        for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, ++k) {
+            if (k > 0) {
+                if (!wait_spin(&sh.pe_consumed, (k - 1) & 1, &sh.abort, a.status, 160)) break;
+                if (saving && !wait_spin(&sh.pe_free, (k - 1) & 1, &sh.abort, a.status, 161)) break;
+            }
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) produce_pe_row(a.cam, a.delta, a.zvals, smem + kOffPE, w, tiles_per_item, i * 32 + lane);
             fence_async_smem();
             warp_arrive(smem_u32(&sh.pe_ready), lane);
-        };
+        }
+    } else {
+        // ======================= epilogue =======================
+        // Eight warps, every one on EVERY accumulator chunk: warp = (TMEM lane quarter, column half); it drains 32 rows x 64
+        // columns as two 32-column pieces.  Splitting a chunk by columns (rather than handing whole chunks to alternating groups)
+        // halves the latency from "chunk committed" to "accumulator read" - which the MMA issuer waits for before chunk 2 can
+        // reuse chunk 0's columns - and to "outputs stored".  Few, fat warps on purpose: the issuer shares its scheduler with
+        // two of them.
+        const int ew = warp;
+        const int g = ew >> 2, quarter = ew & 3;                    // g: columns [64g, 64g+64) of every chunk
+        const int row = quarter * 32 + lane;                        // tile row = TMEM lane
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        uint32_t base_n = 0, sidx = 0, tile_i = 0;                  // first chunk index of the tile; saved chunks so far
+        const int pe_after = c_fwd.pe_after_epi;
+        int cached_b = -1;
+        for (int i = tid; i < HN_HIDDEN; i += kFwdEpiThreads) sh.w_density[i] = __ldg(a.w_density + i);
+        (&sh.dens[0][0])[tid] = 0.f;
+        named_sync(3, kFwdEpiThreads);
 
         HN_PC_DECL(ec, 16);
-        if (work0 < n_tiles) produce_pe(work0);
         float dens = 0.f;
         for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, base_n += kFwdEpis, ++tile_i) {
             const int tile = w;
             const size_t m = (size_t)tile * HN_TILE + row;
             const int b = tile / tiles_per_item;
-            if (b != cached_b) {                                    // (re)load the item's bias row: both groups meet here
-                named_sync(3, kEpiThreads);
+            if (b != cached_b) {                                    // (re)load the item's bias row
+                named_sync(3, kFwdEpiThreads);
                 const float4* src = reinterpret_cast<const float4*>(a.bias + (size_t)b * HN_BIAS_STRIDE);
-                for (int i = tid - kCtrlWarps * 32; i < HN_BIAS_STRIDE / 4; i += kEpiThreads) {
+                for (int i = tid; i < HN_BIAS_STRIDE / 4; i += kFwdEpiThreads) {
                     const float4 v4 = __ldg(src + i);
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(smem + kOffBias + i * 16), "f"(v4.x), "f"(v4.y), "f"(v4.z), "f"(v4.w) : "memory");
                 }
-                named_sync(3, kEpiThreads);
+                named_sync(3, kFwdEpiThreads);
                 cached_b = b;
             }
             const uint32_t bias_row = smem + kOffBias;
-            // the group that drains FeaExt_module_5's last chunk builds its half of the next PE block right after it, the
-            // other group after its next own chunk (by then that chunk's MMAs, the last readers of the PE block, are done)
-            const int pe_e = (((base_n + pe_after) & 1) == (uint32_t)g) ? pe_after : pe_after + 1;
+            const uint32_t hx = (tile_i & 1u) << 8;                 // odd tiles: the TMEM halves swap roles
+            uint32_t hold0[16], hold1[16];                          // packed output of chunk 0 of a pair, stored with chunk 1's
+            uint32_t hold_addr = 0;
+            bool holding = false;
             for (int e = 0; e < kFwdEpis; ++e) {
                 const uint32_t n = base_n + e;
-                if ((n & 1) != (uint32_t)g) continue;
-                const EpiOp2 op = c_fwd.epi[e];
-                // on a pipeline fault every later wait returns at once; the loop still runs to its end so that all
-                // epilogue threads keep meeting at the same named barriers
+                const EpiFields op = load_epi(e);
                 HN_PC_T0(ec);
-                wait_or_abort(&sh.acc_full[g], (n >> 1) & 1, &sh.abort, a.status, 300 + e);
+                wait_spin(&sh.acc_full[n & 7], (n >> 3) & 1, &sh.abort, a.status, 300 + e);
                 HN_PC_LAP(ec, 1);
+                { const int tile_k = (int)tile_i; HN_TR(ew == 0 && lane == 0, 1024 + e * 4 + 0); }
                 tc_fence_after_sync();
-                const int col = half * 64;                         // first column of this warp inside the chunk
-                const bool act0 = 2 * half < op.width32, act1 = 2 * half + 1 < op.width32;
+                // FeaExt_module_5's last chunk is complete: every MMA that reads the PE block has run
+                if (e == pe_after) warp_arrive(smem_u32(&sh.pe_consumed), lane);
                 const bool save = saving && op.save_blk != 0xFFFF;
-                const uint32_t bp = bias_row + (op.bias_off + col) * 4;
-                const uint32_t acc_addr = tmem_base + lane_base + op.acc_col + col;
-                // after the accumulator loads: both warps of this lane quarter have read their part, so packed outputs may be
-                // stored over it (in-place slots) and the MMA issuer may reuse it two chunks later
-                auto release_acc = [&]() {
-                    tc_fence_before_sync();
-                    named_sync(qbar, 64);
-                    tc_fence_after_sync();
-                    warp_arrive(smem_u32(&sh.acc_empty[g]), lane);
-                    warp_arrive(smem_u32(&sh.ld_done[g][(n >> 1) & 3]), lane);
-                    if (op.wait_prev && n > 0) {                   // output slot drained by chunk n-1: the other group's loads
-                        wait_or_abort(&sh.ld_done[g ^ 1][((n - 1) >> 1) & 3], ((n - 1) >> 3) & 1, &sh.abort, a.status, 330);
-                        tc_fence_after_sync();
-                    }
-                    // staging buffer of this group (saved chunk, or scratch of the final-feature store): previous bulk read done?
-                    if (save || (saving && op.kind == EPI_FEAT)) wait_or_abort(&sh.stg_free[g], (use_n & 1) ^ 1, &sh.abort, a.status, 340);
-                };
+                const bool active = 2 * g < (int)op.width32;       // RGB_layer_1's second chunk has 64 columns: the upper half idles
+                const uint32_t bp = bias_row + (op.bias_off + 64 * g) * 4;
+                const uint32_t acc_addr = tmem_base + lane_base + (op.acc_col ^ hx) + 64 * g;
+                uint32_t v0[32], v1[32];
+                if (active) { tmem_ld32(acc_addr, v0); tmem_ld32(acc_addr + 32, v1); }
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                warp_arrive(smem_u32(&sh.loaded[n & 7]), lane);    // (the MMA issuer waits on this for chunk 0 before it starts chunk 2)
+                { const int tile_k = (int)tile_i; HN_TR(ew == 0 && lane == 0, 1024 + e * 4 + 1); }
+                HN_PC_LAP(ec, 2);
+                const uint32_t sb = sidx & 1;                      // staging buffer of this saved chunk
                 if (op.kind == EPI_FEAT) {
-                    // final features: stage the 32 rows x 32 columns of each piece in shared memory (swizzled 16-byte chunks),
-                    // then write whole 128-byte row segments (8 lanes each) instead of 32 scattered 16-byte pieces
-                    const uint32_t stg = smem + kOffStg + (uint32_t)ew * 4096;                  // 32 rows x 128 B per warp
-                    float* gbase = a.feat + ((size_t)tile * HN_TILE + quarter * 32) * HN_FEAT + op.col0 + col;
-#pragma unroll
-                    for (int pc = 0; pc < 2; ++pc) {
-                        uint32_t v[32];
-                        tmem_ld32(acc_addr + pc * 32, v);
-                        tmem_ld_wait();
-                        if (pc == 1) { HN_PC_LAP(ec, 2); release_acc(); HN_PC_LAP(ec, 3); }
+                    // final features: stage 32 rows x 32 columns per piece in shared memory (swizzled 16-byte chunks), then write
+                    // whole 128-byte row segments (8 lanes each) instead of 32 scattered 16-byte pieces.  Scratch = the staging
+                    // buffer whose last saved chunk is the older one (chunk 29 -> buffer of chunk 27, chunk 30 -> of chunk 28).
+                    const uint32_t fb = (sidx + (uint32_t)(e & 1 ? 0 : 1)) & 1;     // e = 29: sidx & 1;  e = 30: (sidx + 1) & 1
+                    const uint32_t fidx = sidx + (uint32_t)(e & 1 ? 0 : 1);
+                    if (saving) wait_spin(&sh.stg_free[fb], ((fidx >> 1) & 1) ^ 1, &sh.abort, a.status, 340);
+                    const uint32_t stg = smem + kOffStg + fb * 2 * kUnitBytes + (uint32_t)ew * 4096;   // 32 rows x 128 B per warp
+                    float* gbase = a.feat + ((size_t)tile * HN_TILE + quarter * 32) * HN_FEAT + op.col0 + 64 * g;
+                    auto emit = [&](const uint32_t (&v)[32], int pc) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float4 bb;
@@ -339,11 +370,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                             }
                         }
                         __syncwarp();
-                    }
+                    };
+                    emit(v0, 0);
+                    emit(v1, 1);
                     HN_PC_LAP(ec, 4);
                 } else {
-                    // piece 0 is converted before piece 1 is loaded (registers); its packed columns are stored after the barrier
-                    uint32_t pk0[16];
                     auto convert = [&](const uint32_t (&v)[32], int pc, uint32_t (&pk)[16]) {
                         float y[32];
 #pragma unroll
@@ -357,9 +388,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                         }
                         if (op.kind == EPI_HIDDEN) {
                             if (a.masks && op.mask_word != 0xFFFF)
-                                a.masks[m * HN_MASK_WORDS + op.mask_word + 2 * half + pc] = positive_mask32(y);
+                                a.masks[m * HN_MASK_WORDS + op.mask_word + 2 * g + pc] = positive_mask32(y);
                             if (op.density) {                      // density head on the fp32 activations (models.py:78,83)
-                                const float4* wp = reinterpret_cast<const float4*>(sh.w_density + op.col0 + col + pc * 32);
+                                const float4* wp = reinterpret_cast<const float4*>(sh.w_density + op.col0 + 64 * g + pc * 32);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     const float4 ww = wp[i];
@@ -374,61 +405,64 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
                             for (int i = 0; i < 16; ++i) pk[i] = pack_sat(y[2 * i], y[2 * i + 1]);
                         }
                     };
-                    const uint32_t out_addr = tmem_base + lane_base + op.out_col + half * 32;
-                    const uint32_t stg = smem + kOffStg + (uint32_t)g * 2 * kUnitBytes;
-                    if (act0) {
-                        uint32_t v[32];
-                        tmem_ld32(acc_addr, v);
-                        tmem_ld_wait();
-                        convert(v, 0, pk0);
-                    }
-                    uint32_t v1[32];
-                    if (act1) { tmem_ld32(acc_addr + 32, v1); tmem_ld_wait(); }
-                    HN_PC_LAP(ec, 2);
-                    release_acc();
-                    HN_PC_LAP(ec, 3);
-                    if (act0) {
-                        tmem_st16(out_addr, pk0);
-                        if (save) store_row_packed(stg, row, col, pk0);
-                    }
-                    if (act1) {
-                        uint32_t pk1[16];
-                        convert(v1, 1, pk1);
-                        tmem_st16(out_addr + 16, pk1);
-                        if (save) store_row_packed(stg, row, col + 32, pk1);
+                    const uint32_t out_addr = tmem_base + lane_base + (op.out_col ^ hx) + 32 * g;
+                    const uint32_t stg = smem + kOffStg + sb * 2 * kUnitBytes;
+                    // staging buffer: has the bulk store of its previous saved chunk read it?
+                    if (save) wait_spin(&sh.stg_free[sb], ((sidx >> 1) & 1) ^ 1, &sh.abort, a.status, 341);
+                    if (op.wait_next) {
+                        // chunk 0 of a pair: its output slot is the upper half of chunk 1's accumulator, which is read only in the
+                        // next iteration - keep the packed columns in registers (the saved image can be staged now)
+                        if (active) {
+                            convert(v0, 0, hold0); convert(v1, 1, hold1);
+                            if (save) { store_row_packed(stg, row, 64 * g, hold0); store_row_packed(stg, row, 64 * g + 32, hold1); }
+                        }
+                        hold_addr = out_addr; holding = true;
+                    } else {
+                        // every warp has read its part of this accumulator (and, after a held chunk, of the previous one): stores
+                        // into in-place or neighbouring columns are safe now
+                        wait_spin(&sh.loaded[n & 7], (n >> 3) & 1, &sh.abort, a.status, 330);
+                        tc_fence_after_sync();
+                        if (holding) {
+                            tmem_st16(hold_addr, hold0);
+                            tmem_st16(hold_addr + 16, hold1);
+                        }
+                        if (active) {
+                            uint32_t pk[16];
+                            convert(v0, 0, pk);
+                            tmem_st16(out_addr, pk);
+                            if (save) store_row_packed(stg, row, 64 * g, pk);
+                            convert(v1, 1, pk);
+                            tmem_st16(out_addr + 16, pk);
+                            if (save) store_row_packed(stg, row, 64 * g + 32, pk);
+                        }
                     }
                     HN_PC_LAP(ec, 4);
                     tmem_st_wait();
                     HN_PC_LAP(ec, 5);
                 }
-                if (save) { fence_async_smem(); warp_arrive(smem_u32(&sh.stg_full[g]), lane); ++use_n; }
-                if (op.ready_idx != 255) {
+                if (save) { fence_async_smem(); warp_arrive(smem_u32(&sh.stg_full[sb]), lane); ++sidx; }
+                if (op.kind != EPI_FEAT && !op.wait_next) {
                     tc_fence_before_sync();
-                    warp_arrive(smem_u32(&sh.a_ready[op.ready_idx]), lane);
+                    if (holding) { warp_arrive(smem_u32(&sh.a_ready[0]), lane); holding = false; }     // the held chunk is chunk 0 of its layer
+                    if (op.ready_idx != 255) warp_arrive(smem_u32(&sh.a_ready[op.ready_idx]), lane);
                 }
                 HN_PC_LAP(ec, 6);
-                if (op.density) {
-                    // this warp's last density chunk of the tile: publish its partial dot products; the group that owns the
-                    // layer's last chunk adds the bias and writes sigma once all 16 warps have contributed
-                    const bool last_mine = (op.density == 2) || (e + 2 >= kFwdEpis) || !c_fwd.epi[e + 2].density;
-                    if (last_mine) {
-                        atomicAdd(&sh.dens[tile_i & 1][row], dens);
-                        dens = 0.f;
-                        __threadfence_block();
-                        warp_arrive(smem_u32(&sh.dens_done), lane);
-                    }
-                    if (op.density == 2) {
-                        wait_or_abort(&sh.dens_done, tile_i & 1, &sh.abort, a.status, 350);
-                        if (half == 0) {
-                            const float tot = *((volatile float*)&sh.dens[tile_i & 1][row]);
-                            a.sigma[m] = fmaxf(tot + __ldg(a.bias + (size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_DENSITY), 0.f);
-                            sh.dens[tile_i & 1][row] = 0.f;        // next use is two tiles away
-                        }
+                { const int tile_k = (int)tile_i; HN_TR(ew == 0 && lane == 0, 1024 + e * 4 + 2); }
+                if (op.density == 2) {
+                    // last density chunk of the tile: publish the partial dot products; once all 8 warps have contributed the
+                    // lower-half warps add the bias and write sigma
+                    atomicAdd(&sh.dens[tile_i & 1][row], dens);
+                    dens = 0.f;
+                    __threadfence_block();
+                    warp_arrive(smem_u32(&sh.dens_done), lane);
+                    if (g == 0) {
+                        wait_spin(&sh.dens_done, tile_i & 1, &sh.abort, a.status, 350);
+                        const float tot = *((volatile float*)&sh.dens[tile_i & 1][row]);
+                        a.sigma[m] = fmaxf(tot + __ldg(a.bias + (size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_DENSITY), 0.f);
+                        sh.dens[tile_i & 1][row] = 0.f;            // next use is two tiles away
                     }
                 }
                 HN_PC_LAP(ec, 7);
-                if (e == pe_e && w + work_stride < n_tiles) produce_pe(w + work_stride);
-                HN_PC_LAP(ec, 8);
             }
         }
         HN_PC_FLUSH(ec, 16, a.status + 18, blockIdx.x == 0 && ew == 0 && lane == 0);
@@ -436,7 +470,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_fwd_kernel(const hn_mlp_
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) tmem_free<kTmemCols>(tmem_base);
+    if (cw == 2) tmem_free<kTmemCols>(tmem_base);
 }
 
 static std::mutex g_fwd_mu;
@@ -469,6 +503,6 @@ extern "C" int hn_mlp_fwd(const hn_mlp_fwd_t* a, void* stream) {
     const int n_tiles = (int)(M / HN_TILE);
     const int tiles_per_item = (int)(((int64_t)a->cam.n_rays * a->cam.n_samples) / HN_TILE);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    mlp_fwd_kernel<<<grid, kFusedThreads, kFwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, tiles_per_item);
+    mlp_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, tiles_per_item);
     return check_launch("hn_mlp_fwd");
 }

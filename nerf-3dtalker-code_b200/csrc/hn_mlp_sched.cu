@@ -133,157 +133,108 @@ struct Builder {
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Forward chain, second generation (A operand in tensor memory): slot allocator + table generation.
-struct SlotSim {
-    // state of each 64-column TMEM slot: 0 busy; 1 free, last touched by MMAs (ordered by issue order);
-    // 2 free once the epilogue of chunk rel_n has loaded its accumulator
-    int kind[8], rel_n[8];
-    bool ok_acc(int s, int n) const { return kind[s] == 1 || (kind[s] == 2 && rel_n[s] <= n - 2); }
-    bool ok_out(int s, int n) const { return kind[s] == 1 || (kind[s] == 2 && rel_n[s] <= n); }
-};
+// Forward chain (A operand in tensor memory, alternating TMEM halves): table generation, see hn_mlp_sched.h.
+struct FwdLayer { int w_idx; bool pe; int n_kb; int widths[3]; int n_chunks; EpiKind kind; int bias_off; int save_blk; int mask_word; bool l5_hidden; int density; bool to_tmem; };
 
-struct Fwd2Layer { int w_idx; bool pe; int n_kb; int widths[3]; int n_chunks; EpiKind kind; int bias_off; int save_blk; int mask_word; bool l5_hidden; int density; bool to_tmem; };
-
-struct Chunk2 { int acc_slot; int acc_slots; int out_slot; int wait_prev; };
-
-// returns false if `fixed` (when given) violates a hazard rule from the initial state `sim`
-bool run_slots(const std::vector<Fwd2Layer>& layers, SlotSim& sim, int n0, std::vector<Chunk2>& table, bool fixed) {
-    std::vector<int> X;
-    int n = n0;
-    size_t idx = 0;
-    for (const Fwd2Layer& L : layers) {
-        std::vector<int> Y;
-        for (int j = 0; j < L.n_chunks; ++j, ++n, ++idx) {
-            const int need = L.widths[j] == 128 ? 2 : 1;
-            Chunk2 c{};
-            if (fixed) c = table[idx];
-            else {
-                c.acc_slots = need; c.acc_slot = -1;
-                if (need == 2) {
-                    int best = -1, best_cost = 99;
-                    for (int a = 0; a < 8; a += 2)
-                        if (sim.ok_acc(a, n) && sim.ok_acc(a + 1, n)) {
-                            const int cost = (sim.kind[a] != 1) + (sim.kind[a + 1] != 1);
-                            if (cost < best_cost) { best = a; best_cost = cost; }
-                        }
-                    c.acc_slot = best;
-                } else {
-                    int best = -1, best_cost = 99;
-                    for (int a = 0; a < 8; ++a)
-                        if (sim.ok_acc(a, n)) {
-                            const int cost = 2 * (sim.kind[a ^ 1] != 0) + (sim.kind[a] != 1);     // keep free pairs intact
-                            if (cost < best_cost) { best = a; best_cost = cost; }
-                        }
-                    c.acc_slot = best;
-                }
-                if (c.acc_slot < 0) return false;
-            }
-            for (int k = 0; k < need; ++k) { if (!sim.ok_acc(c.acc_slot + k, n)) return false; sim.kind[c.acc_slot + k] = 0; }
-            if (!L.to_tmem) c.out_slot = -1;
-            else if (!fixed) {
-                c.out_slot = -1;
-                for (int a = 0; a < 8 && c.out_slot < 0; ++a)            // a lone free slot (its pair partner is not free)
-                    if (sim.ok_out(a, n) && !sim.ok_out(a ^ 1, n)) c.out_slot = a;
-                if (c.out_slot < 0) c.out_slot = c.acc_slot;            // in place over the first accumulator slot
-            }
-            if (c.out_slot >= 0 && !(c.out_slot >= c.acc_slot && c.out_slot < c.acc_slot + need)) {
-                if (!sim.ok_out(c.out_slot, n)) return false;
-                const int wp = (sim.kind[c.out_slot] == 2 && sim.rel_n[c.out_slot] == n - 1) ? 1 : 0;
-                if (fixed && wp && !c.wait_prev) return false;
-                if (!fixed) c.wait_prev = wp;
-                sim.kind[c.out_slot] = 0;
-            }
-            for (int k = 0; k < need; ++k)
-                if (c.acc_slot + k != c.out_slot) { sim.kind[c.acc_slot + k] = 2; sim.rel_n[c.acc_slot + k] = n; }
-            if (c.out_slot >= 0) Y.push_back(c.out_slot);
-            if (!fixed) table.push_back(c);
-        }
-        for (int s : X) sim.kind[s] = 1;                               // this layer's inputs: free once its MMAs are issued
-        X = Y;
-    }
-    for (int s : X) sim.kind[s] = 1;
-    return true;
-}
-
-void build_fwd2(HostSchedules* hs) {
+void build_fwd(HostSchedules* hs) {
     // ---- layer list: NetWorks/models.py:69-82
-    std::vector<Fwd2Layer> layers;
+    std::vector<FwdLayer> layers;
     for (int l = 0; l < 8; ++l)
         layers.push_back({l, l == 0 || l == 5, l == 0 ? 0 : 6, {128, 128, 128}, 3, EPI_HIDDEN, l * HN_HIDDEN, HN_SLOT_H0 + 6 * l, 12 * l, l == 5, l == 7 ? 1 : 0, true});
     layers.push_back({W_R0, false, 6, {128, 128, 128}, 3, EPI_LINEAR, HN_BIAS_OFF_R0, HN_SLOT_R0, -1, false, 0, true});
     layers.push_back({W_R1, false, 6, {128, 64, 0}, 2, EPI_HIDDEN, HN_BIAS_OFF_R1, HN_SLOT_X, 96, false, 0, true});
     layers.push_back({W_R2, false, 3, {128, 128, 0}, 2, EPI_FEAT, HN_BIAS_OFF_R2, -1, -1, false, 0, false});
 
-    // ---- TMEM slots: derive the table from an empty TMEM, then prove it is also valid when a tile starts from the
-    // state the previous tile (same table) leaves behind
-    std::vector<Chunk2> table;
-    SlotSim sim{};
-    for (int s = 0; s < 8; ++s) { sim.kind[s] = 1; sim.rel_n[s] = 0; }
-    bool ok = run_slots(layers, sim, 0, table, false);
-    assert(ok && (int)table.size() == kFwdEpis);
-    for (int s = 0; s < 8; ++s) { assert(sim.kind[s] != 0); sim.rel_n[s] -= kFwdEpis; }
-    ok = run_slots(layers, sim, 0, table, true);
-    assert(ok && "forward TMEM slot table is not periodic");
-    (void)ok;
-
-    // ---- tables
-    std::vector<MmaOp2> mma;
+    std::vector<StageOp> stages;
     std::vector<PackOp> pack;
     std::vector<EpiOp2> epi;
-    std::vector<int> X;                                                // TMEM column of every input K block
-    size_t idx = 0;
+    std::vector<int> X;                                                // TMEM column of every input K block (even-tile columns)
+    int chunk0 = 0;
+    auto pack_unit = [&](const FwdLayer& L, int j, int k) {            // weight unit (chunk j, K block k); k < 0: empty unit
+        PackOp p{};
+        p.w_idx = (int8_t)L.w_idx; p.transposed = 0;
+        if (k < 0) { p.valid_r = 0; p.valid_c = 0; pack.push_back(p); return; }
+        const bool is_pe = L.pe && k == 0;
+        const int kb = k - (L.pe ? 1 : 0);
+        p.row0 = (int16_t)(128 * j); p.valid_r = (int16_t)L.widths[j];
+        if (is_pe) { p.col0 = 0; p.valid_c = HN_PE; p.l5_hidden = 0; }
+        else { p.col0 = (int16_t)(64 * kb); p.valid_c = 64; p.l5_hidden = (int8_t)L.l5_hidden; }
+        pack.push_back(p);
+    };
     for (size_t li = 0; li < layers.size(); ++li) {
-        const Fwd2Layer& L = layers[li];
+        const FwdLayer& L = layers[li];
+        const int B = (li & 1) ? 256 : 0;                              // accumulator half of this layer (even tiles)
+        const int n_k = (L.pe ? 1 : 0) + L.n_kb;
+        auto a_src = [&](int k) -> uint16_t { return (L.pe && k == 0) ? (uint16_t)(kSrcSmem | 0) : (uint16_t)X[k - (L.pe ? 1 : 0)]; };
+        auto wait_of = [&](int k) -> uint8_t {                        // whoever meets an input slot first waits for it
+            if (L.pe && k == 0) return li == 0 ? 4 : 0;
+            const int kb = k - (L.pe ? 1 : 0);
+            return (kb % 2 == 0) ? (uint8_t)(1 + kb / 2) : 0;
+        };
+        // phase A: chunks 0 and 1 together, one stage per K block
+        for (int k = 0; k < n_k; ++k) {
+            StageOp s{};
+            s.a_src0 = a_src(k); s.a_src1 = kSrcNone;
+            s.acc_col = (uint16_t)B;
+            s.n8 = (uint8_t)((L.widths[0] + L.widths[1]) / 8);
+            s.first = (uint8_t)(k == 0);
+            s.commit = (uint8_t)(k == n_k - 1 ? 2 : 0);
+            s.chunk = (uint8_t)chunk0;
+            s.wait_src = wait_of(k);
+            stages.push_back(s);
+            pack_unit(L, 0, k); pack_unit(L, 1, k);
+        }
+        // phase B: chunk 2 alone over [B, B+128), two K blocks per stage (the PE block, read from shared memory, gets a stage
+        // of its own next to an empty unit: the issuer handles one kind of A operand per stage)
+        if (L.n_chunks == 3) {
+            std::vector<std::pair<int, int>> sts;
+            int k = 0;
+            if (L.pe) { sts.push_back({0, -1}); k = 1; }
+            for (; k < n_k; k += 2) sts.push_back({k, k + 1 < n_k ? k + 1 : -1});
+            for (size_t i = 0; i < sts.size(); ++i) {
+                StageOp s{};
+                s.a_src0 = a_src(sts[i].first); s.a_src1 = sts[i].second >= 0 ? a_src(sts[i].second) : kSrcNone;
+                s.acc_col = (uint16_t)B;
+                s.n8 = 16;
+                s.first = (uint8_t)(i == 0);
+                s.commit = (uint8_t)(i + 1 == sts.size() ? 1 : 0);
+                s.chunk = (uint8_t)(chunk0 + 2);
+                s.wait_p = (uint8_t)(i == 0);
+                stages.push_back(s);
+                pack_unit(L, 2, sts[i].first); pack_unit(L, 2, sts[i].second);
+            }
+        }
+        // epilogue ops and where their packed outputs go
         std::vector<int> Y;
-        for (int j = 0; j < L.n_chunks; ++j, ++idx) {
-            const Chunk2& c = table[idx];
+        for (int j = 0; j < L.n_chunks; ++j) {
             const int width = L.widths[j];
-            const int acc_col = c.acc_slot * 64;
-            const int n_kb = (L.pe ? 1 : 0) + L.n_kb;
-            for (int k = 0; k < n_kb; ++k) {
-                const bool is_pe = L.pe && k == 0;
-                const int kb = k - (L.pe ? 1 : 0);
-                MmaOp2 m{};
-                m.a_src = is_pe ? (uint16_t)(kSrcSmem | 0) : (uint16_t)X[kb];
-                m.acc_col = (uint16_t)acc_col;
-                m.n8 = (uint8_t)(width / 8);
-                m.first = (uint8_t)(k == 0);
-                m.commit = (uint8_t)(k == n_kb - 1);
-                m.wait_src = 0;
-                if (j == 0) {                                           // the first chunk of a layer meets every input block first
-                    if (is_pe) m.wait_src = (li == 0) ? 4 : 0;
-                    else if (kb % 2 == 0) m.wait_src = (uint8_t)(1 + kb / 2);
-                }
-                mma.push_back(m);
-                PackOp p{};
-                p.w_idx = (int8_t)L.w_idx; p.transposed = 0;
-                p.row0 = (int16_t)(128 * j); p.valid_r = (int16_t)width;
-                if (is_pe) { p.col0 = 0; p.valid_c = HN_PE; p.l5_hidden = 0; }
-                else { p.col0 = (int16_t)(64 * kb); p.valid_c = 64; p.l5_hidden = (int8_t)L.l5_hidden; }
-                pack.push_back(p);
+            int acc = B + (j == 1 ? 128 : 0), out = -1, wait_next = 0;
+            if (L.to_tmem) {
+                if (L.n_chunks == 3) { out = j == 0 ? B + 192 : (j == 1 ? B + 128 : B); wait_next = (j == 0); }
+                else { out = j == 0 ? B + 192 : B + 128; }              // RGB_layer_1: [B+192, B+256) is outside its 192-wide accumulator
             }
             EpiOp2 e{};
-            e.acc_col = (uint16_t)acc_col;
-            e.out_col = c.out_slot < 0 ? kNoCol : (uint16_t)(c.out_slot * 64);
+            e.acc_col = (uint16_t)acc;
+            e.out_col = out < 0 ? kNoCol : (uint16_t)out;
             e.width32 = (uint8_t)(width / 32);
             e.kind = L.kind;
             e.ready_idx = L.to_tmem ? (uint8_t)j : 255;
-            e.density = (uint8_t)(L.density ? (j == L.n_chunks - 1 ? 2 : 1) : 0);
-            e.wait_prev = (uint8_t)c.wait_prev;
+            e.flags = (uint8_t)((L.density ? (j == L.n_chunks - 1 ? 2 : 1) : 0) | (wait_next ? 4 : 0) | ((L.n_chunks == 3 && j == 0) ? 8 : 0));
             e.bias_off = (uint16_t)(L.bias_off + 128 * j);
             e.col0 = (uint16_t)(128 * j);
             e.save_blk = L.save_blk < 0 ? 0xFFFF : (uint16_t)(L.save_blk + 2 * j);
             e.mask_word = L.mask_word < 0 ? 0xFFFF : (uint16_t)(L.mask_word + 4 * j);
             epi.push_back(e);
-            if (c.out_slot >= 0) for (int h = 0; h < width / 64; ++h) Y.push_back(c.out_slot * 64 + 32 * h);
+            if (out >= 0) for (int h = 0; h < width / 64; ++h) Y.push_back(out + 32 * h);
         }
+        chunk0 += L.n_chunks;
         X = Y;
     }
-    assert((int)mma.size() == kFwdUnits && (int)epi.size() == kFwdEpis);
+    assert((int)stages.size() == kFwdStages && (int)pack.size() == kFwdUnits && (int)epi.size() == kFwdEpis);
     memcpy(hs->fwd_pack, pack.data(), sizeof(PackOp) * kFwdUnits);
-    memcpy(hs->fwd.mma, mma.data(), sizeof(MmaOp2) * kFwdUnits);
+    memcpy(hs->fwd.stage, stages.data(), sizeof(StageOp) * kFwdStages);
     memcpy(hs->fwd.epi, epi.data(), sizeof(EpiOp2) * kFwdEpis);
-    hs->fwd.n_ops = kFwdUnits;
+    hs->fwd.n_stages = kFwdStages;
     // the PE block is free once FeaExt_module_5's last chunk has completed: the next tile's PE is produced there
     hs->fwd.pe_after_epi = 17;
     for (const EpiOp2& e : epi) if (e.ready_idx != 255) hs->fwd.n_ready[e.ready_idx]++;
@@ -313,7 +264,7 @@ std::vector<MmaOp> merge_k_pairs(const std::vector<MmaOp>& in) {
 HostSchedules* build() {
     auto* hs = new HostSchedules();
     memset(hs, 0, sizeof(*hs));
-    build_fwd2(hs);
+    build_fwd(hs);
     for (int with_pe = 1; with_pe >= 0; --with_pe) {
         // ---- data-gradient chain (reverse order); dL/dPE accumulated at FeaExt_module_5 and _0
         Builder b; b.n_acc = 3; b.backward = true;

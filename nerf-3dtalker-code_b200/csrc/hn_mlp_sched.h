@@ -67,51 +67,59 @@ struct EpiOp {
     uint16_t mask_word;            // word offset in the per-sample mask row, 0xFFFF = none
 };
 
-constexpr int kFwdUnits = 168;
+constexpr int kFwdUnits = 170;     // 168 weight units + 2 empty ones that keep every ring stage a PAIR of units
+constexpr int kFwdStages = kFwdUnits / 2;
 constexpr int kFwdEpis = 31;
 constexpr int kBwdUnitsMax = 176;
 constexpr int kBwdEpisMax = 36;
 
-// ---- forward chain, second generation: the A operand (activations) lives in TENSOR MEMORY.
-// TMEM (512 columns) is managed as eight 64-column slots.  A 128-wide accumulator chunk takes an aligned slot pair;
-// its epilogue packs the 128 fp32 columns to 64 columns of f16 pairs (two 64-wide K blocks of the next GEMM) and
-// stores them into a free slot, or in place over the first slot of its own accumulator.  The slot of every chunk is
-// chosen on the host by a small allocator that knows the only two ordering facts the kernel provides:
-//   (a) tcgen05.mma instructions execute in issue order (a later MMA may overwrite what an earlier one read);
-//   (b) the MMA issuer waits, before chunk n, for the epilogue of chunk n-2 to have drained its accumulator; the
-//       epilogue warps form two groups that take alternate chunks, so the stores of chunk n are ordered after the
-//       accumulator loads of chunk n (own group barrier) and of every chunk <= n-2 (through (a) and acc_full of n);
-//       a store into a slot drained by chunk n-1 (the other group) first waits for that group (EpiOp2::wait_prev).
-// Chunks are computed N-outer (one chunk over all its K blocks, then the next), so the weight units stream in
-// (layer, chunk, K block) order, one 16 KiB unit per ring stage.
-constexpr uint16_t kSrcSmem = 0x8000;   // MmaOp2::a_src flag: K block comes from shared memory (low bits: block index)
+// ---- forward chain: the A operand (activations) lives in TENSOR MEMORY; the two 256-column halves of TMEM alternate
+// between "accumulators of this layer" and "inputs of this layer" from layer to layer (and so from tile to tile: 11 layers).
+// Inside the accumulator half (base B) of a 384-wide layer:
+//   phase A  chunks 0 and 1 are ONE accumulator of 256 columns [B, B+256): every K block is a single tcgen05.mma of N = 256
+//            whose B operand is a ring stage = the two weight units (chunk 0 rows, chunk 1 rows) of that K block;
+//   phase B  chunk 2 reuses [B, B+128) once chunk 0's epilogue has drained it (barrier p_free); a stage holds two K blocks;
+//   outputs  (128 outputs -> 64 columns of packed f16 pairs): chunk 0 -> B+192 (upper half of chunk 1's accumulator, after
+//            the other epilogue group has loaded it), chunk 1 -> B+128 (in place), chunk 2 -> B (in place).
+// The next layer reads those three slots as its K blocks and accumulates in the OTHER half, whose last readers (this layer's
+// MMAs) precede it in issue order and whose last epilogue loads precede this layer's outputs: no accumulator barrier needed.
+// All TMEM columns in the tables are for even tiles; odd tiles use column ^ 256.
+constexpr uint16_t kSrcSmem = 0x8000;   // a_src flag: K block comes from shared memory (low bits: block index)
+constexpr uint16_t kSrcNone = 0x7FFF;   // second unit of the stage absent (phase A stage, or an empty unit)
 constexpr uint16_t kNoCol = 0xFFFF;
 
-struct MmaOp2 {
-    uint16_t a_src;                // TMEM column of the 32-column A K block, or kSrcSmem | shared-memory block
-    uint16_t acc_col;              // TMEM column of the accumulator chunk
-    uint8_t n8;                    // MMA N / 8
-    uint8_t first;                 // 1: first K block of the chunk (wait for the accumulator, overwrite it)
-    uint8_t commit;                // 1: last K block of the chunk -> acc_full
-    uint8_t wait_src;              // 0 none, 1..3 a_ready[c-1], 4 pe_ready
+struct StageOp {                   // 16 bytes, one per ring stage (two consecutive weight units), read as one 128-bit word
+    uint16_t a_src0;               // TMEM column of the A K block of the first MMA group, or kSrcSmem | block
+    uint16_t a_src1;               // same for the second MMA group (phase B), kSrcNone = none
+    uint16_t acc_col;              // TMEM column of the accumulator
+    uint8_t n8;                    // MMA N / 8 (32: two chunks at once, 24: RGB_layer_1, 16: one chunk)
+    uint8_t first;                 // 1: the first MMA of the stage overwrites the accumulator
+    uint8_t commit;                // chunks completed by this stage: 0, 1 or 2 -> acc_full of chunk, chunk + 1
+    uint8_t chunk;                 // first completing chunk (epilogue op index)
+    uint8_t wait_src;              // before the stage: 0 none, 1..3 a_ready[c-1], 4 pe_ready
+    uint8_t wait_p;                // 1: wait p_free (chunk 0's accumulator drained) before the stage
+    uint32_t pad;
 };
+static_assert(sizeof(StageOp) == 16, "StageOp is read as one 128-bit word");
 
-struct EpiOp2 {
+struct EpiOp2 {                   // 16 bytes: read with one 128-bit constant load
     uint16_t acc_col;              // TMEM column of the accumulator chunk
     uint16_t out_col;              // TMEM column of the packed output (64 columns per 128 outputs), kNoCol = none
-    uint8_t width32;               // columns / 32
-    uint8_t kind;
-    uint8_t ready_idx;             // a_ready barrier to arrive on, 255 = none
-    uint8_t density;               // 1 accumulate density dot, 2 = also finish it
-    uint8_t wait_prev;             // 1: the output slot was drained by chunk n-1: wait for the other group's loads
-    uint8_t pad;
     uint16_t bias_off;
     uint16_t col0;                 // first logical output column of this chunk
     uint16_t save_blk;             // first block of the save slot, 0xFFFF = none
     uint16_t mask_word;            // word offset in the per-sample mask row, 0xFFFF = none
+    uint8_t width32;               // columns / 32
+    uint8_t kind;
+    uint8_t ready_idx;             // a_ready barrier to arrive on, 255 = none
+    uint8_t flags;                 // bits 0-1: density (1 accumulate density dot, 2 = also finish it); bit 2: the output slot is
+                                   // the accumulator of chunk n+1: wait for the other group's loads; bit 3: signal p_free after
+                                   // this chunk's accumulator loads
 };
+static_assert(sizeof(EpiOp2) == 16, "EpiOp2 is read as one 128-bit word");
 
-struct FwdTables { MmaOp2 mma[kFwdUnits]; EpiOp2 epi[kFwdEpis]; int n_ops; int pe_after_epi; int n_ready[3]; };
+struct FwdTables { StageOp stage[kFwdStages]; EpiOp2 epi[kFwdEpis]; int n_stages; int pe_after_epi; int n_ready[3]; int pad; };
+
 struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_ops; int n_epis; int n_ready[3]; int n_empty[4]; };
 
 struct HostSchedules {

@@ -243,7 +243,7 @@ class RenderFunction(torch.autograd.Function):
         sigma, delta = torch.empty(M, device=dev), torch.empty(M, device=dev)
         act = torch.empty(lib.hn_act_bytes(M), dtype=torch.uint8, device=dev) if need_bwd else None
         masks = torch.empty(M * L.MASK_WORDS, dtype=torch.int32, device=dev) if need_bwd else None
-        status = torch.zeros(64, dtype=torch.int32, device=dev)
+        status = torch.zeros(64 if not os.environ.get("HN_TRACE") else 8192, dtype=torch.int32, device=dev)   # HN_TRACE: room for the debug timeline
         a = L.MlpFwd()
         a.cam = _camera(xy_c, R_c, T_c, K_c, tr_c, ns, meta["world_z1"], meta["world_z2"])
         a.bias, a.w_density, a.packed = _ptr(bias_c), _ptr(wd), _ptr(meta["packed"])

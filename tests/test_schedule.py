@@ -72,7 +72,6 @@ def _replay_fwd(mma, epi, n_tiles, late):
                 epi_load(loads_done); loads_done += 1
 
     for t in range(n_tiles):
-        chunk = t * n_chunks
         # producer chunk of every a_src column is whatever tag sits there when the layer's first chunk reads it; later
         # chunks of the same layer must see the very same tags
         seen = {}
@@ -83,8 +82,9 @@ def _replay_fwd(mma, epi, n_tiles, late):
                 # the MMA issuer blocks until that epilogue has stored: force exactly as much epilogue progress as needed
                 while ready[c] < ready_used[c]:
                     run_epilogues(min(stores_done + 1, commits), stores_done + 1)
+            chunk = t * n_chunks + m["chunk"]
             if m["first"] and chunk >= 2:
-                run_epilogues(chunk - 1, stores_done)  # accumulator loads of chunk n-2 done
+                run_epilogues(max(chunk - 1, loads_done), stores_done)  # accumulator loads of chunk n-2 done
             if not late:
                 run_epilogues(commits, commits)
             if not m["smem"]:
@@ -95,8 +95,8 @@ def _replay_fwd(mma, epi, n_tiles, late):
             for c in range(m["acc_col"], m["acc_col"] + m["n"], 32):
                 tm[c] = ("acc", chunk)
             if m["commit"]:
+                assert chunk == commits, "chunks must complete in epilogue order"
                 commits += 1
-                chunk += 1
     run_epilogues(commits, commits)
 
 
@@ -121,6 +121,8 @@ def test_forward_tmem_schedule(dump, late):
     # weight units follow the (layer, chunk, K block) stream
     for u, m in enumerate(mma):
         assert m["vr"] == m["n"] and m["row0"] % 128 == 0
+    firsts = [m["chunk"] for m in mma if m["first"]]
+    assert firsts == sorted(firsts), "chunks must start in order (the n-2 accumulator rule relies on it)"
 
 
 @pytest.mark.parametrize("which", ["bwd"])

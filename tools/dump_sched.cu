@@ -10,18 +10,20 @@ int main(int argc, char** argv) {
     const HostSchedules& hs = host_schedules();
     const bool bwd = argc > 1 && !strcmp(argv[1], "bwd");
     if (!bwd) {
-        // forward chain: A operand in tensor memory (MmaOp2 / EpiOp2)
-        printf("units %d epis %d pe_after %d\n", hs.fwd.n_ops, kFwdEpis, hs.fwd.pe_after_epi);
-        for (int u = 0; u < hs.fwd.n_ops; ++u) {
-            const MmaOp2& m = hs.fwd.mma[u];
-            printf("U %d smem %d a_src %d acc_col %d n %d first %d commit %d wait_src %d", u, (m.a_src & kSrcSmem) ? 1 : 0, m.a_src & 0x7FFF, m.acc_col,
-                   m.n8 * 8, m.first, m.commit, m.wait_src);
-            print_pack(hs.fwd_pack[u]);
+        // forward chain: A operand in tensor memory (StageOp / EpiOp2)
+        printf("stages %d epis %d pe_after %d\n", hs.fwd.n_stages, kFwdEpis, hs.fwd.pe_after_epi);
+        for (int u = 0; u < hs.fwd.n_stages; ++u) {
+            const StageOp& m = hs.fwd.stage[u];
+            printf("S %d chunk %d smem0 %d a0 %d smem1 %d a1 %d acc_col %d n %d first %d commit %d wait_src %d wait_p %d", u, m.chunk, (m.a_src0 & kSrcSmem) ? 1 : 0,
+                   m.a_src0 & 0x7FFF, (m.a_src1 != kSrcNone && (m.a_src1 & kSrcSmem)) ? 1 : 0, m.a_src1 == kSrcNone ? -1 : (m.a_src1 & 0x7FFF), m.acc_col, m.n8 * 8,
+                   m.first, m.commit, m.wait_src, m.wait_p);
+            print_pack(hs.fwd_pack[2 * u]);
+            printf("P %d", 2 * u + 1); print_pack(hs.fwd_pack[2 * u + 1]);
         }
         for (int e = 0; e < kFwdEpis; ++e) {
             const EpiOp2& o = hs.fwd.epi[e];
-            printf("E %d acc_col %d out_col %d width %d kind %d ready %d density %d wait_prev %d bias_off %d col0 %d save_blk %d mask_word %d\n", e, o.acc_col,
-                   o.out_col == kNoCol ? -1 : (int)o.out_col, o.width32 * 32, o.kind, o.ready_idx, o.density, o.wait_prev, o.bias_off, o.col0, o.save_blk, o.mask_word);
+            printf("E %d acc_col %d out_col %d width %d kind %d ready %d density %d wait_next %d signal_p %d bias_off %d col0 %d save_blk %d mask_word %d\n", e, o.acc_col,
+                   o.out_col == kNoCol ? -1 : (int)o.out_col, o.width32 * 32, o.kind, o.ready_idx, o.flags & 3, (o.flags >> 2) & 1, (o.flags >> 3) & 1, o.bias_off, o.col0, o.save_blk, o.mask_word);
         }
         return 0;
     }
