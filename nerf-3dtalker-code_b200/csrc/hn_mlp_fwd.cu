@@ -373,14 +373,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                     };
                     emit(v0, 0);
                     emit(v1, 1);
-                    HN_PC_LAP(ec, 4);
+                    HN_PC_LAP(ec, 9);
                 } else {
                     auto convert = [&](const uint32_t (&v)[32], int pc, uint32_t (&pk)[16]) {
+#ifdef HN_EXP_X4
+                        for (int i = 0; i < 16; ++i) pk[i] = v[i] ^ v[i + 16];
+                        return;
+#endif
                         float y[32];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float4 bb;
+#ifdef HN_EXP_X2
+                            bb = make_float4(0.5f, 0.25f, 0.125f, 1.f);
+#else
                             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(bp + pc * 128 + i * 16));
+#endif
                             y[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
                             y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
                             y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
@@ -420,19 +428,33 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                     } else {
                         // every warp has read its part of this accumulator (and, after a held chunk, of the previous one): stores
                         // into in-place or neighbouring columns are safe now
+#ifndef HN_EXP_X1
                         wait_spin(&sh.loaded[n & 7], (n >> 3) & 1, &sh.abort, a.status, 330);
                         tc_fence_after_sync();
+#endif
                         if (holding) {
+                            // chunk 0's output first, signalled at once: the next layer's first K blocks are what the MMA
+                            // issuer will ask for as soon as chunk 2 is issued
                             tmem_st16(hold_addr, hold0);
                             tmem_st16(hold_addr + 16, hold1);
+                            tmem_st_wait();
+                            tc_fence_before_sync();
+                            warp_arrive(smem_u32(&sh.a_ready[0]), lane);
+                            holding = false;
                         }
                         if (active) {
                             uint32_t pk[16];
                             convert(v0, 0, pk);
+#ifndef HN_EXP_X3
                             tmem_st16(out_addr, pk);
+#endif
                             if (save) store_row_packed(stg, row, 64 * g, pk);
                             convert(v1, 1, pk);
+#ifndef HN_EXP_X3
                             tmem_st16(out_addr + 16, pk);
+#else
+                            if (pk[3] == 0x12345u) a.sigma[m] = 0.f;
+#endif
                             if (save) store_row_packed(stg, row, 64 * g + 32, pk);
                         }
                     }
@@ -443,7 +465,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                 if (save) { fence_async_smem(); warp_arrive(smem_u32(&sh.stg_full[sb]), lane); ++sidx; }
                 if (op.kind != EPI_FEAT && !op.wait_next) {
                     tc_fence_before_sync();
-                    if (holding) { warp_arrive(smem_u32(&sh.a_ready[0]), lane); holding = false; }     // the held chunk is chunk 0 of its layer
                     if (op.ready_idx != 255) warp_arrive(smem_u32(&sh.a_ready[op.ready_idx]), lane);
                 }
                 HN_PC_LAP(ec, 6);

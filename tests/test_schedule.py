@@ -27,7 +27,7 @@ def dump():
         mma, epi = [], []
         for line in out.splitlines():
             kv = dict(re.findall(r"(\w+) (-?\d+)", line.replace("|", " ")))
-            if line.startswith("U "):
+            if line.startswith("U ") or line.startswith("S "):
                 mma.append({k: int(v) for k, v in kv.items()})
             elif line.startswith("E "):
                 epi.append({k: int(v) for k, v in kv.items()})
@@ -35,94 +35,105 @@ def dump():
     return run
 
 
-def _replay_fwd(mma, epi, n_tiles, late):
-    """Replays the forward chain (A operand in tensor memory) against the two ordering facts the kernel provides
-    (MMAs execute in issue order; chunk n's MMAs wait for the accumulator loads of chunk n-2; epilogue stores of chunk n
-    follow the loads of every chunk <= n) with the epilogues running as EARLY or as LATE as those facts allow, tagging
-    every 32-column TMEM block with what was last written there.  Asserts that every MMA reads the K block it expects
-    and every epilogue drains its own, unclobbered accumulator."""
-    tm = {}                                           # 32-column block -> tag
+def _replay_fwd(stages, epi, n_tiles, late):
+    """Replays the forward chain (A operand in tensor memory, alternating TMEM halves) against the ordering facts the kernel
+    provides - MMAs execute in issue order; a stage with wait_src waits for that a_ready barrier, one with wait_p for the
+    accumulator loads of chunk-2; the epilogue takes chunks in order, loads a chunk only after its commit, stores chunk 0 of
+    a pair together with chunk 1 (after chunk 1's loads), any other chunk after its own loads - with the epilogue running as
+    EARLY or as LATE as those facts allow.  Every 32-column TMEM block is tagged with what was last written there; every MMA
+    must read the K block it expects and every epilogue must drain its own, unclobbered accumulator."""
+    tm = {}
     n_chunks = len(epi)
-    loads_done = stores_done = 0                      # global epilogue progress (chunk counters)
+    loads_done = stores_done = 0                      # chunks whose accumulator has been loaded / whose output has been stored
     commits = 0
     ready = [0, 0, 0]; ready_used = [0, 0, 0]
 
-    def epi_load(n):
-        t, e = divmod(n, n_chunks)
-        op = epi[e]
-        for c in range(op["acc_col"], op["acc_col"] + op["width"], 32):
-            assert tm.get(c) == ("acc", n), f"epilogue {e} (tile {t}) finds {tm.get(c)} at column {c}"
+    def hx(n):
+        return 256 if (n // n_chunks) & 1 else 0
 
-    def epi_store(n):
-        t, e = divmod(n, n_chunks)
-        op = epi[e]
+    def do_load(n):
+        op = epi[n % n_chunks]
+        for c in range(op["acc_col"], op["acc_col"] + op["width"], 32):
+            assert tm.get(c ^ hx(n)) == ("acc", n), f"epilogue of chunk {n} finds {tm.get(c ^ hx(n))} at column {c ^ hx(n)}"
+
+    def do_store(n):
+        op = epi[n % n_chunks]
         if op["out_col"] >= 0:
             for h in range(op["width"] // 64):
-                tm[op["out_col"] + 32 * h] = ("act", n, h)
+                tm[(op["out_col"] + 32 * h) ^ hx(n)] = ("act", n, h)
         if op["ready"] != 255:
             ready[op["ready"]] += 1
 
-    def run_epilogues(until_loads, until_stores):
+    def step_epilogue():
+        """one more epilogue event, in program order; returns False if it has to wait for a commit"""
         nonlocal loads_done, stores_done
-        while loads_done < until_loads or stores_done < until_stores:
-            if stores_done < loads_done:              # a warp stores chunk n before it loads chunk n+1
-                epi_store(stores_done); stores_done += 1
+        n = loads_done
+        pending_store = stores_done < loads_done      # a loaded chunk whose output is not stored yet
+        if pending_store:
+            m = stores_done
+            if epi[m % n_chunks]["wait_next"] and loads_done == m + 1:
+                pass                                  # held: stored after the NEXT chunk's loads
             else:
-                assert loads_done < commits, "epilogue would wait for an accumulator that is never committed"
-                epi_load(loads_done); loads_done += 1
+                do_store(m); stores_done += 1
+                return True
+        if n >= commits:
+            return False
+        do_load(n); loads_done += 1
+        return True
 
+    def run_until(cond):
+        while not cond():
+            assert step_epilogue(), "deadlock: the epilogue waits for a commit the MMA issuer cannot reach"
+
+    seen = {}
     for t in range(n_tiles):
-        # producer chunk of every a_src column is whatever tag sits there when the layer's first chunk reads it; later
-        # chunks of the same layer must see the very same tags
-        seen = {}
-        for u, m in enumerate(mma):
+        base = t * n_chunks
+        layer_key = None
+        for u, m in enumerate(stages):
             if m["wait_src"] in (1, 2, 3):
                 c = m["wait_src"] - 1
                 ready_used[c] += 1
-                # the MMA issuer blocks until that epilogue has stored: force exactly as much epilogue progress as needed
-                while ready[c] < ready_used[c]:
-                    run_epilogues(min(stores_done + 1, commits), stores_done + 1)
-            chunk = t * n_chunks + m["chunk"]
-            if m["first"] and chunk >= 2:
-                run_epilogues(max(chunk - 1, loads_done), stores_done)  # accumulator loads of chunk n-2 done
+                run_until(lambda: ready[c] >= ready_used[c])
+            if m["wait_p"]:
+                run_until(lambda: loads_done > base + m["chunk"] - 2)
             if not late:
-                run_epilogues(commits, commits)
-            if not m["smem"]:
-                tag = tm.get(m["a_src"])
-                assert tag is not None and tag[0] == "act", f"MMA unit {u} (tile {t}) reads {tag} at column {m['a_src']}"
-                seen.setdefault((layer_first_of(mma, u), m["a_src"]), tag)
-                assert seen[(layer_first_of(mma, u), m["a_src"])] == tag, f"MMA unit {u}: K block at column {m['a_src']} changed under the layer"
+                while step_epilogue():
+                    pass
+            if m["first"] and m["wait_src"] in (1, 4):
+                layer_key = (t, u)
+            for a_src, smem in ((m["a0"], m["smem0"]), (m["a1"], m["smem1"])):
+                if a_src < 0 or smem:
+                    continue
+                col = a_src ^ (256 if t & 1 else 0)
+                tag = tm.get(col)
+                assert tag is not None and tag[0] == "act", f"stage {u} (tile {t}) reads {tag} at column {col}"
+                seen.setdefault((layer_key, a_src), tag)
+                assert seen[(layer_key, a_src)] == tag, f"stage {u}: K block at column {col} changed under the layer"
             for c in range(m["acc_col"], m["acc_col"] + m["n"], 32):
-                tm[c] = ("acc", chunk)
-            if m["commit"]:
-                assert chunk == commits, "chunks must complete in epilogue order"
+                chunk = base + m["chunk"] + (1 if (m["n"] > 128 and c >= m["acc_col"] + 128) else 0)
+                tm[c ^ (256 if t & 1 else 0)] = ("acc", chunk)
+            for k in range(m["commit"]):
+                assert base + m["chunk"] + k == commits, "chunks must complete in epilogue order"
                 commits += 1
-    run_epilogues(commits, commits)
-
-
-def layer_first_of(mma, u):
-    """index of the first unit of the layer that unit u belongs to (layers start where a_ready[0] / pe_ready is awaited)"""
-    while not (mma[u]["wait_src"] in (1, 4) and mma[u]["first"]):
-        u -= 1
-    return u
+    while step_epilogue():
+        pass
+    assert loads_done == commits == n_tiles * n_chunks and stores_done == commits
 
 
 @pytest.mark.parametrize("late", [False, True])
 def test_forward_tmem_schedule(dump, late):
-    mma, epi = dump("fwd")
-    assert len(mma) == 168 and len(epi) == 31
+    stages, epi = dump("fwd")
+    assert len(stages) == 85 and len(epi) == 31
     for c in range(3):
         arrivals = sum(1 for e in epi if e["ready"] == c)
-        waits = sum(1 for m in mma if m["wait_src"] == 1 + c)
+        waits = sum(1 for m in stages if m["wait_src"] == 1 + c)
         assert arrivals == waits, f"a_ready[{c}]: {arrivals} arrivals vs {waits} waits"
-    assert sum(m["commit"] for m in mma) == len(epi) and sum(m["first"] for m in mma) == len(epi)
-    # every layer's K blocks come from the previous layer's chunks in order (chunk j -> K blocks 2j, 2j+1)
-    _replay_fwd(mma, epi, 3, late)
-    # weight units follow the (layer, chunk, K block) stream
-    for u, m in enumerate(mma):
-        assert m["vr"] == m["n"] and m["row0"] % 128 == 0
-    firsts = [m["chunk"] for m in mma if m["first"]]
-    assert firsts == sorted(firsts), "chunks must start in order (the n-2 accumulator rule relies on it)"
+    assert sum(m["commit"] for m in stages) == len(epi)
+    # a chunk whose output is held for its neighbour must be followed by a chunk of the same layer that stores
+    for i, e in enumerate(epi):
+        if e["wait_next"]:
+            assert i + 1 < len(epi) and not epi[i + 1]["wait_next"] and epi[i + 1]["ready"] == 1 and e["ready"] == 0
+    _replay_fwd(stages, epi, 4, late)
 
 
 @pytest.mark.parametrize("which", ["bwd"])

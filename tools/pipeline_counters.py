@@ -21,7 +21,7 @@ for need_grad in (False, True):
     epi = st[18:50].view(torch.int64).tolist()
     tiles = (2 * 4096 * 64 // 128 + 147) // 148
     mn = ["total", "wait_pe", "wait_a_ready", "wait_acc_empty", "wait_w_full", "-", "issue_mma", "commit"]
-    en = ["total", "wait_acc_full", "ld+convert0", "release_acc(+waits)", "convert1+st", "tmem_st_wait", "arrives", "density", "next_pe"]
+    en = ["total", "wait_acc_full", "tmem_ld+arrive", "-", "convert+stores", "tmem_st_wait", "stage/a_ready arrives", "density", "-", "feat_store"]
     print("saving" if need_grad else "inference", "| cycles per tile:", mma[0] // tiles)
     print("  MMA thread :", {n: f"{v / max(mma[0], 1):.3f}" for n, v in zip(mn, mma)})
-    print("  epilogue w0 (cycles/op):", {n: int(v / tiles / 15.5) for n, v in zip(en, epi)})
+    print("  epilogue w0 (cycles/op):", {n: int(v / tiles / 31) for n, v in zip(en, epi)})
