@@ -149,28 +149,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
             // the whole warp walks the schedule (uniform control flow keeps descriptors in uniform registers); one
             // elected lane issues the MMAs and commits
             uint32_t uc = 0, par_ready = 0, par_in = 0, par_empty = 0;
+            // The issuer shares its scheduler with four epilogue warps and gets a fraction of the issue slots, so what it
+            // executes per MMA bounds the tensor pipe: dependencies are polled without clock reads, the NEXT unit's weight
+            // barrier is queried before its answer is needed, and one elected-lane block issues the MMAs and the commits.
+            bool pre = !PAIR && mbar_try_wait(smem_u32(&sh.w_full[0]), 0);
+            MmaOp op = tb.mma[0];
             for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
-                MmaOp op = tb.mma[0];
                 for (int u = 0; u < n_ops; ++u, ++uc) {
                     const MmaOp nxt = tb.mma[u + 1 < n_ops ? u + 1 : 0];          // table read off the critical path
                     bool ok = true;
                     if (op.wait_src == 5) {
-                        ok = wait_or_abort(&sh.in_ready, par_in, &sh.abort, a.status, 501);
+                        ok = wait_spin(&sh.in_ready, par_in, &sh.abort, a.status, 501);
                         if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.in_peer, par_in, &sh.abort, a.status, 509);
                         par_in ^= 1;
                     } else if (op.wait_src) {
                         const int c = op.wait_src - 1;
-                        ok = wait_or_abort(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 502 + c);
+                        ok = wait_spin(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 502 + c);
                         if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.a_ready_p[c], (par_ready >> c) & 1, &sh.abort, a.status, 242 + c);
                         par_ready ^= 1u << c;
                     }
                     if (ok && op.wait_empty) {
-                        ok = wait_or_abort(&sh.acc_empty[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 510 + op.q);
+                        ok = wait_spin(&sh.acc_empty[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 510 + op.q);
                         if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.acc_empty_p[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 246 + op.q);
                         par_empty ^= 1u << op.q;
                     }
                     const uint32_t stage = uc % STAGES, par = (uc / STAGES) & 1;
-                    if (ok) ok = wait_or_abort(&sh.w_full[stage], par, &sh.abort, a.status, 520);
+                    if (ok && !pre) ok = wait_spin(&sh.w_full[stage], par, &sh.abort, a.status, 520);
                     if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.w_peer[stage], par, &sh.abort, a.status, 521);
                     if (!ok) break;
                     tc_fence_after_sync();
@@ -180,6 +184,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
                     const uint32_t d_addr = tmem_base + (uint32_t)op.tmem_col8 * 8;
                     const uint32_t a_lo = desc_lo(a_addr, 16), b_lo = desc_lo(b_addr, 16);
                     const uint32_t first = op.first, nkb = op.nkb;
+                    const uint32_t empty_bar = smem_u32(&sh.w_empty[stage]), full_bar = smem_u32(&sh.acc_full[op.q]);
                     if (elect_one()) {
                         for (uint32_t k = 0; k < nkb; ++k) {
 #pragma unroll
@@ -187,10 +192,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
                                 umma_lohi_x<PAIR>(d_addr, a_lo + k * (kUnitBytes >> 4) + ks * 2, b_lo + k * (KB_STRIDE >> 4) + ks * 2, idesc,
                                                   (first && k == 0 && ks == 0) ? 0u : 1u);
                         }
-                        umma_commit_x<PAIR>(smem_u32(&sh.w_empty[stage]));
-                        if (op.commit) umma_commit_x<PAIR>(smem_u32(&sh.acc_full[op.q]));
+                        umma_commit_x<PAIR>(empty_bar);
+                        if (op.commit) umma_commit_x<PAIR>(full_bar);
                     }
                     __syncwarp();
+                    // ask for the next unit's weights now; the answer is consumed at the top of the next iteration
+                    pre = !PAIR && mbar_try_wait(smem_u32(&sh.w_full[(uc + 1) % STAGES]), ((uc + 1) / STAGES) & 1);
                     op = nxt;
                 }
             }

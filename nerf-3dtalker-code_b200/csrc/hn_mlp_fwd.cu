@@ -42,7 +42,9 @@ constexpr uint32_t kOffBias = kOffStg + 4 * kUnitBytes;     // this item's effec
 constexpr uint32_t kBiasBytes = HN_BIAS_STRIDE * 4;
 constexpr uint32_t kOffShared = kOffBias + kBiasBytes;      // barriers and small arrays (FwdShared) close the dynamic region
 constexpr uint32_t kTmemCols = 512;
-constexpr int kFwdEpiWarps = 8;                              // two epilogue groups of four warps take alternate accumulator chunks
+constexpr int kFwdEpiWarps = 8;                              // (4 TMEM lane quarters) x (2 column groups of a 128-column chunk); a 16-warp
+                                                            // (4 column groups, 96 registers) variant was tried: slower issuer, no gain
+constexpr int kPW = 16 / kFwdEpiWarps;                      // 32-column pieces per warp and chunk: 2 or 1
 constexpr int kGroupWarps = kFwdEpiWarps / 2;
 constexpr int kFwdEpiThreads = kFwdEpiWarps * 32;
 constexpr int kFwdThreads = (kFwdEpiWarps + kCtrlWarps) * 32; // 384 = 12 warps (registers are granted per 4 warps: 13 would cost like 16)
@@ -287,14 +289,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
         // reuse chunk 0's columns - and to "outputs stored".  Few, fat warps on purpose: the issuer shares its scheduler with
         // two of them.
         const int ew = warp;
-        const int g = ew >> 2, quarter = ew & 3;                    // g: columns [64g, 64g+64) of every chunk
+        const int g = ew >> 2, quarter = ew & 3;                    // g: columns [32 kPW g, 32 kPW (g+1)) of every chunk
+        constexpr int CW = 32 * kPW;                                // accumulator columns per warp
         const int row = quarter * 32 + lane;                        // tile row = TMEM lane
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t base_n = 0, sidx = 0, tile_i = 0;                  // first chunk index of the tile; saved chunks so far
         const int pe_after = c_fwd.pe_after_epi;
         int cached_b = -1;
         for (int i = tid; i < HN_HIDDEN; i += kFwdEpiThreads) sh.w_density[i] = __ldg(a.w_density + i);
-        (&sh.dens[0][0])[tid] = 0.f;
+        if (tid < 256) (&sh.dens[0][0])[tid] = 0.f;
         named_sync(3, kFwdEpiThreads);
 
         HN_PC_DECL(ec, 16);
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
             }
             const uint32_t bias_row = smem + kOffBias;
             const uint32_t hx = (tile_i & 1u) << 8;                 // odd tiles: the TMEM halves swap roles
-            uint32_t hold0[16], hold1[16];                          // packed output of chunk 0 of a pair, stored with chunk 1's
+            uint32_t hold[kPW][16];                                 // packed output of chunk 0 of a pair, stored with chunk 1's
             uint32_t hold_addr = 0;
             bool holding = false;
             for (int e = 0; e < kFwdEpis; ++e) {
@@ -329,11 +332,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                 // FeaExt_module_5's last chunk is complete: every MMA that reads the PE block has run
                 if (e == pe_after) warp_arrive(smem_u32(&sh.pe_consumed), lane);
                 const bool save = saving && op.save_blk != 0xFFFF;
-                const bool active = 2 * g < (int)op.width32;       // RGB_layer_1's second chunk has 64 columns: the upper half idles
-                const uint32_t bp = bias_row + (op.bias_off + 64 * g) * 4;
-                const uint32_t acc_addr = tmem_base + lane_base + (op.acc_col ^ hx) + 64 * g;
-                uint32_t v0[32], v1[32];
-                if (active) { tmem_ld32(acc_addr, v0); tmem_ld32(acc_addr + 32, v1); }
+                const bool active = kPW * g < (int)op.width32;     // RGB_layer_1's second chunk has 64 columns: the upper column groups idle
+                const uint32_t bp = bias_row + (op.bias_off + CW * g) * 4;
+                const uint32_t acc_addr = tmem_base + lane_base + (op.acc_col ^ hx) + CW * g;
+                uint32_t v[kPW][32];
+                if (active) {
+#pragma unroll
+                    for (int pc = 0; pc < kPW; ++pc) tmem_ld32(acc_addr + 32 * pc, v[pc]);
+                }
                 tmem_ld_wait();
                 tc_fence_before_sync();
                 warp_arrive(smem_u32(&sh.loaded[n & 7]), lane);    // (the MMA issuer waits on this for chunk 0 before it starts chunk 2)
@@ -346,9 +352,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                     // buffer whose last saved chunk is the older one (chunk 29 -> buffer of chunk 27, chunk 30 -> of chunk 28).
                     const uint32_t fb = (sidx + (uint32_t)(e & 1 ? 0 : 1)) & 1;     // e = 29: sidx & 1;  e = 30: (sidx + 1) & 1
                     const uint32_t fidx = sidx + (uint32_t)(e & 1 ? 0 : 1);
-                    if (saving) wait_spin(&sh.stg_free[fb], ((fidx >> 1) & 1) ^ 1, &sh.abort, a.status, 340);
-                    const uint32_t stg = smem + kOffStg + fb * 2 * kUnitBytes + (uint32_t)ew * 4096;   // 32 rows x 128 B per warp
-                    float* gbase = a.feat + ((size_t)tile * HN_TILE + quarter * 32) * HN_FEAT + op.col0 + 64 * g;
+                    if (saving) {
+                        wait_spin(&sh.stg_free[fb], ((fidx >> 1) & 1) ^ 1, &sh.abort, a.status, 340);
+                        if (kFwdEpiWarps == 16) wait_spin(&sh.stg_free[fb ^ 1], (((fidx + 1) >> 1) & 1) ^ 1, &sh.abort, a.status, 342);   // scratch spans both buffers
+                    }
+                    const uint32_t stg = smem + kOffStg + (kFwdEpiWarps == 8 ? fb * 2 * kUnitBytes : 0u) + (uint32_t)ew * 4096;   // 32 rows x 128 B per warp
+                    float* gbase = a.feat + ((size_t)tile * HN_TILE + quarter * 32) * HN_FEAT + op.col0 + CW * g;
                     auto emit = [&](const uint32_t (&v)[32], int pc) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -371,8 +380,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                         }
                         __syncwarp();
                     };
-                    emit(v0, 0);
-                    emit(v1, 1);
+#pragma unroll
+                    for (int pc = 0; pc < kPW; ++pc) emit(v[pc], pc);
                     HN_PC_LAP(ec, 9);
                 } else {
                     auto convert = [&](const uint32_t (&v)[32], int pc, uint32_t (&pk)[16]) {
@@ -396,9 +405,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                         }
                         if (op.kind == EPI_HIDDEN) {
                             if (a.masks && op.mask_word != 0xFFFF)
-                                a.masks[m * HN_MASK_WORDS + op.mask_word + 2 * g + pc] = positive_mask32(y);
+                                a.masks[m * HN_MASK_WORDS + op.mask_word + kPW * g + pc] = positive_mask32(y);
                             if (op.density) {                      // density head on the fp32 activations (models.py:78,83)
-                                const float4* wp = reinterpret_cast<const float4*>(sh.w_density + op.col0 + 64 * g + pc * 32);
+                                const float4* wp = reinterpret_cast<const float4*>(sh.w_density + op.col0 + CW * g + pc * 32);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     const float4 ww = wp[i];
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                             for (int i = 0; i < 16; ++i) pk[i] = pack_sat(y[2 * i], y[2 * i + 1]);
                         }
                     };
-                    const uint32_t out_addr = tmem_base + lane_base + (op.out_col ^ hx) + 32 * g;
+                    const uint32_t out_addr = tmem_base + lane_base + (op.out_col ^ hx) + (CW / 2) * g;
                     const uint32_t stg = smem + kOffStg + sb * 2 * kUnitBytes;
                     // staging buffer: has the bulk store of its previous saved chunk read it?
                     if (save) wait_spin(&sh.stg_free[sb], ((sidx >> 1) & 1) ^ 1, &sh.abort, a.status, 341);
@@ -421,8 +430,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                         // chunk 0 of a pair: its output slot is the upper half of chunk 1's accumulator, which is read only in the
                         // next iteration - keep the packed columns in registers (the saved image can be staged now)
                         if (active) {
-                            convert(v0, 0, hold0); convert(v1, 1, hold1);
-                            if (save) { store_row_packed(stg, row, 64 * g, hold0); store_row_packed(stg, row, 64 * g + 32, hold1); }
+#pragma unroll
+                            for (int pc = 0; pc < kPW; ++pc) {
+                                convert(v[pc], pc, hold[pc]);
+                                if (save) store_row_packed(stg, row, CW * g + 32 * pc, hold[pc]);
+                            }
                         }
                         hold_addr = out_addr; holding = true;
                     } else {
@@ -435,27 +447,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                         if (holding) {
                             // chunk 0's output first, signalled at once: the next layer's first K blocks are what the MMA
                             // issuer will ask for as soon as chunk 2 is issued
-                            tmem_st16(hold_addr, hold0);
-                            tmem_st16(hold_addr + 16, hold1);
+#pragma unroll
+                            for (int pc = 0; pc < kPW; ++pc) tmem_st16(hold_addr + 16 * pc, hold[pc]);
                             tmem_st_wait();
                             tc_fence_before_sync();
                             warp_arrive(smem_u32(&sh.a_ready[0]), lane);
                             holding = false;
                         }
                         if (active) {
-                            uint32_t pk[16];
-                            convert(v0, 0, pk);
-#ifndef HN_EXP_X3
-                            tmem_st16(out_addr, pk);
-#endif
-                            if (save) store_row_packed(stg, row, 64 * g, pk);
-                            convert(v1, 1, pk);
-#ifndef HN_EXP_X3
-                            tmem_st16(out_addr + 16, pk);
-#else
-                            if (pk[3] == 0x12345u) a.sigma[m] = 0.f;
-#endif
-                            if (save) store_row_packed(stg, row, 64 * g + 32, pk);
+#pragma unroll
+                            for (int pc = 0; pc < kPW; ++pc) {
+                                uint32_t pk[16];
+                                convert(v[pc], pc, pk);
+                                tmem_st16(out_addr + 16 * pc, pk);
+                                if (save) store_row_packed(stg, row, CW * g + 32 * pc, pk);
+                            }
                         }
                     }
                     HN_PC_LAP(ec, 4);
