@@ -204,6 +204,59 @@ typedef struct {
 size_t hn_wgrad_workspace_bytes(int B);
 int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * High-precision mode ("fp32-accumulate mode" with split operands): the same chain, layer by layer, with
+ * fp32 activations in HBM and every tensor-core product computed as hi*hi + lo*hi + hi*lo over
+ * half-precision hi/lo splits of BOTH operands (~22 significant bits; csrc/hn_precise.cu).
+ * Replaces the same reference code as hn_mlp_fwd / hn_mlp_bwd_data (NetWorks/models.py:62-87,
+ * NetWorks/utils.py:43-51,147-161 and their autograd); used when the feature-map tolerance must hold at
+ * any activation scale and for the ill-conditioned camera gradients.
+ * Workspaces are fp32, sample-major: `acts` = [PE 64 | FeaExt_module_0..7 8x384 | RGB_layer_0 384 |
+ * RGB_layer_1 192] floats per sample, stored buffer after buffer (buffer k at acts + M*offset_k, row
+ * stride = its width); `gz` = [dZ FeaExt_module_0..7 8x384 | dZ RGB_layer_0 384 | dZ RGB_layer_1 192 |
+ * dL/dPE 64], loss-scaled by *grad_scale.  Both have hn_precise_workspace_floats(M) elements.          */
+size_t hn_precise_packed_bytes(void);
+size_t hn_precise_workspace_floats(int64_t M);
+int hn_pack_weights_precise(const hn_weights_t* w, void* packed_hl, void* stream);
+
+typedef struct {
+    hn_camera_t cam;
+    const float* bias;        /* [B, HN_BIAS_STRIDE] effective biases                                 */
+    const float* w_density;   /* [384]                                                                */
+    const void* packed_hl;    /* from hn_pack_weights_precise                                         */
+    float* feat;              /* [M,256] out                                                          */
+    float* sigma;             /* [M] out                                                              */
+    float* delta;             /* [M] out                                                              */
+    float* zvals;             /* [M] out or NULL                                                      */
+    float* acts;              /* workspace / saved activations (see above)                            */
+    int* status;
+} hn_mlp_fwd_precise_t;
+
+int hn_mlp_fwd_precise(const hn_mlp_fwd_precise_t* a, void* stream);
+
+typedef struct {
+    hn_camera_t cam;
+    const void* packed_hl;
+    const float* w_density;
+    const float* dfeat;       /* [M,256] fp32, unscaled (hn_composite_bwd)                            */
+    const float* dsigma;      /* [M] unscaled                                                         */
+    const float* ddelta;      /* [M] unscaled or NULL                                                 */
+    const float* sigma;       /* [M] saved forward output                                             */
+    const float* grad_scale;  /* device scalar (power of two)                                         */
+    const float* acts;        /* saved by hn_mlp_fwd_precise                                          */
+    float* gz;                /* out: pre-activation gradients (see above)                            */
+    float* g_ray_o;           /* [B*n_rays,3] accumulated, or NULL (no camera gradients)              */
+    float* g_ray_v;
+    float* g_ray_l;
+    float* dbias;             /* [B, HN_BIAS_STRIDE] accumulated (caller zero-initialises), or NULL   */
+    void* act_image;          /* optional: half-precision operand images of acts / gz / dfeat in the  */
+    void* grads_image;        /* layouts hn_mlp_bwd_weights reads (all three or none)                 */
+    void* dfeat_image;
+    int* status;
+} hn_mlp_bwd_data_precise_t;
+
+int hn_mlp_bwd_data_precise(const hn_mlp_bwd_data_precise_t* a, void* stream);
+
 /* Bytes of the saved-for-backward buffers for M samples. */
 size_t hn_act_bytes(int64_t M);
 size_t hn_grads_bytes(int64_t M);

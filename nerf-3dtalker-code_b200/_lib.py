@@ -57,9 +57,22 @@ class MlpBwdWeights(C.Structure):
                 ("items_workspace", _p), ("items_workspace_bytes", C.c_size_t), ("status", _p)]
 
 
+class MlpFwdPrecise(C.Structure):
+    _fields_ = [("cam", Camera), ("bias", _p), ("w_density", _p), ("packed_hl", _p), ("feat", _p), ("sigma", _p),
+                ("delta", _p), ("zvals", _p), ("acts", _p), ("status", _p)]
+
+
+class MlpBwdDataPrecise(C.Structure):
+    _fields_ = [("cam", Camera), ("packed_hl", _p), ("w_density", _p), ("dfeat", _p), ("dsigma", _p), ("ddelta", _p),
+                ("sigma", _p), ("grad_scale", _p), ("acts", _p), ("gz", _p), ("g_ray_o", _p), ("g_ray_v", _p),
+                ("g_ray_l", _p), ("dbias", _p), ("act_image", _p), ("grads_image", _p), ("dfeat_image", _p), ("status", _p)]
+
+
 EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pack_weights", "hn_sample_rays",
            "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
-           "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes"]
+           "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes",
+           "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
+           "hn_mlp_bwd_data_precise"]
 
 _lib = None
 
@@ -87,6 +100,12 @@ def load():
     lib.hn_wgrad_workspace_bytes.restype = C.c_size_t
     lib.hn_wgrad_workspace_bytes.argtypes = [C.c_int]
     lib.hn_pack_weights.argtypes = [C.POINTER(Weights), _p, _p]
+    lib.hn_precise_packed_bytes.restype = C.c_size_t
+    lib.hn_precise_workspace_floats.restype = C.c_size_t
+    lib.hn_precise_workspace_floats.argtypes = [C.c_int64]
+    lib.hn_pack_weights_precise.argtypes = [C.POINTER(Weights), _p, _p]
+    lib.hn_mlp_fwd_precise.argtypes = [C.POINTER(MlpFwdPrecise), _p]
+    lib.hn_mlp_bwd_data_precise.argtypes = [C.POINTER(MlpBwdDataPrecise), _p]
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
     lib.hn_mlp_fwd.argtypes = [C.POINTER(MlpFwd), _p]
     lib.hn_composite_fwd.argtypes = [C.POINTER(CompositeFwd), _p]
@@ -94,7 +113,8 @@ def load():
     lib.hn_mlp_bwd_data.argtypes = [C.POINTER(MlpBwdData), _p]
     lib.hn_mlp_bwd_weights.argtypes = [C.POINTER(MlpBwdWeights), _p]
     for name in ("hn_pack_weights", "hn_sample_rays", "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd",
-                 "hn_mlp_bwd_data", "hn_mlp_bwd_weights"):
+                 "hn_mlp_bwd_data", "hn_mlp_bwd_weights", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
+                 "hn_mlp_bwd_data_precise"):
         getattr(lib, name).restype = C.c_int
     if lib.hn_abi_version() != 1:
         raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")

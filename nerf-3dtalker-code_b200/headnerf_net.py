@@ -6,6 +6,8 @@ fg_CD_predictor -> compositing) runs in libheadnerf_b200.so instead of eager tor
 (shape/expression(+gaze), audio style, appearance) never get broadcast to [B,C,N_r,N_s] (HeadNeRFNet.py:149-152):
 their weight columns are folded into one effective bias row per batch item (three tiny matmuls that stay in
 autograd, so code gradients and the latent weight-column gradients come from the kernel's bias gradient)."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -78,7 +80,12 @@ class HeadNeRFNet(nn.Module):
                                             min_feat=32, featmap_size=self.featmap_size, img_size=self.pred_img_size)
         self._packed = None
         self._packed_key = None
+        self._packed_hl = None
+        self._packed_hl_key = None
         self.last_meta = None
+        # "fast": fused single-pass half-precision-operand kernels (fp32 accumulate); "high": split-operand (hi+lo) tensor-core
+        # GEMMs with fp32 activations, ~fp32 accuracy at ~3x the tensor work.  Not part of the state dict.
+        self.precision = os.environ.get("HN_PRECISION", "fast")
 
     # ------------------------------------------------------------------ weights -> kernel operands
     def _packed_weights(self):
@@ -88,6 +95,14 @@ class HeadNeRFNet(nn.Module):
             self._packed = ops.pack_weights(ws, L.PE + self.shape_dims, out=self._packed)
             self._packed_key = key
         return ws, self._packed
+
+    def _packed_weights_precise(self):
+        ws = [m.weight for m in self.fg_CD_predictor.layers()]
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if self._packed_hl is None or key != self._packed_hl_key:
+            self._packed_hl = ops.pack_weights_precise(ws, L.PE + self.shape_dims, out=self._packed_hl)
+            self._packed_hl_key = key
+        return ws, self._packed_hl
 
     def _fold_biases(self, shape_code, appea_code, audiostyle):
         """Effective bias row per batch item: [B, HN_BIAS_STRIDE]."""
@@ -141,13 +156,20 @@ class HeadNeRFNet(nn.Module):
             t_rand = torch.rand(B, n_r, ns + 1, device=batch_xy.device, dtype=torch.float32)
         if t_rand is not None and pad:
             t_rand = torch.cat([t_rand, t_rand[:, -1:, :].expand(B, pad, ns + 1)], dim=1)
-        ws, packed = self._packed_weights()
+        if self.precision not in ("fast", "high"):
+            raise ValueError(f"precision must be 'fast' or 'high', got {self.precision!r}")
+        high = self.precision == "high"
         bias = self._fold_biases(shape_code.float(), appea_code.float(), audiostyle.float())
         meta = {"n_samples": ns, "world_z1": self.opt.world_z1, "world_z2": self.opt.world_z2,
-                "l5_hidden_col": L.PE + self.shape_dims, "packed": packed,
-                "grad_target": float(getattr(self, "grad_target", 64.0))}
-        Fm, bg = ops.RenderFunction.apply(batch_xy.float(), batch_Rmats.float(), batch_Tvecs.float(),
-                                          batch_inv_inmats.float(), t_rand, bias, *ws, meta)
+                "l5_hidden_col": L.PE + self.shape_dims, "precision": self.precision,
+                "grad_target": float(getattr(self, "grad_target", 1024.0 if high else 64.0))}
+        if high:
+            ws, meta["packed_hl"] = self._packed_weights_precise()
+        else:
+            ws, meta["packed"] = self._packed_weights()
+        fn = ops.RenderFunctionPrecise if high else ops.RenderFunction
+        Fm, bg = fn.apply(batch_xy.float(), batch_Rmats.float(), batch_Tvecs.float(),
+                          batch_inv_inmats.float(), t_rand, bias, *ws, meta)
         self.last_meta = meta
         Fm, bg = Fm.view(B, n_r + pad, L.FEAT), bg.view(B, n_r + pad)
         if pad:

@@ -320,24 +320,144 @@ class RenderFunction(torch.autograd.Function):
             check_status(status, "hn_mlp_bwd")
         meta["last_status"] = status
 
-        gR = gT = gK = None
-        if need_cam:
-            with torch.enable_grad():
-                Rr = R.detach().requires_grad_(need[1])
-                Tr = T.detach().requires_grad_(need[2])
-                Kr = Kinv.detach().requires_grad_(need[3])
-                o, v, l = ray_params_torch(xy, Rr, Tr, Kr)
-                outs = [o, v, l]
-                gouts = [g_o.view(B, n_rays, 3).permute(0, 2, 1), g_v.view(B, n_rays, 3).permute(0, 2, 1), g_l.view(B, 1, n_rays)]
-                ins = [t for t, n in ((Rr, need[1]), (Tr, need[2]), (Kr, need[3])) if n]
-                gs = list(torch.autograd.grad(outs, ins, gouts, allow_unused=True))
-            if need[1]:
-                gR = gs.pop(0)
-            if need[2]:
-                gT = gs.pop(0)
-                gT = gT.reshape(ctx.T_shape) if gT is not None else None
-            if need[3]:
-                gK = gs.pop(0)
+        gR, gT, gK = _camera_chain(xy, R, T, Kinv, g_o, g_v, g_l, need, ctx.T_shape) if need_cam else (None, None, None)
+        g_weights = [dws[i] if need[6 + i] else None for i in range(12)]
+        return (None, gR, gT, gK, None, dbias if need_bias else None, *g_weights, None)
+
+
+def _camera_chain(xy, R, T, Kinv, g_o, g_v, g_l, need, T_shape):
+    """Per-ray gradients (origin, direction*length, length) -> dL/dR, dL/dT, dL/dK^-1 through NetWorks/utils.py:147-158."""
+    B, _, n_rays = xy.shape
+    gR = gT = gK = None
+    with torch.enable_grad():
+        Rr = R.detach().requires_grad_(need[1])
+        Tr = T.detach().requires_grad_(need[2])
+        Kr = Kinv.detach().requires_grad_(need[3])
+        o, v, l = ray_params_torch(xy, Rr, Tr, Kr)
+        outs = [o, v, l]
+        gouts = [g_o.view(B, n_rays, 3).permute(0, 2, 1), g_v.view(B, n_rays, 3).permute(0, 2, 1), g_l.view(B, 1, n_rays)]
+        ins = [t for t, n in ((Rr, need[1]), (Tr, need[2]), (Kr, need[3])) if n]
+        gs = list(torch.autograd.grad(outs, ins, gouts, allow_unused=True))
+    if need[1]:
+        gR = gs.pop(0)
+    if need[2]:
+        gT = gs.pop(0)
+        gT = gT.reshape(T_shape) if gT is not None else None
+    if need[3]:
+        gK = gs.pop(0)
+    return gR, gT, gK
+
+
+def pack_weights_precise(weights12, l5_hidden_col, out=None):
+    """hi|lo split weight units for the high-precision mode (csrc/hn_precise.cu)."""
+    lib = L.load()
+    ws = [_dev_f32(w.detach(), f"weight[{i}]") for i, w in enumerate(weights12)]
+    n = lib.hn_precise_packed_bytes()
+    if out is None or out.numel() != n or out.device != ws[0].device:
+        out = torch.empty(n, dtype=torch.uint8, device=ws[0].device)
+    a = L.Weights()
+    for i, w in enumerate(ws):
+        a.w[i] = w.data_ptr()
+        a.ld[i] = w.numel() // w.shape[0]
+    a.l5_hidden_col = l5_hidden_col
+    _call("hn_pack_weights_precise", lib.hn_pack_weights_precise, C.byref(a), _ptr(out), _stream())
+    return out
+
+
+class RenderFunctionPrecise(torch.autograd.Function):
+    """Same contract as RenderFunction, high-precision mode: split-operand (hi+lo) tensor-core GEMMs layer by layer with
+    fp32 activations in HBM (include/headnerf_b200.h, hn_mlp_fwd_precise / hn_mlp_bwd_data_precise)."""
+
+    @staticmethod
+    def forward(ctx, xy, R, T, Kinv, t_rand, bias_eff, *rest):
+        weights, meta = rest[:12], rest[12]
+        lib = L.load()
+        ns = meta["n_samples"]
+        xy_c, R_c, T_c, K_c, tr_c = _check_camera(xy, R, T, Kinv, t_rand, ns)
+        B, _, n_rays = xy_c.shape
+        bias_c = _dev_f32(bias_eff, "bias_eff", (B, L.BIAS_STRIDE))
+        wd = _dev_f32(weights[8].detach().reshape(-1), "w_density", (L.HIDDEN,))
+        M = B * n_rays * ns
+        dev = xy_c.device
+        feat = torch.empty(M, L.FEAT, device=dev)
+        sigma, delta = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        acts = torch.empty(lib.hn_precise_workspace_floats(M), device=dev)
+        status = torch.zeros(64, dtype=torch.int32, device=dev)
+        a = L.MlpFwdPrecise()
+        a.cam = _camera(xy_c, R_c, T_c, K_c, tr_c, ns, meta["world_z1"], meta["world_z2"])
+        a.bias, a.w_density, a.packed_hl = _ptr(bias_c), _ptr(wd), _ptr(meta["packed_hl"])
+        a.feat, a.sigma, a.delta, a.zvals, a.acts, a.status = _ptr(feat), _ptr(sigma), _ptr(delta), None, _ptr(acts), _ptr(status)
+        _call("hn_mlp_fwd_precise", lib.hn_mlp_fwd_precise, C.byref(a), _stream(), kernels=13)
+        Fm, bg, _, _ = _composite_fwd(feat, sigma, delta, None, ns)
+        if _DEBUG_SYNC:
+            check_status(status, "hn_mlp_fwd_precise")
+        meta["last_status"] = status
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(xy_c, R_c, T_c, K_c, tr_c, wd, feat, sigma, delta, acts, *weights)
+            ctx.meta = meta
+            ctx.T_shape = T.shape
+        return Fm, bg
+
+    @staticmethod
+    def backward(ctx, gF, g_bg):
+        lib = L.load()
+        xy, R, T, Kinv, t_rand, wd, feat, sigma, delta, acts = ctx.saved_tensors[:10]
+        weights = ctx.saved_tensors[10:]
+        meta = ctx.meta
+        ns = meta["n_samples"]
+        B, _, n_rays = xy.shape
+        M = B * n_rays * ns
+        dev = xy.device
+        need = ctx.needs_input_grad
+        need_cam = need[1] or need[2] or need[3]
+        need_w = any(need[6:18])
+        need_bias = need[5]
+        gF = gF.contiguous().float()
+        g_bg = g_bg.contiguous().float()
+        gmax = torch.maximum(gF.abs().amax(), g_bg.abs().amax() * 0.0).clamp_min(1e-30)
+        scale = torch.pow(2.0, torch.floor(torch.log2(meta.get("grad_target", 64.0) / gmax))).reshape(1)
+        dfeat, _, dsigma, ddelta = _composite_bwd(feat, sigma, delta, None, gF, g_bg, None, ns, image=False, want_ddelta=need_cam)
+        gz = torch.empty(lib.hn_precise_workspace_floats(M), device=dev)
+        g_o = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
+        g_v = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
+        g_l = torch.zeros(B * n_rays, device=dev) if need_cam else None
+        dbias = torch.zeros(B, L.BIAS_STRIDE, device=dev) if (need_bias or need_w) else None
+        status = torch.zeros(64, dtype=torch.int32, device=dev)
+        act_img = grads_img = dfeat_img = None
+        if need_w:
+            act_img = torch.empty(lib.hn_act_bytes(M), dtype=torch.uint8, device=dev)
+            grads_img = torch.empty(lib.hn_grads_bytes(M), dtype=torch.uint8, device=dev)
+            dfeat_img = torch.empty(lib.hn_dfeat_image_bytes(M), dtype=torch.uint8, device=dev)
+        a = L.MlpBwdDataPrecise()
+        a.cam = _camera(xy, R, T, Kinv, t_rand, ns, meta["world_z1"], meta["world_z2"])
+        a.packed_hl, a.w_density, a.dfeat = _ptr(meta["packed_hl"]), _ptr(wd), _ptr(dfeat)
+        a.dsigma, a.ddelta, a.sigma, a.grad_scale = _ptr(dsigma), _ptr(ddelta), _ptr(sigma), _ptr(scale)
+        a.acts, a.gz = _ptr(acts), _ptr(gz)
+        a.g_ray_o, a.g_ray_v, a.g_ray_l = _ptr(g_o), _ptr(g_v), _ptr(g_l)
+        # with weight gradients the bias gradients come out of the weight pass (ones-operand MMA) instead
+        a.dbias = _ptr(dbias) if (need_bias and not need_w) else None
+        a.act_image, a.grads_image, a.dfeat_image, a.status = _ptr(act_img), _ptr(grads_img), _ptr(dfeat_img), _ptr(status)
+        n_k = 10 + (2 if need_cam else 0) + (12 if (need_bias and not need_w) else 0) + (23 if need_w else 0)
+        _call("hn_mlp_bwd_data_precise", lib.hn_mlp_bwd_data_precise, C.byref(a), _stream(), kernels=n_k)
+        dws = [None] * 12
+        if need_w:
+            w = L.MlpBwdWeights()
+            w.B, w.n_rays, w.n_samples = B, n_rays, ns
+            w.act, w.grads, w.dfeat_image, w.grad_scale = _ptr(act_img), _ptr(grads_img), _ptr(dfeat_img), _ptr(scale)
+            ws_bytes = lib.hn_wgrad_workspace_bytes(B)
+            wksp = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            w.items_workspace, w.items_workspace_bytes = _ptr(wksp), ws_bytes
+            for i, wt in enumerate(weights):
+                dws[i] = torch.zeros_like(wt)
+                w.dw[i] = dws[i].data_ptr()
+                w.ld[i] = wt.numel() // wt.shape[0]
+            w.l5_hidden_col = meta["l5_hidden_col"]
+            w.dbias, w.status = _ptr(dbias), _ptr(status)
+            _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=2)
+        if _DEBUG_SYNC:
+            check_status(status, "hn_mlp_bwd_precise")
+        meta["last_status"] = status
+        gR, gT, gK = _camera_chain(xy, R, T, Kinv, g_o, g_v, g_l, need, ctx.T_shape) if need_cam else (None, None, None)
         g_weights = [dws[i] if need[6 + i] else None for i in range(12)]
         return (None, gR, gT, gK, None, dbias if need_bias else None, *g_weights, None)
 
