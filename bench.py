@@ -165,6 +165,24 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     hn.ops.check_status(net.last_meta["last_status"], "timed region")
 
+    # the same step in the high-precision mode (split-operand GEMMs, fp32 activations): reported beside the headline, N = 1 only
+    high = None
+    if world == 1 and not args.no_high:
+        net.precision = "high"
+        for _ in range(2):
+            step(resident)
+        torch.cuda.synchronize()
+        timer.reset(); timer.enabled = True
+        n_high = max(2, min(args.steps, 10))
+        ms_high = timed(lambda: step(resident), n_high)
+        timer.enabled = False
+        hn.ops.check_status(net.last_meta["last_status"], "high-precision timed region")
+        high = {"ms_per_step": round(ms_high / n_high, 4), "value": round(M / (ms_high / n_high * 1e-3), 1), "unit": "ray*samples/s", "steps": n_high,
+                "gpu_launches_per_step": timer.launches / n_high,
+                "calls_ms": {k: round(v["ms_avg"], 4) for k, v in timer.summary().items()},
+                "note": "precision='high': hi+lo split operands, 3 tcgen05 products per GEMM, fp32 activations in HBM (csrc/hn_precise.cu)"}
+        net.precision = "fast"
+
     if world > 1:
         import torch.distributed as tdist
         tdist.barrier()
@@ -216,6 +234,9 @@ def run_ours(args):
         "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
         "roofline": roofline, "kernels": kernels, "clocks": clocks,
     }
+    if high is not None:
+        high["tflops_algorithmic_step"] = round(FLOP_STEP * M / (high["ms_per_step"] * 1e-3) / 1e12, 1)
+        out["high_precision"] = high
     if world == 1:
         out["cpu_baseline"] = cpu_baseline(sample_rays=1024, repeats=2)
     print(json.dumps(out), flush=True)
@@ -294,6 +315,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-high", action="store_true", help="skip the auxiliary high-precision-mode measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
