@@ -12,6 +12,7 @@
 //               pass, bulk-stored to HBM as operand images; finally dL/dPE -> dL/dpts (PE backward) ->
 //               per-ray reductions (origin, direction*length, length) for the camera gradients
 // Gradients are carried multiplied by the power-of-two *grad_scale so that fp16 keeps them in range.
+#include <cstdlib>
 #include <mutex>
 #include "hn_api.h"
 #include "hn_mlp_common.cuh"
@@ -356,6 +357,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
 static std::mutex g_bwd_mu;
 static bool g_bwd_ready[64] = {};
 
+int launch_bwd_data_tmem(const hn_mlp_bwd_data_t* a, void* stream);   // hn_mlp_fwd.cu: the chain with gradients resident in tensor memory
+
 }  // namespace hn
 
 extern "C" int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream) {
@@ -367,6 +370,11 @@ extern "C" int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream) {
     const bool with_pe = (a->g_ray_o != nullptr);
     if (with_pe && (!a->g_ray_v || !a->g_ray_l))
         return set_error(HN_E_BADARG, "hn_mlp_bwd_data: g_ray_o, g_ray_v and g_ray_l must be given together");
+    const int64_t M_all = total_samples(a->cam.B, a->cam.n_rays, a->cam.n_samples);
+    // the training step (no camera gradients) runs on the tensor-memory chain; dL/dPE needs this file's kernel (it keeps a
+    // dedicated accumulator for it).  HN_BWD_SMEM=1 forces the shared-memory-operand kernel (A/B comparisons).
+    static const bool force_smem = [] { const char* e = getenv("HN_BWD_SMEM"); return e && atoi(e) != 0; }();
+    if (!with_pe && !force_smem && !use_cta_pairs((int)(M_all / HN_TILE))) return launch_bwd_data_tmem(a, stream);
     int dev = 0;
     cudaGetDevice(&dev);
     {

@@ -16,6 +16,13 @@
 //   saver            : (backward needed) every finished activation chunk is also staged in shared memory as an
 //                      operand image and bulk-stored to HBM, with 1-bit ReLU masks written by the epilogue
 // Reference semantics: NetWorks/utils.py:43-51,147-161; NetWorks/models.py:62-87; HeadNeRFNet.py:139-152.
+//
+// The same kernel, instantiated with BWD = true, runs the DATA-GRADIENT chain of the training step (no dL/dPE):
+// dX = dZ * W for RGB_layer_2, _1, _0, FeaExt_module_7..1 with the gradients resident in tensor memory.  Differences: the
+// first GEMM's four K blocks (the dL/dfeat operand image written by hn_composite_bwd) stream from HBM through a two-block
+// shared-memory ring (the PE warp becomes their loader); the epilogue applies the forward's saved 1-bit ReLU masks and the
+// density head's rank-1 term instead of bias + ReLU; every chunk is saved as an operand image for the weight-gradient pass.
+// (With camera gradients the older shared-memory-operand kernel of hn_mlp_bwd.cu runs instead: it also accumulates dL/dPE.)
 #include <mutex>
 #include "hn_api.h"
 #include "hn_mlp_common.cuh"
@@ -32,15 +39,36 @@ namespace hn {
 #endif
 
 __constant__ __align__(16) FwdTables c_fwd;
+__constant__ __align__(16) FwdTables c_bwdt;
+
+// arguments of either chain (filled from hn_mlp_fwd_t / hn_mlp_bwd_data_t by the entry points)
+struct ChainArgs {
+    hn_camera_t cam;             // forward
+    const float* bias;           // forward
+    const float* w_density;
+    const void* packed;          // weight units of this chain in stage order
+    float* feat;                 // forward out
+    float* sigma;                // forward: out; data gradients: the saved forward output (ReLU mask of the density head)
+    float* delta;                // forward out
+    float* zvals;                // forward out or NULL
+    void* act;                   // saved operand images: activations (forward) / pre-activation gradients (data gradients), or NULL
+    uint32_t* masks;             // forward: out; data gradients: in
+    const void* dfeat_image;     // data gradients
+    const float* dsigma;         // data gradients
+    const float* grad_scale;     // data gradients
+    int* status;
+};
 
 constexpr int kStages = 4;                                  // weight ring: two consecutive 16 KiB units (32 KiB) per stage
 constexpr uint32_t kStageBytes = 2 * kUnitBytes;
-constexpr uint32_t kOffPE = 0;                              // PE operand block
-constexpr uint32_t kOffW = kUnitBytes;                      // weight ring
-constexpr uint32_t kOffStg = kOffW + kStages * kStageBytes;  // 2 staging buffers of two blocks (saved activations)
-constexpr uint32_t kOffBias = kOffStg + 4 * kUnitBytes;     // this item's effective bias row
+constexpr uint32_t kOffPE = 0;                              // PE operand block (forward) / two-block dL/dfeat ring (data gradients)
 constexpr uint32_t kBiasBytes = HN_BIAS_STRIDE * 4;
-constexpr uint32_t kOffShared = kOffBias + kBiasBytes;      // barriers and small arrays (FwdShared) close the dynamic region
+template <bool BWD> struct Lay {
+    static constexpr uint32_t kOffW = (BWD ? 2 : 1) * kUnitBytes;           // weight ring
+    static constexpr uint32_t kOffStg = kOffW + kStages * kStageBytes;      // 2 staging buffers of two blocks (saved chunks)
+    static constexpr uint32_t kOffBias = kOffStg + 4 * kUnitBytes;          // this item's effective bias row (forward only)
+    static constexpr uint32_t kOffShared = kOffBias + (BWD ? 0 : kBiasBytes);   // barriers and small arrays close the dynamic region
+};
 constexpr uint32_t kTmemCols = 512;
 constexpr int kFwdEpiWarps = 8;                              // (4 TMEM lane quarters) x (2 column groups of a 128-column chunk); a 16-warp
                                                             // (4 column groups, 96 registers) variant was tried: slower issuer, no gain
@@ -52,6 +80,7 @@ constexpr int kFwdThreads = (kFwdEpiWarps + kCtrlWarps) * 32; // 384 = 12 warps 
 struct FwdShared {
     uint64_t w_full[kStages], w_empty[kStages];
     uint64_t a_ready[3], pe_ready, pe_free, pe_consumed, dens_done;
+    uint64_t in_full[2], in_empty[2];   // data gradients: the dL/dfeat ring
     // per accumulator chunk n, rotating over 8 (the issuer can run at most a few chunks ahead of the slowest epilogue warp):
     uint64_t acc_full[8];               //   committed by the MMA issuer
     uint64_t loaded[8];                 //   all eight epilogue warps have read their part of the accumulator
@@ -61,16 +90,18 @@ struct FwdShared {
     uint32_t tmem_base;
     volatile int abort;
 };
-constexpr uint32_t kFwdSmem = kOffShared + sizeof(FwdShared);
-static_assert(kOffShared % 16 == 0 && kFwdSmem <= 232448, "shared-memory budget (227 KiB per CTA)");
+template <bool BWD> constexpr uint32_t chain_smem() { return Lay<BWD>::kOffShared + sizeof(FwdShared); }
+constexpr uint32_t kFwdSmem = chain_smem<false>();
+static_assert(Lay<false>::kOffShared % 16 == 0 && Lay<true>::kOffShared % 16 == 0 && chain_smem<false>() <= 232448 && chain_smem<true>() <= 232448,
+              "shared-memory budget (227 KiB per CTA)");
 
 // one EpiOp2 (16 bytes) fetched with a single 128-bit constant load and decoded with shifts: the fields stay in registers
 // instead of being re-read from the constant bank wherever they are used
 struct EpiFields {
     uint32_t acc_col, out_col, bias_off, col0, save_blk, mask_word, width32, kind, ready_idx, density, wait_next, signal_p;
 };
-__device__ __forceinline__ EpiFields load_epi(int e) {
-    const uint4 r = reinterpret_cast<const uint4*>(c_fwd.epi)[e];
+template <bool BWD> __device__ __forceinline__ EpiFields load_epi(int e) {
+    const uint4 r = reinterpret_cast<const uint4*>(BWD ? c_bwdt.epi : c_fwd.epi)[e];
     EpiFields f;
     f.acc_col = r.x & 0xFFFFu; f.out_col = r.x >> 16;
     f.bias_off = r.y & 0xFFFFu; f.col0 = r.y >> 16;
@@ -107,8 +138,11 @@ __device__ __forceinline__ void produce_pe_row(const hn_camera_t cam, float* del
                      pack_h2(v[8 * c + 4], v[8 * c + 5]), pack_h2(v[8 * c + 6], v[8 * c + 7]));
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fwd_t a, const int n_tiles, const int tiles_per_item) {
+template <bool BWD>
+__global__ void __launch_bounds__(kFwdThreads, 1) mlp_chain_kernel(const ChainArgs a, const int n_tiles, const int tiles_per_item) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];      // no static shared memory in this kernel: the window starts aligned
+    constexpr uint32_t kOffW = Lay<BWD>::kOffW, kOffStg = Lay<BWD>::kOffStg, kOffBias = Lay<BWD>::kOffBias, kOffShared = Lay<BWD>::kOffShared;
+    const FwdTables& T = BWD ? c_bwdt : c_fwd;
     FwdShared& sh = *reinterpret_cast<FwdShared*>(smem_raw + kOffShared);
     const uint32_t smem = smem_u32(smem_raw);
     // warps 0..7: epilogue (TMEM lane quarter = warp & 3); warps 8..11: control roles.  The warp scheduler favours the
@@ -126,6 +160,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
         mbar_init(smem_u32(&sh.dens_done), kFwdEpiWarps);
         for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.loaded[i]), kFwdEpiWarps); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&sh.stg_full[i]), kFwdEpiWarps); mbar_init(smem_u32(&sh.stg_free[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&sh.in_full[i]), 1); mbar_init(smem_u32(&sh.in_empty[i]), 1); }
         sh.abort = 0;
         mbar_fence_init();
     }
@@ -134,7 +169,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = sh.tmem_base;
-    const int n_stages = c_fwd.n_stages;
+    const int n_stages = T.n_stages, n_epis = T.n_epis;
+    const uint32_t tile_flip = (uint32_t)T.tile_flip;
 
     if (cw == 0) {
         // ======================= weight producers: three lanes of one warp, each with its own copies in flight =======================
@@ -162,14 +198,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
             uint32_t sidx = 0, par_pe = 0;                           // saved chunks so far: buffer = sidx & 1, its use = sidx >> 1
             for (int w = work0; w < n_tiles && !sh.abort; w += work_stride) {
                 const int tile = w;
-                if (!wait_spin(&sh.pe_ready, par_pe, &sh.abort, a.status, 150)) break;
-                par_pe ^= 1;
-                bulk_s2g((uint8_t*)a.act + ((size_t)HN_SLOT_PE * n_tiles + tile) * kUnitBytes, smem + kOffPE, kUnitBytes);
-                bulk_commit();
-                bulk_wait_read<0>();
-                mbar_arrive(smem_u32(&sh.pe_free));
-                for (int e = 0; e < kFwdEpis; ++e) {
-                    const EpiFields op = load_epi(e);
+                if (!BWD) {
+                    if (!wait_spin(&sh.pe_ready, par_pe, &sh.abort, a.status, 150)) break;
+                    par_pe ^= 1;
+                    bulk_s2g((uint8_t*)a.act + ((size_t)HN_SLOT_PE * n_tiles + tile) * kUnitBytes, smem + kOffPE, kUnitBytes);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                    mbar_arrive(smem_u32(&sh.pe_free));
+                }
+                for (int e = 0; e < n_epis; ++e) {
+                    const EpiFields op = load_epi<BWD>(e);
                     if (op.save_blk == 0xFFFF) continue;
                     const uint32_t sb = sidx & 1;
                     if (!wait_spin(&sh.stg_full[sb], (sidx >> 1) & 1, &sh.abort, a.status, 151)) break;
@@ -189,17 +227,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
         // ======================= MMA issuer =======================
         // the whole warp walks the schedule (uniform control flow keeps descriptors in uniform registers); one
         // elected lane issues the MMAs and commits
-        uint32_t pc = 0, par_ready = 0, par_pe = 0, base_n = 0;
+        uint32_t pc = 0, par_ready = 0, par_pe = 0, base_n = 0, in_use = 0;
         int tile_k = 0;
         HN_PC_DECL(pcn, 8);
         // The issuer shares its scheduler with four epilogue warps and gets only a fraction of the issue slots, so its
         // instruction stream per MMA is what bounds the tensor pipe: a stage is one 128-bit table word, four MMAs of N = 256
         // (or eight of N = 128), one release; the NEXT stage's weight barrier is queried before its answer is needed.
         bool pre = mbar_try_wait(smem_u32(&sh.w_full[0]), 0);
-        const uint4* table = reinterpret_cast<const uint4*>(c_fwd.stage);
+        const uint4* table = reinterpret_cast<const uint4*>(T.stage);
         uint4 cur = table[0];
-        for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, base_n += kFwdEpis, ++tile_k) {
-            const uint32_t hx = (uint32_t)(tile_k & 1) << 8;           // odd tiles: the TMEM halves swap roles
+        for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, base_n += n_epis, ++tile_k) {
+            const uint32_t hx = ((uint32_t)tile_k & tile_flip) << 8;   // odd tiles: the TMEM halves swap roles (odd layer counts)
             for (int st = 0; st < n_stages; ++st, ++pc) {
                 const uint4 nxt = table[st + 1 < n_stages ? st + 1 : 0];           // table read off the critical path
                 const uint32_t stage = pc % kStages, par = (pc / kStages) & 1;
@@ -209,7 +247,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                 HN_TR(lane == 0, st * 4 + 0);
                 if (cur.z >> 16) {                                     // rare: an input slot or chunk 0's accumulator must be awaited
                     const uint32_t wait_src = (cur.z >> 16) & 0xFFu;
-                    if (wait_src == 4) { ok = wait_spin(&sh.pe_ready, par_pe, &sh.abort, a.status, 201); par_pe ^= 1; }
+                    if (wait_src == 4) {
+                        if (BWD) ok = wait_spin(&sh.in_full[in_use & 1], (in_use >> 1) & 1, &sh.abort, a.status, 205);   // streamed dL/dfeat block
+                        else { ok = wait_spin(&sh.pe_ready, par_pe, &sh.abort, a.status, 201); par_pe ^= 1; }
+                    }
                     else if (wait_src) {
                         const int c = (int)wait_src - 1;
                         ok = wait_spin(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 202 + c);
@@ -232,7 +273,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                 const uint32_t n0 = base_n + chunk, n1 = n0 + 1;
                 const uint32_t full0 = smem_u32(&sh.acc_full[n0 & 7]), full1 = smem_u32(&sh.acc_full[n1 & 7]);
                 if (a0 & kSrcSmem) {
-                    const uint32_t a_lo = desc_lo(smem + kOffPE + (a0 & 0x7FFFu) * kUnitBytes, 16);
+                    const uint32_t a_lo = desc_lo(smem + kOffPE + (BWD ? (a0 & 1u) : (a0 & 0x7FFFu)) * kUnitBytes, 16);
+                    const uint32_t in_bar = smem_u32(&sh.in_empty[in_use & 1]);
                     if (elect_one()) {
 #pragma unroll
                         for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_lohi(d, a_lo + ks * 2, b_lo + ks * 2, idesc, ks == 0 ? acc0 : 1u);
@@ -243,7 +285,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                         if (commit) umma_commit(full0);
                         if (commit == 2) umma_commit(full1);
                         umma_commit(smem_u32(&sh.w_empty[stage]));
+                        if (BWD) umma_commit(in_bar);                   // the ring slot may be refilled once these MMAs retire
                     }
+                    if (BWD) ++in_use;
                 } else {
                     const uint32_t a_t0 = tmem_base + (a0 ^ hx), a_t1 = tmem_base + (a1 ^ hx);
                     if (elect_one()) {
@@ -270,6 +314,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
         // ======================= PE warp: sampling + positional encoding of the NEXT tile, off everybody's critical path =======================
         // four rows per lane; the PE block is free once FeaExt_module_5's last chunk has been committed (its MMAs were the last
         // readers) and - when activations are saved - the saver's bulk store has read it
+        if (BWD) {
+            // data gradients: this warp's lane 0 streams the tile's four dL/dfeat K blocks through the two-block ring
+            if (lane == 0) {
+                uint32_t i = 0;
+                const uint8_t* din = (const uint8_t*)a.dfeat_image;
+                for (int w = work0; w < n_tiles && !sh.abort; w += work_stride) {
+                    for (int kb = 0; kb < 4; ++kb, ++i) {
+                        if (!wait_spin(&sh.in_empty[i & 1], ((i >> 1) & 1) ^ 1, &sh.abort, a.status, 162)) break;
+                        const uint32_t fb = smem_u32(&sh.in_full[i & 1]);
+                        mbar_arrive_expect_tx(fb, kUnitBytes);
+                        bulk_g2s(smem + kOffPE + (i & 1) * kUnitBytes, din + ((size_t)kb * n_tiles + w) * kUnitBytes, kUnitBytes, fb);
+                    }
+                }
+            }
+        } else {
         uint32_t k = 0;
         for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, ++k) {
             if (k > 0) {
@@ -280,6 +339,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
             for (int i = 0; i < 4; ++i) produce_pe_row(a.cam, a.delta, a.zvals, smem + kOffPE, w, tiles_per_item, i * 32 + lane);
             fence_async_smem();
             warp_arrive(smem_u32(&sh.pe_ready), lane);
+        }
         }
     } else {
         // ======================= epilogue =======================
@@ -294,7 +354,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
         const int row = quarter * 32 + lane;                        // tile row = TMEM lane
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t base_n = 0, sidx = 0, tile_i = 0;                  // first chunk index of the tile; saved chunks so far
-        const int pe_after = c_fwd.pe_after_epi;
+        const int pe_after = T.pe_after_epi;
         int cached_b = -1;
         for (int i = tid; i < HN_HIDDEN; i += kFwdEpiThreads) sh.w_density[i] = __ldg(a.w_density + i);
         if (tid < 256) (&sh.dens[0][0])[tid] = 0.f;
@@ -302,11 +362,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
 
         HN_PC_DECL(ec, 16);
         float dens = 0.f;
-        for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, base_n += kFwdEpis, ++tile_i) {
+        const float gscale = BWD ? __ldg(a.grad_scale) : 1.0f;
+        for (int w = work0; w < n_tiles && !sh.abort; w += work_stride, base_n += n_epis, ++tile_i) {
             const int tile = w;
             const size_t m = (size_t)tile * HN_TILE + row;
             const int b = tile / tiles_per_item;
-            if (b != cached_b) {                                    // (re)load the item's bias row
+            // data gradients: d/d(pre-ReLU density) of this row, loss-scaled (the density head's rank-1 term and pseudo layer)
+            const float dsr = (BWD && __ldg(a.sigma + m) > 0.f) ? __ldg(a.dsigma + m) * gscale : 0.f;
+            if (!BWD && b != cached_b) {                            // (re)load the item's bias row
                 named_sync(3, kFwdEpiThreads);
                 const float4* src = reinterpret_cast<const float4*>(a.bias + (size_t)b * HN_BIAS_STRIDE);
                 for (int i = tid; i < HN_BIAS_STRIDE / 4; i += kFwdEpiThreads) {
@@ -317,20 +380,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                 cached_b = b;
             }
             const uint32_t bias_row = smem + kOffBias;
-            const uint32_t hx = (tile_i & 1u) << 8;                 // odd tiles: the TMEM halves swap roles
+            const uint32_t hx = (tile_i & tile_flip) << 8;          // odd tiles: the TMEM halves swap roles (odd layer counts)
             uint32_t hold[kPW][16];                                 // packed output of chunk 0 of a pair, stored with chunk 1's
             uint32_t hold_addr = 0;
             bool holding = false;
-            for (int e = 0; e < kFwdEpis; ++e) {
+            for (int e = 0; e < n_epis; ++e) {
                 const uint32_t n = base_n + e;
-                const EpiFields op = load_epi(e);
+                const EpiFields op = load_epi<BWD>(e);
+                uint32_t mwords[kPW];
+                if (BWD && op.mask_word != 0xFFFF && kPW * g < (int)op.width32) {   // saved ReLU masks: fetched ahead of the accumulator
+#pragma unroll
+                    for (int pc = 0; pc < kPW; ++pc) mwords[pc] = __ldg(a.masks + m * HN_MASK_WORDS + op.mask_word + kPW * g + pc);
+                }
                 HN_PC_T0(ec);
                 wait_spin(&sh.acc_full[n & 7], (n >> 3) & 1, &sh.abort, a.status, 300 + e);
                 HN_PC_LAP(ec, 1);
                 { const int tile_k = (int)tile_i; HN_TR(ew == 0 && lane == 0, 1024 + e * 4 + 0); }
                 tc_fence_after_sync();
                 // FeaExt_module_5's last chunk is complete: every MMA that reads the PE block has run
-                if (e == pe_after) warp_arrive(smem_u32(&sh.pe_consumed), lane);
+                if (!BWD && e == pe_after) warp_arrive(smem_u32(&sh.pe_consumed), lane);
                 const bool save = saving && op.save_blk != 0xFFFF;
                 const bool active = kPW * g < (int)op.width32;     // RGB_layer_1's second chunk has 64 columns: the upper column groups idle
                 const uint32_t bp = bias_row + (op.bias_off + CW * g) * 4;
@@ -346,7 +414,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                 { const int tile_k = (int)tile_i; HN_TR(ew == 0 && lane == 0, 1024 + e * 4 + 1); }
                 HN_PC_LAP(ec, 2);
                 const uint32_t sb = sidx & 1;                      // staging buffer of this saved chunk
-                if (op.kind == EPI_FEAT) {
+                if (!BWD && op.kind == EPI_FEAT) {
                     // final features: stage 32 rows x 32 columns per piece in shared memory (swizzled 16-byte chunks), then write
                     // whole 128-byte row segments (8 lanes each) instead of 32 scattered 16-byte pieces.  Scratch = the staging
                     // buffer whose last saved chunk is the older one (chunk 29 -> buffer of chunk 27, chunk 30 -> of chunk 28).
@@ -385,6 +453,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                     HN_PC_LAP(ec, 9);
                 } else {
                     auto convert = [&](const uint32_t (&v)[32], int pc, uint32_t (&pk)[16]) {
+                        if (BWD) {
+                            // dX = (acc + dsigma * w_density) * [forward pre-activation > 0]
+                            float y[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]);
+                            if (op.kind == EPI_GRAD_DENSITY) {
+                                const float4* wp = reinterpret_cast<const float4*>(sh.w_density + op.col0 + CW * g + pc * 32);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 ww = wp[i];
+                                    y[4 * i + 0] = fmaf(dsr, ww.x, y[4 * i + 0]); y[4 * i + 1] = fmaf(dsr, ww.y, y[4 * i + 1]);
+                                    y[4 * i + 2] = fmaf(dsr, ww.z, y[4 * i + 2]); y[4 * i + 3] = fmaf(dsr, ww.w, y[4 * i + 3]);
+                                }
+                            }
+                            if (op.kind != EPI_GRAD_LINEAR) {
+                                const uint32_t mw = mwords[pc];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) y[i] = (mw & (1u << i)) ? y[i] : 0.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[i] = pack_sat(y[2 * i], y[2 * i + 1]);
+                            return;
+                        }
 #ifdef HN_EXP_X4
                         for (int i = 0; i < 16; ++i) pk[i] = v[i] ^ v[i + 16];
                         return;
@@ -404,7 +495,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                             y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
                         }
                         if (op.kind == EPI_HIDDEN) {
-                            if (a.masks && op.mask_word != 0xFFFF)
+                            if (!BWD && a.masks && op.mask_word != 0xFFFF)
                                 a.masks[m * HN_MASK_WORDS + op.mask_word + kPW * g + pc] = positive_mask32(y);
                             if (op.density) {                      // density head on the fp32 activations (models.py:78,83)
                                 const float4* wp = reinterpret_cast<const float4*>(sh.w_density + op.col0 + CW * g + pc * 32);
@@ -423,7 +514,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                         }
                     };
                     const uint32_t out_addr = tmem_base + lane_base + (op.out_col ^ hx) + (CW / 2) * g;
+                    const bool has_out = !BWD || op.out_col != kNoCol;      // the chain's last data-gradient chunk is only saved
                     const uint32_t stg = smem + kOffStg + sb * 2 * kUnitBytes;
+                    if (BWD && save && op.kind == EPI_GRAD_DENSITY && op.col0 == 0 && g == 0) {
+                        // density head as a one-channel pseudo layer for the weight pass: row = [dsr, 0, ..., 0]
+                        uint8_t* drow = (uint8_t*)a.act + ((size_t)HN_GSLOT_DENS * n_tiles + tile) * kUnitBytes + (row >> 3) * 1024 + (row & 7) * 128;
+                        const uint32_t first = pack_sat(dsr, 0.f);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<uint4*>(drow + ((c ^ (row & 7)) << 4)) = make_uint4(c == 0 ? first : 0u, 0u, 0u, 0u);
+                    }
                     // staging buffer: has the bulk store of its previous saved chunk read it?
                     if (save) wait_spin(&sh.stg_free[sb], ((sidx >> 1) & 1) ^ 1, &sh.abort, a.status, 341);
                     if (op.wait_next) {
@@ -459,7 +559,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                             for (int pc = 0; pc < kPW; ++pc) {
                                 uint32_t pk[16];
                                 convert(v[pc], pc, pk);
-                                tmem_st16(out_addr + 16 * pc, pk);
+                                if (has_out) tmem_st16(out_addr + 16 * pc, pk);
                                 if (save) store_row_packed(stg, row, CW * g + 32 * pc, pk);
                             }
                         }
@@ -475,7 +575,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const hn_mlp_fw
                 }
                 HN_PC_LAP(ec, 6);
                 { const int tile_k = (int)tile_i; HN_TR(ew == 0 && lane == 0, 1024 + e * 4 + 2); }
-                if (op.density == 2) {
+                if (!BWD && op.density == 2) {
                     // last density chunk of the tile: publish the partial dot products; once all 8 warps have contributed the
                     // lower-half warps add the bias and write sigma
                     atomicAdd(&sh.dens[tile_i & 1][row], dens);
@@ -505,6 +605,52 @@ static bool g_fwd_ready[64] = {};
 
 }  // namespace hn
 
+namespace hn {
+static int prepare_chain_device(int* n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_fwd_mu);
+        if (dev < 64 && !g_fwd_ready[dev]) {
+            const HostSchedules& hs = host_schedules();
+            cudaError_t e = cudaMemcpyToSymbol(c_fwd, &hs.fwd, sizeof(FwdTables));
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_bwdt, &hs.bwdt, sizeof(FwdTables));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<false>());
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<true>());
+            if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+            g_fwd_ready[dev] = true;
+        }
+    }
+    *n_sm = 148;
+    cudaDeviceGetAttribute(n_sm, cudaDevAttrMultiProcessorCount, dev);
+    return HN_OK;
+}
+
+// data-gradient chain without dL/dPE on the tensor-memory kernel (called by hn_mlp_bwd_data, hn_mlp_bwd.cu)
+int launch_bwd_data_tmem(const hn_mlp_bwd_data_t* a, void* stream) {
+    int n_sm = 148;
+    if (int rc = prepare_chain_device(&n_sm)) return rc;
+    const HostSchedules& hs = host_schedules();
+    ChainArgs c{};
+    c.cam = a->cam;
+    c.w_density = a->w_density;
+    c.packed = (const uint8_t*)a->packed + (size_t)(kFwdUnits + hs.n_bwd_pack_units) * kUnitBytes;
+    c.sigma = const_cast<float*>(a->sigma);
+    c.act = a->grads;
+    c.masks = const_cast<uint32_t*>(a->masks);
+    c.dfeat_image = a->dfeat_image;
+    c.dsigma = a->dsigma;
+    c.grad_scale = a->grad_scale;
+    c.status = a->status;
+    const int64_t M = total_samples(a->cam.B, a->cam.n_rays, a->cam.n_samples);
+    const int n_tiles = (int)(M / HN_TILE);
+    const int tiles_per_item = (int)(((int64_t)a->cam.n_rays * a->cam.n_samples) / HN_TILE);
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    mlp_chain_kernel<true><<<grid, kFwdThreads, chain_smem<true>(), (cudaStream_t)stream>>>(c, n_tiles, tiles_per_item);
+    return check_launch("hn_mlp_bwd_data (tensor-memory chain)");
+}
+}  // namespace hn
+
 extern "C" int hn_mlp_fwd(const hn_mlp_fwd_t* a, void* stream) {
     using namespace hn;
     if (!a || !a->cam.xy || !a->cam.Rmats || !a->cam.Tvecs || !a->cam.inv_inmats || !a->bias || !a->w_density ||
@@ -513,23 +659,16 @@ extern "C" int hn_mlp_fwd(const hn_mlp_fwd_t* a, void* stream) {
     if (int rc = check_geometry(a->cam.B, a->cam.n_rays, a->cam.n_samples, "hn_mlp_fwd")) return rc;
     if ((a->act == nullptr) != (a->masks == nullptr))
         return set_error(HN_E_BADARG, "hn_mlp_fwd: act and masks must both be given (backward) or both be NULL");
-    int dev = 0;
-    cudaGetDevice(&dev);
-    {
-        std::lock_guard<std::mutex> lk(g_fwd_mu);
-        if (dev < 64 && !g_fwd_ready[dev]) {
-            cudaError_t e = cudaMemcpyToSymbol(c_fwd, &host_schedules().fwd, sizeof(FwdTables));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
-            if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-            g_fwd_ready[dev] = true;
-        }
-    }
     int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (int rc = prepare_chain_device(&n_sm)) return rc;
+    ChainArgs c{};
+    c.cam = a->cam; c.bias = a->bias; c.w_density = a->w_density; c.packed = a->packed;
+    c.feat = a->feat; c.sigma = a->sigma; c.delta = a->delta; c.zvals = a->zvals;
+    c.act = a->act; c.masks = a->masks; c.status = a->status;
     const int64_t M = total_samples(a->cam.B, a->cam.n_rays, a->cam.n_samples);
     const int n_tiles = (int)(M / HN_TILE);
     const int tiles_per_item = (int)(((int64_t)a->cam.n_rays * a->cam.n_samples) / HN_TILE);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    mlp_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, tiles_per_item);
+    mlp_chain_kernel<false><<<grid, kFwdThreads, kFwdSmem, (cudaStream_t)stream>>>(c, n_tiles, tiles_per_item);
     return check_launch("hn_mlp_fwd");
 }

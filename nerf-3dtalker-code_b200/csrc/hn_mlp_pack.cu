@@ -1,7 +1,7 @@
 // hn_mlp_pack.cu — hn_pack_weights: fp32 state-dict weights ([out,in] row-major, NetWorks/models.py:32-59)
 // -> the half-precision weight-unit stream the fused kernels consume.  One unit = one 16 KiB operand image
 // (<=128 rows x 64 cols, SWIZZLE_128B), units stored in exactly the order the kernels' MMA tables read them:
-//   [ forward units (kFwdUnits) | data-gradient units (W^T, bwd.n_units) ].
+//   [ forward units (kFwdUnits) | data-gradient units (W^T, bwd.n_units) | tensor-memory data-gradient chain units (kBwdTUnits) ].
 #include <mutex>
 #include "hn_api.h"
 #include "hn_mlp_sched.h"
@@ -9,7 +9,7 @@
 
 namespace hn {
 
-__constant__ PackOp c_pack[kFwdUnits + kBwdUnitsMax];
+__constant__ PackOp c_pack[kFwdUnits + kBwdUnitsMax + kBwdTUnits];
 
 struct PackArgs { const float* w[12]; int ld[12]; int l5_hidden_col; int n_units; };
 
@@ -48,7 +48,7 @@ static bool g_uploaded[64] = {};
 }  // namespace hn
 
 extern "C" size_t hn_packed_weights_bytes(void) {
-    return (size_t)(hn::kFwdUnits + hn::host_schedules().n_bwd_pack_units) * hn::kUnitBytes;
+    return (size_t)(hn::kFwdUnits + hn::host_schedules().n_bwd_pack_units + hn::kBwdTUnits) * hn::kUnitBytes;
 }
 
 extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream) {
@@ -68,6 +68,8 @@ extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream
             cudaError_t e = cudaMemcpyToSymbol(c_pack, hs.fwd_pack, sizeof(PackOp) * kFwdUnits, 0);
             if (e == cudaSuccess)
                 e = cudaMemcpyToSymbol(c_pack, hs.bwd_pack, sizeof(PackOp) * hs.n_bwd_pack_units, sizeof(PackOp) * kFwdUnits);
+            if (e == cudaSuccess)
+                e = cudaMemcpyToSymbol(c_pack, hs.bwdt_pack, sizeof(PackOp) * kBwdTUnits, sizeof(PackOp) * (kFwdUnits + hs.n_bwd_pack_units));
             if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
             g_uploaded[dev] = true;
         }
@@ -75,7 +77,7 @@ extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream
     PackArgs a;
     for (int i = 0; i < 12; ++i) { a.w[i] = w->w[i]; a.ld[i] = w->ld[i]; }
     a.l5_hidden_col = w->l5_hidden_col;
-    a.n_units = kFwdUnits + hs.n_bwd_pack_units;
+    a.n_units = kFwdUnits + hs.n_bwd_pack_units + kBwdTUnits;
     pack_kernel<<<a.n_units, 256, 0, (cudaStream_t)stream>>>(a, (uint8_t*)packed);
     return check_launch("hn_pack_weights");
 }

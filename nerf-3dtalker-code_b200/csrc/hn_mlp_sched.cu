@@ -134,17 +134,15 @@ struct Builder {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Forward chain (A operand in tensor memory, alternating TMEM halves): table generation, see hn_mlp_sched.h.
-struct FwdLayer { int w_idx; bool pe; int n_kb; int widths[3]; int n_chunks; EpiKind kind; int bias_off; int save_blk; int mask_word; bool l5_hidden; int density; bool to_tmem; };
+struct FwdLayer {
+    int w_idx; int smem_kb; int n_kb; int widths[3]; int n_chunks; EpiKind kind; int bias_off; int save_blk; int mask_word; bool l5_hidden; int density; bool to_tmem;
+    bool transposed = false;        // data-gradient chain: units hold W^T (rows = layer inputs, columns = layer outputs)
+};
 
-void build_fwd(HostSchedules* hs) {
-    // ---- layer list: NetWorks/models.py:69-82
-    std::vector<FwdLayer> layers;
-    for (int l = 0; l < 8; ++l)
-        layers.push_back({l, l == 0 || l == 5, l == 0 ? 0 : 6, {128, 128, 128}, 3, EPI_HIDDEN, l * HN_HIDDEN, HN_SLOT_H0 + 6 * l, 12 * l, l == 5, l == 7 ? 1 : 0, true});
-    layers.push_back({W_R0, false, 6, {128, 128, 128}, 3, EPI_LINEAR, HN_BIAS_OFF_R0, HN_SLOT_R0, -1, false, 0, true});
-    layers.push_back({W_R1, false, 6, {128, 64, 0}, 2, EPI_HIDDEN, HN_BIAS_OFF_R1, HN_SLOT_X, 96, false, 0, true});
-    layers.push_back({W_R2, false, 3, {128, 128, 0}, 2, EPI_FEAT, HN_BIAS_OFF_R2, -1, -1, false, 0, false});
-
+// Generates the stage / pack / epilogue tables of a GEMM chain whose activations live in tensor memory.  `smem_kb` leading
+// K blocks of a layer come from shared memory: the forward's positional-encoding block (1, awaited once per tile) or the
+// data-gradient chain's streamed dL/dfeat blocks (4, each awaited).
+void build_tmem_chain(const std::vector<FwdLayer>& layers, bool streamed_input, FwdTables* T, PackOp* pack_out, int n_units_expected, int n_epis_expected) {
     std::vector<StageOp> stages;
     std::vector<PackOp> pack;
     std::vector<EpiOp2> epi;
@@ -152,10 +150,16 @@ void build_fwd(HostSchedules* hs) {
     int chunk0 = 0;
     auto pack_unit = [&](const FwdLayer& L, int j, int k) {            // weight unit (chunk j, K block k); k < 0: empty unit
         PackOp p{};
-        p.w_idx = (int8_t)L.w_idx; p.transposed = 0;
+        p.w_idx = (int8_t)L.w_idx; p.transposed = (int8_t)L.transposed;
         if (k < 0) { p.valid_r = 0; p.valid_c = 0; pack.push_back(p); return; }
-        const bool is_pe = L.pe && k == 0;
-        const int kb = k - (L.pe ? 1 : 0);
+        if (L.transposed) {                                            // unit(r,c) = W[(row0 + c) * ld + col0 + r]
+            p.row0 = (int16_t)(64 * k); p.valid_c = 64;
+            p.col0 = (int16_t)(128 * j); p.valid_r = (int16_t)L.widths[j]; p.l5_hidden = (int8_t)L.l5_hidden;
+            pack.push_back(p);
+            return;
+        }
+        const bool is_pe = k < L.smem_kb;
+        const int kb = k - L.smem_kb;
         p.row0 = (int16_t)(128 * j); p.valid_r = (int16_t)L.widths[j];
         if (is_pe) { p.col0 = 0; p.valid_c = HN_PE; p.l5_hidden = 0; }
         else { p.col0 = (int16_t)(64 * kb); p.valid_c = 64; p.l5_hidden = (int8_t)L.l5_hidden; }
@@ -164,11 +168,11 @@ void build_fwd(HostSchedules* hs) {
     for (size_t li = 0; li < layers.size(); ++li) {
         const FwdLayer& L = layers[li];
         const int B = (li & 1) ? 256 : 0;                              // accumulator half of this layer (even tiles)
-        const int n_k = (L.pe ? 1 : 0) + L.n_kb;
-        auto a_src = [&](int k) -> uint16_t { return (L.pe && k == 0) ? (uint16_t)(kSrcSmem | 0) : (uint16_t)X[k - (L.pe ? 1 : 0)]; };
+        const int n_k = L.smem_kb + L.n_kb;
+        auto a_src = [&](int k) -> uint16_t { return (k < L.smem_kb) ? (uint16_t)(kSrcSmem | (streamed_input ? k : 0)) : (uint16_t)X[k - L.smem_kb]; };
         auto wait_of = [&](int k) -> uint8_t {                        // whoever meets an input slot first waits for it
-            if (L.pe && k == 0) return li == 0 ? 4 : 0;
-            const int kb = k - (L.pe ? 1 : 0);
+            if (k < L.smem_kb) return (streamed_input || li == 0) ? 4 : 0;
+            const int kb = k - L.smem_kb;
             return (kb % 2 == 0) ? (uint8_t)(1 + kb / 2) : 0;
         };
         // phase A: chunks 0 and 1 together, one stage per K block
@@ -187,9 +191,10 @@ void build_fwd(HostSchedules* hs) {
         // phase B: chunk 2 alone over [B, B+128), two K blocks per stage (the PE block, read from shared memory, gets a stage
         // of its own next to an empty unit: the issuer handles one kind of A operand per stage)
         if (L.n_chunks == 3) {
+            assert(!(streamed_input && L.smem_kb));                    // streamed blocks are consumed once, in phase A only
             std::vector<std::pair<int, int>> sts;
             int k = 0;
-            if (L.pe) { sts.push_back({0, -1}); k = 1; }
+            if (L.smem_kb) { sts.push_back({0, -1}); k = 1; }
             for (; k < n_k; k += 2) sts.push_back({k, k + 1 < n_k ? k + 1 : -1});
             for (size_t i = 0; i < sts.size(); ++i) {
                 StageOp s{};
@@ -211,7 +216,7 @@ void build_fwd(HostSchedules* hs) {
             int acc = B + (j == 1 ? 128 : 0), out = -1, wait_next = 0;
             if (L.to_tmem) {
                 if (L.n_chunks == 3) { out = j == 0 ? B + 192 : (j == 1 ? B + 128 : B); wait_next = (j == 0); }
-                else { out = j == 0 ? B + 192 : B + 128; }              // RGB_layer_1: [B+192, B+256) is outside its 192-wide accumulator
+                else { out = j == 0 ? B + 192 : B + 128; }              // 192-wide layers: [B+192, B+256) is outside the accumulator
             }
             EpiOp2 e{};
             e.acc_col = (uint16_t)acc;
@@ -230,14 +235,49 @@ void build_fwd(HostSchedules* hs) {
         chunk0 += L.n_chunks;
         X = Y;
     }
-    assert((int)stages.size() == kFwdStages && (int)pack.size() == kFwdUnits && (int)epi.size() == kFwdEpis);
-    memcpy(hs->fwd_pack, pack.data(), sizeof(PackOp) * kFwdUnits);
-    memcpy(hs->fwd.stage, stages.data(), sizeof(StageOp) * kFwdStages);
-    memcpy(hs->fwd.epi, epi.data(), sizeof(EpiOp2) * kFwdEpis);
-    hs->fwd.n_stages = kFwdStages;
+    assert((int)stages.size() * 2 == n_units_expected && (int)pack.size() == n_units_expected && (int)epi.size() == n_epis_expected);
+    assert((int)stages.size() <= kFwdStages && (int)epi.size() <= kFwdEpis);
+    memcpy(pack_out, pack.data(), sizeof(PackOp) * pack.size());
+    memcpy(T->stage, stages.data(), sizeof(StageOp) * stages.size());
+    memcpy(T->epi, epi.data(), sizeof(EpiOp2) * epi.size());
+    T->n_stages = (int)stages.size();
+    T->n_epis = (int)epi.size();
+    // Across tiles the same no-barrier argument must hold between the LAST layer of a tile and the FIRST of the next: their
+    // accumulators must sit in different halves.  An odd layer count needs the halves swapped on odd tiles, an even one does not.
+    T->tile_flip = (int)(layers.size() & 1);
+    for (const EpiOp2& e : epi) if (e.ready_idx != 255) T->n_ready[e.ready_idx]++;
+}
+
+void build_fwd(HostSchedules* hs) {
+    // ---- layer list: NetWorks/models.py:69-82
+    std::vector<FwdLayer> layers;
+    for (int l = 0; l < 8; ++l)
+        layers.push_back({l, (l == 0 || l == 5) ? 1 : 0, l == 0 ? 0 : 6, {128, 128, 128}, 3, EPI_HIDDEN, l * HN_HIDDEN, HN_SLOT_H0 + 6 * l, 12 * l, l == 5, l == 7 ? 1 : 0, true});
+    layers.push_back({W_R0, 0, 6, {128, 128, 128}, 3, EPI_LINEAR, HN_BIAS_OFF_R0, HN_SLOT_R0, -1, false, 0, true});
+    layers.push_back({W_R1, 0, 6, {128, 64, 0}, 2, EPI_HIDDEN, HN_BIAS_OFF_R1, HN_SLOT_X, 96, false, 0, true});
+    layers.push_back({W_R2, 0, 3, {128, 128, 0}, 2, EPI_FEAT, HN_BIAS_OFF_R2, -1, -1, false, 0, false});
+    build_tmem_chain(layers, false, &hs->fwd, hs->fwd_pack, kFwdUnits, kFwdEpis);
     // the PE block is free once FeaExt_module_5's last chunk has completed: the next tile's PE is produced there
     hs->fwd.pe_after_epi = 17;
-    for (const EpiOp2& e : epi) if (e.ready_idx != 255) hs->fwd.n_ready[e.ready_idx]++;
+}
+
+// data-gradient chain without dL/dPE (autograd of NetWorks/models.py:62-87 in reverse): dX = dZ * W, then the ReLU mask of the
+// layer below; RGB_layer_0's input gradient also receives the density head's rank-1 term
+void build_bwdt(HostSchedules* hs) {
+    std::vector<FwdLayer> layers;
+    FwdLayer r2{W_R2, 4, 0, {128, 64, 0}, 2, EPI_GRAD_MASK, 0, HN_GSLOT_R1, 96, false, 0, true}; r2.transposed = true;
+    layers.push_back(r2);
+    FwdLayer r1{W_R1, 0, 3, {128, 128, 128}, 3, EPI_GRAD_LINEAR, 0, HN_GSLOT_R0, -1, false, 0, true}; r1.transposed = true;
+    layers.push_back(r1);
+    FwdLayer r0{W_R0, 0, 6, {128, 128, 128}, 3, EPI_GRAD_DENSITY, 0, HN_GSLOT_Z0 + 6 * 7, 12 * 7, false, 0, true}; r0.transposed = true;
+    layers.push_back(r0);
+    for (int l = 7; l >= 1; --l) {
+        // FeaExt_module_1^T closes the chain: its output (dZ of FeaExt_module_0) is only saved, no GEMM reads it
+        FwdLayer s{l, 0, 6, {128, 128, 128}, 3, EPI_GRAD_MASK, 0, HN_GSLOT_Z0 + 6 * (l - 1), 12 * (l - 1), l == 5, 0, l > 1}; s.transposed = true;
+        layers.push_back(s);
+    }
+    build_tmem_chain(layers, true, &hs->bwdt, hs->bwdt_pack, kBwdTUnits, kBwdTEpis);
+    hs->bwdt.pe_after_epi = -1;
 }
 
 // Two consecutive weight units that continue the same accumulator chunk over the next K block become one
@@ -265,6 +305,7 @@ HostSchedules* build() {
     auto* hs = new HostSchedules();
     memset(hs, 0, sizeof(*hs));
     build_fwd(hs);
+    build_bwdt(hs);
     for (int with_pe = 1; with_pe >= 0; --with_pe) {
         // ---- data-gradient chain (reverse order); dL/dPE accumulated at FeaExt_module_5 and _0
         Builder b; b.n_acc = 3; b.backward = true;

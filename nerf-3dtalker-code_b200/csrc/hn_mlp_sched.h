@@ -118,7 +118,16 @@ struct EpiOp2 {                   // 16 bytes: read with one 128-bit constant lo
 };
 static_assert(sizeof(EpiOp2) == 16, "EpiOp2 is read as one 128-bit word");
 
-struct FwdTables { StageOp stage[kFwdStages]; EpiOp2 epi[kFwdEpis]; int n_stages; int pe_after_epi; int n_ready[3]; int pad; };
+struct FwdTables { StageOp stage[kFwdStages]; EpiOp2 epi[kFwdEpis]; int n_stages; int pe_after_epi; int n_ready[3]; int n_epis;
+                   int tile_flip;   // 1: odd tiles swap the TMEM halves (chains with an odd number of layers), 0: they do not
+                   int pad; };
+
+// ---- data-gradient chain without dL/dPE (the training step), same machinery as the forward chain: gradients live in tensor
+// memory as the A operand, W^T units stream through the ring.  The first GEMM (RGB_layer_2^T) reads the four dL/dfeat
+// K blocks from a two-block shared-memory ring (a_src = kSrcSmem | k, slot k & 1, every block awaited: wait_src 4).
+constexpr int kBwdTUnits = 162;    // 2 * 81 stages (fits the forward tables' arrays: 81 <= 85 stages, 29 <= 31 chunks)
+constexpr int kBwdTStages = kBwdTUnits / 2;
+constexpr int kBwdTEpis = 29;
 
 struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_ops; int n_epis; int n_ready[3]; int n_empty[4]; };
 
@@ -129,6 +138,8 @@ struct HostSchedules {
     BwdTables bwd;                 // full data-gradient chain incl. dL/dPE (camera gradients)
     BwdTables bwd_nope;            // same without the dL/dPE chunks; `unit` still indexes the full stream
     int n_bwd_pack_units;          // weight units in the data-gradient stream (packed after the kFwdUnits forward units)
+    PackOp bwdt_pack[kBwdTUnits];  // W^T units of the tensor-memory data-gradient chain (packed after the two streams above)
+    FwdTables bwdt;
 };
 
 const HostSchedules& host_schedules();   // built on first use (hn_mlp_sched.cpp part of hn_mlp_pack.cu)

@@ -25,7 +25,10 @@ def dump():
     def run(which):
         out = subprocess.run([exe] + ([which] if which != "fwd" else []), check=True, capture_output=True, text=True).stdout
         mma, epi = [], []
+        run.tile_flip = 1
         for line in out.splitlines():
+            if line.startswith("stages ") and "tile_flip" in line:
+                run.tile_flip = int(line.split("tile_flip")[1])
             kv = dict(re.findall(r"(\w+) (-?\d+)", line.replace("|", " ")))
             if line.startswith("U ") or line.startswith("S "):
                 mma.append({k: int(v) for k, v in kv.items()})
@@ -35,7 +38,7 @@ def dump():
     return run
 
 
-def _replay_fwd(stages, epi, n_tiles, late):
+def _replay_fwd(stages, epi, n_tiles, late, tile_flip=1):
     """Replays the forward chain (A operand in tensor memory, alternating TMEM halves) against the ordering facts the kernel
     provides - MMAs execute in issue order; a stage with wait_src waits for that a_ready barrier, one with wait_p for the
     accumulator loads of chunk-2; the epilogue takes chunks in order, loads a chunk only after its commit, stores chunk 0 of
@@ -49,7 +52,7 @@ def _replay_fwd(stages, epi, n_tiles, late):
     ready = [0, 0, 0]; ready_used = [0, 0, 0]
 
     def hx(n):
-        return 256 if (n // n_chunks) & 1 else 0
+        return 256 if (n // n_chunks) & tile_flip else 0
 
     def do_load(n):
         op = epi[n % n_chunks]
@@ -104,14 +107,14 @@ def _replay_fwd(stages, epi, n_tiles, late):
             for a_src, smem in ((m["a0"], m["smem0"]), (m["a1"], m["smem1"])):
                 if a_src < 0 or smem:
                     continue
-                col = a_src ^ (256 if t & 1 else 0)
+                col = a_src ^ (256 if t & tile_flip else 0)
                 tag = tm.get(col)
                 assert tag is not None and tag[0] == "act", f"stage {u} (tile {t}) reads {tag} at column {col}"
                 seen.setdefault((layer_key, a_src), tag)
                 assert seen[(layer_key, a_src)] == tag, f"stage {u}: K block at column {col} changed under the layer"
             for c in range(m["acc_col"], m["acc_col"] + m["n"], 32):
                 chunk = base + m["chunk"] + (1 if (m["n"] > 128 and c >= m["acc_col"] + 128) else 0)
-                tm[c ^ (256 if t & 1 else 0)] = ("acc", chunk)
+                tm[c ^ (256 if t & tile_flip else 0)] = ("acc", chunk)
             for k in range(m["commit"]):
                 assert base + m["chunk"] + k == commits, "chunks must complete in epilogue order"
                 commits += 1
@@ -134,6 +137,26 @@ def test_forward_tmem_schedule(dump, late):
         if e["wait_next"]:
             assert i + 1 < len(epi) and not epi[i + 1]["wait_next"] and epi[i + 1]["ready"] == 1 and e["ready"] == 0
     _replay_fwd(stages, epi, 4, late)
+
+
+@pytest.mark.parametrize("late", [False, True])
+def test_data_gradient_tmem_schedule(dump, late):
+    """The data-gradient chain without dL/dPE runs on the same tensor-memory machinery as the forward chain."""
+    stages, epi = dump("bwdt")
+    assert len(stages) == 81 and len(epi) == 29
+    for c in range(3):
+        assert sum(1 for e in epi if e["ready"] == c) == sum(1 for m in stages if m["wait_src"] == 1 + c), f"a_ready[{c}]"
+    assert sum(m["commit"] for m in stages) == len(epi)
+    # the four dL/dfeat K blocks stream through a two-block shared-memory ring: each is awaited, in order, in phase A only
+    smem = [m for m in stages if m["smem0"]]
+    assert [m["a0"] for m in smem] == [0, 1, 2, 3] and all(m["wait_src"] == 4 and m["a1"] < 0 for m in smem)
+    for i, e in enumerate(epi):
+        if e["wait_next"]:
+            assert i + 1 < len(epi) and not epi[i + 1]["wait_next"] and epi[i + 1]["ready"] == 1 and e["ready"] == 0
+    assert dump.tile_flip == 0                      # even number of layers: the halves must NOT swap between tiles
+    _replay_fwd(stages, epi, 4, late, tile_flip=0)
+    with pytest.raises(AssertionError):             # ... and the replay does catch the cross-tile clobber if they did
+        _replay_fwd(stages, epi, 4, True, tile_flip=1)
 
 
 @pytest.mark.parametrize("which", ["bwd"])

@@ -9,19 +9,22 @@ static void print_pack(const PackOp& p) {
 int main(int argc, char** argv) {
     const HostSchedules& hs = host_schedules();
     const bool bwd = argc > 1 && !strcmp(argv[1], "bwd");
+    const bool bwdt = argc > 1 && !strcmp(argv[1], "bwdt");
     if (!bwd) {
-        // forward chain: A operand in tensor memory (StageOp / EpiOp2)
-        printf("stages %d epis %d pe_after %d\n", hs.fwd.n_stages, kFwdEpis, hs.fwd.pe_after_epi);
-        for (int u = 0; u < hs.fwd.n_stages; ++u) {
-            const StageOp& m = hs.fwd.stage[u];
+        // forward chain / tensor-memory data-gradient chain: A operand in tensor memory (StageOp / EpiOp2)
+        const FwdTables& T = bwdt ? hs.bwdt : hs.fwd;
+        const PackOp* pk = bwdt ? hs.bwdt_pack : hs.fwd_pack;
+        printf("stages %d epis %d pe_after %d tile_flip %d\n", T.n_stages, T.n_epis, T.pe_after_epi, T.tile_flip);
+        for (int u = 0; u < T.n_stages; ++u) {
+            const StageOp& m = T.stage[u];
             printf("S %d chunk %d smem0 %d a0 %d smem1 %d a1 %d acc_col %d n %d first %d commit %d wait_src %d wait_p %d", u, m.chunk, (m.a_src0 & kSrcSmem) ? 1 : 0,
                    m.a_src0 & 0x7FFF, (m.a_src1 != kSrcNone && (m.a_src1 & kSrcSmem)) ? 1 : 0, m.a_src1 == kSrcNone ? -1 : (m.a_src1 & 0x7FFF), m.acc_col, m.n8 * 8,
                    m.first, m.commit, m.wait_src, m.wait_p);
-            print_pack(hs.fwd_pack[2 * u]);
-            printf("P %d", 2 * u + 1); print_pack(hs.fwd_pack[2 * u + 1]);
+            print_pack(pk[2 * u]);
+            printf("P %d", 2 * u + 1); print_pack(pk[2 * u + 1]);
         }
-        for (int e = 0; e < kFwdEpis; ++e) {
-            const EpiOp2& o = hs.fwd.epi[e];
+        for (int e = 0; e < T.n_epis; ++e) {
+            const EpiOp2& o = T.epi[e];
             printf("E %d acc_col %d out_col %d width %d kind %d ready %d density %d wait_next %d signal_p %d bias_off %d col0 %d save_blk %d mask_word %d\n", e, o.acc_col,
                    o.out_col == kNoCol ? -1 : (int)o.out_col, o.width32 * 32, o.kind, o.ready_idx, o.flags & 3, (o.flags >> 2) & 1, (o.flags >> 3) & 1, o.bias_off, o.col0, o.save_blk, o.mask_word);
         }
