@@ -114,6 +114,7 @@ def run_ours(args):
     for p in net.neural_render.parameters():
         p.requires_grad_(False)                       # the consumer is outside the timed hot path
     bucket = dist_mod.GradBucket(net.fg_CD_predictor.parameters())
+    net.fuse_grad_accumulation()                      # kernels accumulate straight into the bucket's views (no per-parameter add kernels)
     host = build_inputs(O, opt_o, B_PER_GPU, seed=rank, device=dev)
     pinned = {k: v.contiguous().pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}

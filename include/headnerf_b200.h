@@ -205,6 +205,37 @@ size_t hn_wgrad_workspace_bytes(int B);
 int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Latent-code folding.  Replaces the broadcast + concat of the codes to every sample
+ * (NetWorks/HeadNeRFNet.py:84-89,149-152; NetWorks/models.py:69,75,80): the codes' weight columns become one
+ * effective bias row per batch item (layout above); the backward maps the bias-row gradient produced by
+ * hn_mlp_bwd_weights / hn_mlp_bwd_data_precise to the gradients of the codes, of the folded weight columns
+ * (accumulated, +=, into full-size weight-gradient tensors) and of the 12 bias vectors (+=).              */
+typedef struct {
+    int B, shape_dims, appea_dims;    /* audio-style code is 64 wide (NetWorks/models.py:32)                */
+    const float* w0;  int ld0;        /* FeaExt_module_0.weight [384, 63 + shape_dims + 64]                 */
+    const float* w5;  int ld5;        /* FeaExt_module_5.weight [384, 63 + shape_dims + 384]                */
+    const float* wr1; int ldr1;       /* RGB_layer_1.weight     [192, 384 + appea_dims]                     */
+    const float* bias[12];            /* bias vectors in hn_weights_t order ([8] = density_module.bias)     */
+    const float* shape_code;          /* [B, shape_dims]                                                    */
+    const float* audio;               /* [B, 64]                                                            */
+    const float* appea;               /* [B, appea_dims]                                                    */
+} hn_fold_t;
+
+typedef struct {
+    float* dshape; float* daudio; float* dappea;   /* written (=); NULL = not needed                       */
+    float* dw0; float* dw5; float* dwr1;           /* latent columns accumulated (+=); NULL = not needed    */
+    float* dbias[12];                              /* accumulated (+=); NULL = not needed                   */
+} hn_fold_grads_t;
+
+int hn_fold_bias(const hn_fold_t* a, float* bias_eff /*[B, HN_BIAS_STRIDE]*/, void* stream);
+int hn_fold_bias_bwd(const hn_fold_t* a, const float* dbias_eff /*[B, HN_BIAS_STRIDE]*/, const hn_fold_grads_t* g, void* stream);
+
+/* Power-of-two loss scale of the half-precision backward chain: *scale_out = 2^floor(log2(target / max|g|)),
+ * computed on the device (no host sync).  scratch8 = 8 bytes, zero before the first call (the kernel leaves
+ * them zero again, so one buffer per stream can be reused without re-clearing).                           */
+int hn_loss_scale(const float* g, int64_t n, float target, float* scale_out, void* scratch8, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * High-precision mode ("fp32-accumulate mode" with split operands): the same chain, layer by layer, with
  * fp32 activations in HBM and every tensor-core product computed as hi*hi + lo*hi + hi*lo over
  * half-precision hi/lo splits of BOTH operands (~22 significant bits; csrc/hn_precise.cu).

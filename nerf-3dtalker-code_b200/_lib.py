@@ -68,11 +68,20 @@ class MlpBwdDataPrecise(C.Structure):
                 ("g_ray_l", _p), ("dbias", _p), ("act_image", _p), ("grads_image", _p), ("dfeat_image", _p), ("status", _p)]
 
 
+class Fold(C.Structure):
+    _fields_ = [("B", C.c_int), ("shape_dims", C.c_int), ("appea_dims", C.c_int), ("w0", _p), ("ld0", C.c_int), ("w5", _p), ("ld5", C.c_int),
+                ("wr1", _p), ("ldr1", C.c_int), ("bias", _p * 12), ("shape_code", _p), ("audio", _p), ("appea", _p)]
+
+
+class FoldGrads(C.Structure):
+    _fields_ = [("dshape", _p), ("daudio", _p), ("dappea", _p), ("dw0", _p), ("dw5", _p), ("dwr1", _p), ("dbias", _p * 12)]
+
+
 EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pack_weights", "hn_sample_rays",
            "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
            "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes",
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
-           "hn_mlp_bwd_data_precise"]
+           "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale"]
 
 _lib = None
 
@@ -106,6 +115,9 @@ def load():
     lib.hn_pack_weights_precise.argtypes = [C.POINTER(Weights), _p, _p]
     lib.hn_mlp_fwd_precise.argtypes = [C.POINTER(MlpFwdPrecise), _p]
     lib.hn_mlp_bwd_data_precise.argtypes = [C.POINTER(MlpBwdDataPrecise), _p]
+    lib.hn_fold_bias.argtypes = [C.POINTER(Fold), _p, _p]
+    lib.hn_fold_bias_bwd.argtypes = [C.POINTER(Fold), _p, C.POINTER(FoldGrads), _p]
+    lib.hn_loss_scale.argtypes = [_p, C.c_int64, C.c_float, _p, _p, _p]
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
     lib.hn_mlp_fwd.argtypes = [C.POINTER(MlpFwd), _p]
     lib.hn_composite_fwd.argtypes = [C.POINTER(CompositeFwd), _p]
@@ -114,7 +126,7 @@ def load():
     lib.hn_mlp_bwd_weights.argtypes = [C.POINTER(MlpBwdWeights), _p]
     for name in ("hn_pack_weights", "hn_sample_rays", "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd",
                  "hn_mlp_bwd_data", "hn_mlp_bwd_weights", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
-                 "hn_mlp_bwd_data_precise"):
+                 "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale"):
         getattr(lib, name).restype = C.c_int
     if lib.hn_abi_version() != 1:
         raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")

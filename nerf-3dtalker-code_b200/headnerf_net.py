@@ -86,6 +86,7 @@ class HeadNeRFNet(nn.Module):
         # "fast": fused single-pass half-precision-operand kernels (fp32 accumulate); "high": split-operand (hi+lo) tensor-core
         # GEMMs with fp32 activations, ~fp32 accuracy at ~3x the tensor work.  Not part of the state dict.
         self.precision = os.environ.get("HN_PRECISION", "fast")
+        self._fuse_grads = False
 
     # ------------------------------------------------------------------ weights -> kernel operands
     def _packed_weights(self):
@@ -104,8 +105,31 @@ class HeadNeRFNet(nn.Module):
             self._packed_hl_key = key
         return ws, self._packed_hl
 
+    def fuse_grad_accumulation(self, enable=True):
+        """Opt-in: the kernels accumulate fg_CD_predictor's weight and bias gradients straight into the parameters' existing
+        `.grad` buffers (e.g. the views of dist.GradBucket's flat all-reduce buffer) instead of returning them through
+        autograd's AccumulateGrad - no per-parameter zero-fill and add kernels.  Every parameter needs a `.grad` beforehand."""
+        self._fuse_grads = bool(enable)
+        return self
+
+    def _grad_into(self):
+        if not (self._fuse_grads and torch.is_grad_enabled()):
+            return None
+        lay = self.fg_CD_predictor.layers()
+        if any(m.weight.requires_grad and m.weight.grad is None for m in lay) or any(m.bias.requires_grad and m.bias.grad is None for m in lay):
+            raise RuntimeError("fuse_grad_accumulation: every fg_CD_predictor parameter needs an allocated .grad (e.g. dist.GradBucket)")
+        return {"w": [m.weight.grad if m.weight.requires_grad else None for m in lay],
+                "b": [m.bias.grad if m.bias.requires_grad else None for m in lay]}
+
+    def _fold_biases_cuda(self, shape_code, appea_code, audiostyle, grad_into):
+        """Effective bias row per batch item through the library (hn_fold_bias): [B, HN_BIAS_STRIDE]."""
+        lay = self.fg_CD_predictor.layers()
+        return ops.FoldBiasFunction.apply(shape_code, audiostyle, appea_code, lay[0].weight, lay[5].weight, lay[10].weight,
+                                          *[m.bias for m in lay], {"grad_into": grad_into})
+
     def _fold_biases(self, shape_code, appea_code, audiostyle):
-        """Effective bias row per batch item: [B, HN_BIAS_STRIDE]."""
+        """Effective bias row per batch item: [B, HN_BIAS_STRIDE].  Plain-PyTorch statement of the folding
+        algebra (CPU host-logic tests, any dtype); the render path uses _fold_biases_cuda."""
         fg = self.fg_CD_predictor
         B, S, H = shape_code.shape[0], self.shape_dims, L.HIDDEN
         lay = fg.layers()
@@ -159,9 +183,10 @@ class HeadNeRFNet(nn.Module):
         if self.precision not in ("fast", "high"):
             raise ValueError(f"precision must be 'fast' or 'high', got {self.precision!r}")
         high = self.precision == "high"
-        bias = self._fold_biases(shape_code.float(), appea_code.float(), audiostyle.float())
+        grad_into = self._grad_into()
+        bias = self._fold_biases_cuda(shape_code.float(), appea_code.float(), audiostyle.float(), grad_into)
         meta = {"n_samples": ns, "world_z1": self.opt.world_z1, "world_z2": self.opt.world_z2,
-                "l5_hidden_col": L.PE + self.shape_dims, "precision": self.precision,
+                "l5_hidden_col": L.PE + self.shape_dims, "precision": self.precision, "grad_into": None if high else grad_into,
                 "grad_target": float(getattr(self, "grad_target", 1024.0 if high else 64.0))}
         if high:
             ws, meta["packed_hl"] = self._packed_weights_precise()

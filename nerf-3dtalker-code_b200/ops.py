@@ -221,6 +221,95 @@ def ray_params_torch(xy, R, T, Kinv):
     return o, d * l, l
 
 
+_SCALE_SCRATCH = {}
+
+
+def loss_scale(gF, target):
+    """Device scalar 2^floor(log2(target / max|gF|)) (hn_loss_scale): one launch, no host sync."""
+    lib = L.load()
+    key = (gF.device, torch.cuda.current_stream().cuda_stream)
+    if key not in _SCALE_SCRATCH:
+        _SCALE_SCRATCH[key] = torch.zeros(2, dtype=torch.int32, device=gF.device)
+    scale = torch.empty(1, device=gF.device)
+    _call("hn_loss_scale", lib.hn_loss_scale, _ptr(gF), gF.numel(), C.c_float(float(target)), _ptr(scale), _ptr(_SCALE_SCRATCH[key]), _stream())
+    return scale
+
+
+def _grad_dst(into, i, like):
+    """Gradient destination of input i: the caller's accumulation buffer (fused accumulation, e.g. a view of the flat
+    all-reduce bucket) or None."""
+    if into is None or into[i] is None:
+        return None
+    t = into[i]
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != like.numel() or t.device != like.device:
+        raise ValueError("fused gradient accumulation needs contiguous float32 buffers shaped like the parameters")
+    return t
+
+
+class FoldBiasFunction(torch.autograd.Function):
+    """(shape_code [B,S], audiostyle [B,64], appea_code [B,A], W0, W5, WR1, 12 biases, meta) -> effective bias rows
+    [B, HN_BIAS_STRIDE] (hn_fold_bias / hn_fold_bias_bwd).  meta["grad_into"] (optional): {"w": 12 weight-gradient
+    buffers, "b": 12 bias-gradient buffers} to accumulate into directly instead of returning parameter gradients."""
+
+    @staticmethod
+    def _args(shape, audio, appea, w0, w5, wr1, biases):
+        a = L.Fold()
+        a.B, a.shape_dims, a.appea_dims = shape.shape[0], shape.shape[1], appea.shape[1]
+        a.w0, a.ld0 = w0.data_ptr(), w0.numel() // w0.shape[0]
+        a.w5, a.ld5 = w5.data_ptr(), w5.numel() // w5.shape[0]
+        a.wr1, a.ldr1 = wr1.data_ptr(), wr1.numel() // wr1.shape[0]
+        for i, b in enumerate(biases):
+            a.bias[i] = b.data_ptr()
+        a.shape_code, a.audio, a.appea = shape.data_ptr(), audio.data_ptr(), appea.data_ptr()
+        return a
+
+    @staticmethod
+    def forward(ctx, shape, audio, appea, w0, w5, wr1, *rest):
+        biases, meta = rest[:12], rest[12]
+        lib = L.load()
+        shape, audio, appea = _dev_f32(shape, "shape_code"), _dev_f32(audio, "audiostyle"), _dev_f32(appea, "appea_code")
+        if audio.shape[1] != 64 or audio.shape[0] != shape.shape[0] or appea.shape[0] != shape.shape[0]:
+            raise ValueError("latent code shapes: shape [B,S], audiostyle [B,64], appea [B,A]")
+        w0, w5, wr1 = (_dev_f32(w.detach(), "folded weight") for w in (w0, w5, wr1))
+        bs = [_dev_f32(b.detach(), "bias") for b in biases]
+        out = torch.empty(shape.shape[0], L.BIAS_STRIDE, device=shape.device)
+        a = FoldBiasFunction._args(shape, audio, appea, w0, w5, wr1, bs)
+        _call("hn_fold_bias", lib.hn_fold_bias, C.byref(a), _ptr(out), _stream())
+        ctx.save_for_backward(shape, audio, appea, w0, w5, wr1, *bs)
+        ctx.meta = meta
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        shape, audio, appea, w0, w5, wr1 = ctx.saved_tensors[:6]
+        bs = ctx.saved_tensors[6:]
+        need = ctx.needs_input_grad
+        into = ctx.meta.get("grad_into")
+        g = g.contiguous().float()
+        a = FoldBiasFunction._args(shape, audio, appea, w0, w5, wr1, bs)
+        out = L.FoldGrads()
+        res = [None] * 19
+        for i, (name, t) in enumerate((("dshape", shape), ("daudio", audio), ("dappea", appea))):
+            if need[i]:
+                res[i] = torch.empty_like(t)
+                setattr(out, name, res[i].data_ptr())
+        for i, (name, t, widx) in enumerate((("dw0", w0, 0), ("dw5", w5, 5), ("dwr1", wr1, 10))):
+            if need[3 + i]:
+                dst = _grad_dst(into["w"] if into else None, widx, t)
+                if dst is None:
+                    dst = res[3 + i] = torch.zeros_like(t)
+                setattr(out, name, dst.data_ptr())
+        for i, b in enumerate(bs):
+            if need[6 + i]:
+                dst = _grad_dst(into["b"] if into else None, i, b)
+                if dst is None:
+                    dst = res[6 + i] = torch.zeros_like(b)
+                out.dbias[i] = dst.data_ptr()
+        _call("hn_fold_bias_bwd", lib.hn_fold_bias_bwd, C.byref(a), _ptr(g), C.byref(out), _stream(), kernels=2)
+        return tuple(res)
+
+
 class RenderFunction(torch.autograd.Function):
     """inputs : xy [B,2,N_r], R [B,3,3], T [B,3,1], K^-1 [B,3,3], t_rand or None, bias_eff [B,3920],
                 12 weights (header order; [8] is density_module.weight), then non-tensor meta
@@ -277,16 +366,28 @@ class RenderFunction(torch.autograd.Function):
         gF = gF.contiguous().float()
         g_bg = g_bg.contiguous().float()
         # power-of-two loss scale so that half-precision gradient operands stay in range
-        gmax = torch.maximum(gF.abs().amax(), g_bg.abs().amax() * 0.0).clamp_min(1e-30)
-        scale = torch.pow(2.0, torch.floor(torch.log2(meta.get("grad_target", 64.0) / gmax))).reshape(1)
+        scale = loss_scale(gF, meta.get("grad_target", 64.0))
         _, dimg, dsigma, ddelta = _composite_bwd(feat, sigma, delta, None, gF, g_bg, None, ns, image=True,
                                                  grad_scale=scale, want_ddelta=need_cam)
         save_grads = need_w or need_bias
         grads = torch.empty(lib.hn_grads_bytes(M), dtype=torch.uint8, device=dev) if save_grads else None
-        g_o = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
-        g_v = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None
-        g_l = torch.zeros(B * n_rays, device=dev) if need_cam else None
-        status = torch.zeros(64, dtype=torch.int32, device=dev)
+        # every zero-initialised output of this pass is a view of ONE buffer: one memset instead of ~20
+        into = meta.get("grad_into")
+        into_w = into["w"] if into else None
+        dst_w = [_grad_dst(into_w, i, weights[i]) if (need_w and need[6 + i]) else None for i in range(12)]
+        sizes = {"status": 64, "g_o": B * n_rays * 3 if need_cam else 0, "g_v": B * n_rays * 3 if need_cam else 0,
+                 "g_l": B * n_rays if need_cam else 0, "dbias": B * L.BIAS_STRIDE if save_grads else 0}
+        for i in range(12):
+            sizes[f"w{i}"] = weights[i].numel() if (need_w and need[6 + i] and dst_w[i] is None) else 0
+        zbuf = torch.zeros(sum(sizes.values()), device=dev)
+        views, off = {}, 0
+        for k, n in sizes.items():
+            views[k] = zbuf[off:off + n] if n else None
+            off += n
+        g_o = views["g_o"].view(B * n_rays, 3) if need_cam else None
+        g_v = views["g_v"].view(B * n_rays, 3) if need_cam else None
+        g_l = views["g_l"]
+        status = views["status"].view(torch.int32)
         a = L.MlpBwdData()
         a.cam = _camera(xy, R, T, Kinv, t_rand, ns, meta["world_z1"], meta["world_z2"])
         a.packed, a.w_density, a.dfeat_image = _ptr(meta["packed"]), _ptr(wd), _ptr(dimg)
@@ -298,7 +399,7 @@ class RenderFunction(torch.autograd.Function):
         dws = [None] * 12
         dbias = None
         if save_grads:
-            dbias = torch.zeros(B, L.BIAS_STRIDE, device=dev)
+            dbias = views["dbias"].view(B, L.BIAS_STRIDE)
             w = L.MlpBwdWeights()
             w.B, w.n_rays, w.n_samples = B, n_rays, ns
             w.act, w.grads, w.dfeat_image, w.grad_scale = _ptr(act), _ptr(grads), _ptr(dimg), _ptr(scale)
@@ -306,9 +407,12 @@ class RenderFunction(torch.autograd.Function):
             wksp = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             w.items_workspace, w.items_workspace_bytes = _ptr(wksp), ws_bytes
             for i, wt in enumerate(weights):
-                if need_w:
-                    dws[i] = torch.zeros_like(wt)
-                    w.dw[i] = dws[i].data_ptr()
+                if need_w and need[6 + i]:
+                    if dst_w[i] is not None:                       # fused accumulation: straight into the caller's buffer
+                        w.dw[i] = dst_w[i].data_ptr()
+                    else:
+                        dws[i] = views[f"w{i}"].view_as(wt)
+                        w.dw[i] = dws[i].data_ptr()
                 else:
                     w.dw[i] = None
                 w.ld[i] = wt.numel() // wt.shape[0]
@@ -414,8 +518,7 @@ class RenderFunctionPrecise(torch.autograd.Function):
         need_bias = need[5]
         gF = gF.contiguous().float()
         g_bg = g_bg.contiguous().float()
-        gmax = torch.maximum(gF.abs().amax(), g_bg.abs().amax() * 0.0).clamp_min(1e-30)
-        scale = torch.pow(2.0, torch.floor(torch.log2(meta.get("grad_target", 64.0) / gmax))).reshape(1)
+        scale = loss_scale(gF, meta.get("grad_target", 64.0))
         dfeat, _, dsigma, ddelta = _composite_bwd(feat, sigma, delta, None, gF, g_bg, None, ns, image=False, want_ddelta=need_cam)
         gz = torch.empty(lib.hn_precise_workspace_floats(M), device=dev)
         g_o = torch.zeros(B * n_rays, 3, device=dev) if need_cam else None

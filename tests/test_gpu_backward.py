@@ -110,3 +110,36 @@ def test_codes_only(hn, name):
         assert abs(float(cp[k].double().norm()) / max(g["pnorm"][k], 1e-30) - 1.0) < 0.02, k
     print(f"{name} codes-only worst parameter cosine {worst[1]:.6f} ({worst[0]})")
     assert worst[1] >= GATE, worst
+
+
+def test_fused_grad_accumulation_matches_autograd(hn):
+    """fuse_grad_accumulation(): the kernels add straight into the flat bucket's views; the result must equal what autograd's
+    AccumulateGrad produces (twice the single-pass gradient after two backward passes)."""
+    g = load_golden("fs8_train_trained")
+    opt = g["opt"]
+
+    def run(fused):
+        net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": opt.featmap_size, "featmap_nc": 256, "pred_img_size": opt.pred_img_size}), False, False)
+        net.load_state_dict(O.formula_state_dict(opt, g["variant"]), strict=True)
+        net = net.to(DEV).eval()
+        for p in net.neural_render.parameters():
+            p.requires_grad_(False)
+        bucket = hn.dist.GradBucket(net.fg_CD_predictor.parameters())
+        net.fuse_grad_accumulation(fused)
+        x = {k: v.to(DEV) for k, v in g["inp"].items()}
+        gF = torch.randn(g["B"], opt.featmap_size ** 2, 256, generator=torch.Generator().manual_seed(5)).to(DEV) * 1e-2
+        for _ in range(2):
+            codes = {k: x[k].clone().requires_grad_(True) for k in ("shape_code", "appea_code", "audiostyle")}
+            Fm, bg = net.render_rays(g["mode"], x["batch_xy"], codes["audiostyle"], codes["shape_code"], codes["appea_code"],
+                                     x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"], t_rand=x.get("t_rand"))
+            torch.autograd.backward([Fm, bg], [gF, gF[..., 0].contiguous()])
+        hn.ops.check_status(net.last_meta["last_status"], "fused accumulation")
+        return bucket.flat.clone(), {k: v.grad.clone() for k, v in codes.items()}
+
+    flat_a, codes_a = run(False)
+    flat_f, codes_f = run(True)
+    assert float(flat_a.abs().max()) > 0
+    # atomics make the summation order differ between runs: compare to fp32 reduction noise
+    assert (flat_a - flat_f).abs().max() <= 2e-4 * flat_a.abs().max(), float((flat_a - flat_f).abs().max() / flat_a.abs().max())
+    for k in codes_a:
+        assert cosine(codes_a[k], codes_f[k]) > 0.99999

@@ -159,3 +159,39 @@ def test_intermediate_activations_match_oracle(hn):
         m = hn.ops.decode_masks(masks, 12 * i, 384, M).cpu()
         disagree = (m != (ref > 0)) & (ref.abs() > 1e-2)
         assert disagree.sum() == 0
+
+
+def test_fold_bias_kernel_matches_folding_algebra(hn):
+    """hn_fold_bias / hn_fold_bias_bwd against the plain-PyTorch statement of the folding (HeadNeRFNet._fold_biases, itself
+    checked against the reference concat orders on CPU): values and every gradient (codes, folded weight columns, biases)."""
+    torch.manual_seed(3)
+    net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": 8, "featmap_nc": 256, "pred_img_size": 32}), False, False).to(DEV)
+    B = 3
+    codes = [torch.randn(B, n, device=DEV) for n in (179, 127, 64)]                # shape, appea, audio
+    gout = torch.randn(B, hn._lib.BIAS_STRIDE, device=DEV)
+    gout[:, hn._lib.BIAS_OFF_DENSITY + 1:] = 0                                      # padding carries no gradient
+    res = []
+    for fn in ("torch", "cuda"):
+        net.zero_grad(set_to_none=True)
+        xs = [c.clone().requires_grad_(True) for c in codes]
+        bias = net._fold_biases(*xs) if fn == "torch" else net._fold_biases_cuda(*xs, None)
+        (bias * gout).sum().backward()
+        res.append((bias.detach(), [x.grad for x in xs], {k: p.grad.clone() for k, p in net.fg_CD_predictor.named_parameters() if p.grad is not None}))
+    (b0, g0, p0), (b1, g1, p1) = res
+    assert (b0 - b1).abs().max() < 1e-5
+    for a, b in zip(g0, g1):
+        assert (a - b).abs().max() < 1e-4 * (1 + a.abs().max())
+    assert set(p0) == set(p1)
+    for k in p0:
+        assert (p0[k] - p1[k]).abs().max() < 1e-4 * (1 + p0[k].abs().max()), k
+
+
+def test_loss_scale_kernel(hn):
+    torch.manual_seed(0)
+    for n, mx in ((1000003, 3.7e-4), (256, 9.0), (5, 1e-20)):
+        g = torch.randn(n, device=DEV).clamp(-1, 1) * mx * 0.5
+        g[n // 3] = -mx
+        for _ in range(2):                                                          # the scratch words are reused: call twice
+            s = hn.ops.loss_scale(g, 64.0)
+        want = 2.0 ** torch.floor(torch.log2(torch.tensor(64.0 / max(mx, 1e-30))))
+        assert float(s) == float(want), (n, float(s), float(want))
