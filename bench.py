@@ -214,13 +214,13 @@ def run_ours(args):
     # DRAM traffic per launch comes from the committed ncu --set full capture of this workload (profiles/)
     traffic = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r01b_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01d_traffic.json")) as f:
             traffic = {k: v["dram_gbytes_per_launch"] * 1e9 for k, v in json.load(f)["kernels"].items()}
     except Exception:
         pass
     dom = max((n for n in flops if n in kernels), key=lambda n: kernels[n]["ms_avg"])
     roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops_algorithmic"], "peak": peaks["tflops"],
-                "unit": "TFLOP/s", "frac": kernels[dom]["frac_of_tensor_peak"], "traffic": traffic.get(dom), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01b_traffic.json)",
+                "unit": "TFLOP/s", "frac": kernels[dom]["frac_of_tensor_peak"], "traffic": traffic.get(dom), "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01d_traffic.json)",
                 "peak_source": peaks["src"],
                 "step_tflops_algorithmic": round(FLOP_STEP * M / (ms_step * 1e-3) / 1e12, 1)}
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())

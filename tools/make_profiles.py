@@ -16,14 +16,14 @@ agg = collections.OrderedDict()
 for r in rows[1:]:
     if len(r) <= vi or r[hdr.index("Metric Name")] != "gpu__time_duration.sum":
         continue
-    name = re.sub(r"\((?!bool\)).*", "", r[ki])
+    name = re.sub(r"\(.*", "", r[ki])
     unit = r[hdr.index("Metric Unit")]
     v = float(r[vi].replace(",", "")) * ({"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1.0))
     d = agg.setdefault(name, [0, 0.0]); d[0] += 1; d[1] += v
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(prof, f"{tag}_launch_list.md"), "w") as f:
     f.write(f"# ncu launch list, {title}: first {sum(v[0] for v in agg.values())} launches of `python bench.py --steps 3 --warmup 3` (Reso64 batch 2)\n\n")
-    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 220` - cold-cache, serialised times: compare SHARES, not absolutes.\n\n")
+    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 120` - cold-cache, serialised times: compare SHARES, not absolutes.\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
         f.write(f"| {k[:90]} | {n} | {us:.1f} | {100 * us / tot:.1f} % |\n")
@@ -37,16 +37,16 @@ want = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg.per_second", "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum"]
 seen, traffic = set(), {}
-names = {"mlp_fwd_kernel": "hn_mlp_fwd", "mlp_chain_kernel<(bool)0>": "hn_mlp_fwd", "mlp_chain_kernel<(bool)1>": "hn_mlp_bwd_data",
+names = {"mlp_fwd_kernel": "hn_mlp_fwd", "mlp_chain_kernel<0>": "hn_mlp_fwd", "mlp_chain_kernel<1>": "hn_mlp_bwd_data",
          "composite_fwd_kernel": "hn_composite_fwd", "composite_bwd_kernel": "hn_composite_bwd",
          "mlp_bwd_kernel": "hn_mlp_bwd_data", "mlp_wgrad_kernel": "hn_mlp_bwd_weights"}
 with open(os.path.join(prof, f"{tag}_ncu_full_summary.md"), "w") as f:
     f.write(f"# ncu --set full summary, {title} (bench.py --steps 3 --warmup 3; Reso64 batch 2)\n\n")
-    f.write("Source: `ncu --set full --clock-control none --import-source on -k regex:\"mlp_|composite\" -s 15 -c 5` on a B200 (gpurun); the .ncu-rep is not committed.\n")
+    f.write("Source: `ncu --set full --clock-control none --import-source on -k regex:\"mlp_|composite\" -s 12 -c 6` on a B200 (gpurun); the .ncu-rep is not committed.\n")
     f.write("Times under ncu are cold-cache and serialised; the bench's CUDA-event times are the reported ones.\n")
     for r in rr[2:]:
         kname = r[h.index("Kernel Name")]
-        short = re.sub(r"\((?!bool\)).*", "", kname)
+        short = re.sub(r"\(.*", "", kname)
         if short in seen:
             continue
         seen.add(short)
