@@ -203,12 +203,175 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
     if (warp == 1) tmem_free<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant for the 384 x 384 layers (cta_group::2, M = 256): the pair accumulates the dW rows of chunks 0 and 1 of ONE
+// layer over the same samples.  CTA r loads its own dZ chunk and only HALF of the layer-input columns (X blocks 2r, 2r+1 and
+// 4+r): the tensor core reads the B operand's halves from both SMs, so 40 KiB instead of 64 KiB land in each SM's shared memory
+// per 64-sample stage.  Chunk 2 of those layers has no partner (384 = 256 + 128) and stays on the single-CTA kernel.
+// EXPERIMENT, opt-in with HN_WGRAD_PAIRS=1: correct, but slower than the 3-CTA multicast clusters (see hn_mlp_bwd_weights).
+constexpr int kPairStages = 5;
+constexpr uint32_t kPairStageBytes = 5 * kHalfBytes;          // dZ chunk (2 half-blocks) + 3 X half-blocks = 40 KiB
+constexpr uint32_t kPairOffOnes = kPairStages * kPairStageBytes;
+constexpr uint32_t kPairSmem = kPairOffOnes + 2048 + 1024;
+
+struct WPairShared {
+    uint64_t full[kPairStages], peer_full[kPairStages], empty[kPairStages], acc_full, acc_empty;
+    uint32_t tmem_base;
+    volatile int abort;
+};
+
+__device__ __forceinline__ bool wwait_cluster(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
+    const uint32_t b = smem_u32(bar);
+    if (mbar_try_wait_cluster(b, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(b, parity)) {
+        if (*abort_flag) return false;
+        if (clock64() - t0 > 2000000000ll) { *abort_flag = 1; atomicCAS(status, 0, code); return false; }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_pair_kernel(const WArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ WPairShared sh;
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int item0 = (int)blockIdx.x >> 1, item_stride = (int)gridDim.x >> 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < kPairStages; ++i) { mbar_init(smem_u32(&sh.full[i]), 1); mbar_init(smem_u32(&sh.peer_full[i]), 1); mbar_init(smem_u32(&sh.empty[i]), 1); }
+        mbar_init(smem_u32(&sh.acc_full), 1);
+        mbar_init(smem_u32(&sh.acc_empty), 256);                  // the flush threads of BOTH CTAs release the leader's issuer
+        sh.abort = 0;
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 2048 / 4; i += kWThreads)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem + kPairOffOnes + i * 4), "r"(0x3C003C00u) : "memory");
+    fence_async_smem();
+    if (warp == 1) tmem_alloc_pair<512>(smem_u32(&sh.tmem_base));
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = sh.tmem_base;
+
+    if (warp == 0) {
+        // ======================= producer (both CTAs): own dZ chunk + own half of the X columns =======================
+        if (lane == 0) {
+            uint32_t sc = 0;
+            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
+                const WItem w = a.items[it];
+                const int xb[3] = {w.x_blk[2 * rank], w.x_blk[2 * rank + 1], w.x_blk[4 + rank]};
+                for (int tile = w.tile0; tile < w.tile1; ++tile) {
+                    for (int half = 0; half < 2; ++half, ++sc) {
+                        const uint32_t stage = sc % kPairStages, par = (sc / kPairStages) & 1;
+                        if (!wwait_cluster(&sh.empty[stage], par ^ 1, &sh.abort, a.status, 741)) break;
+                        const uint32_t fb = smem_u32(&sh.full[stage]);
+                        mbar_arrive_expect_tx(fb, kPairStageBytes);
+                        const uint32_t dst = smem + stage * kPairStageBytes;
+                        for (int k = 0; k < 2; ++k)
+                            bulk_g2s(dst + k * kHalfBytes, a.grads + ((size_t)(w.g_blk + 2 * rank + k) * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
+                        for (int k = 0; k < 3; ++k)
+                            bulk_g2s(dst + (2 + k) * kHalfBytes, a.act + ((size_t)xb[k] * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 1) {
+            // ======================= peer: relay "my stage has landed" to the leader =======================
+            uint32_t sc = 0;
+            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
+                const WItem w = a.items[it];
+                for (int n = 2 * (w.tile1 - w.tile0); n > 0; --n, ++sc) {
+                    const uint32_t stage = sc % kPairStages, par = (sc / kPairStages) & 1;
+                    if (!wwait(&sh.full[stage], par, &sh.abort, a.status, 750)) break;
+                    mbar_arrive_cluster(smem_u32(&sh.peer_full[stage]), 0);
+                }
+            }
+        } else if (lane == 0) {
+            // ======================= leader: MMA issuer =======================
+            uint32_t sc = 0, n_item = 0;
+            const uint32_t idesc1 = umma_idesc(256, 256, kF16, kF16, 1, 1), idesc2 = umma_idesc(256, 128, kF16, kF16, 1, 1);
+            const uint32_t idesc_bias = umma_idesc(256, 16, kF16, kF16, 1, 0);
+            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride, ++n_item) {
+                const WItem w = a.items[it];
+                bool ok = wwait_cluster(&sh.acc_empty, (n_item & 1) ^ 1, &sh.abort, a.status, 742);
+                bool first = true;
+                for (int tile = w.tile0; tile < w.tile1 && ok; ++tile) {
+                    for (int half = 0; half < 2; ++half, ++sc) {
+                        const uint32_t stage = sc % kPairStages, par = (sc / kPairStages) & 1;
+                        ok = wwait(&sh.full[stage], par, &sh.abort, a.status, 743);
+                        if (ok) ok = wwait_cluster(&sh.peer_full[stage], par, &sh.abort, a.status, 744);
+                        if (!ok) break;
+                        tc_fence_after_sync();
+                        const uint32_t g_addr = smem + stage * kPairStageBytes;
+                        const uint32_t x_addr = g_addr + 2 * kHalfBytes;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t ad = umma_desc_mnmajor(g_addr, ks, kHalfBytes);
+                            const bool acc = !(first && ks == 0);
+                            umma_f16_pair(tmem_base, ad, umma_desc_mnmajor(x_addr, ks, kHalfBytes), idesc1, acc);
+                            umma_f16_pair(tmem_base + 256, ad, umma_desc_mnmajor(x_addr + 2 * kHalfBytes, ks, kHalfBytes), idesc2, acc);
+                            umma_f16_pair(tmem_base + kBiasCol, ad, umma_desc_kmajor(smem + kPairOffOnes, ks), idesc_bias, acc);
+                        }
+                        first = false;
+                        umma_commit_pair(smem_u32(&sh.empty[stage]));          // both CTAs' stages are free once these MMAs retire
+                    }
+                }
+                umma_commit_pair(smem_u32(&sh.acc_full));
+            }
+        }
+    } else {
+        // ======================= flush (both CTAs): own 128 rows of the pair's accumulator =======================
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const float inv_scale = 1.0f / __ldg(a.grad_scale);
+        uint32_t n_item = 0;
+        for (int it = item0; it < a.n_items && !sh.abort; it += item_stride, ++n_item) {
+            const WItem w = a.items[it];
+            wwait_cluster(&sh.acc_full, n_item & 1, &sh.abort, a.status, 745);
+            tc_fence_after_sync();
+            float* dw = (w.w_idx >= 0) ? a.dw[w.w_idx] : nullptr;
+            for (int k = 0; k < 6; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + k * 64 + h * 32, v);
+                    tmem_ld_wait();
+                    if (dw) {
+                        float* dst = dw + (size_t)(w.row0 + 128 * rank + row) * a.ld[w.w_idx] + w.x_col[k] + h * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]) * inv_scale);
+                    }
+                }
+            }
+            {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + kBiasCol, v);
+                tmem_ld_wait();
+                if (w.bias_off >= 0 && a.dbias)
+                    atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + w.bias_off + 128 * rank + row, __uint_as_float(v[0]) * inv_scale);
+            }
+            tc_fence_before_sync();
+            mbar_arrive_cluster(smem_u32(&sh.acc_empty), 0);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_free_pair<512>(tmem_base);
+}
+
 static std::mutex g_w_mu;
 static bool g_w_ready[64] = {};
 
 // host: enumerate work items.  `cluster` = items for the 3-CTA multicast kernel (three consecutive entries = the three
 // 128-channel chunks of one layer over one sample range); `single` = everything else.
-static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters, std::vector<WItem>& cluster, std::vector<WItem>& single) {
+static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters, int n_pairs, std::vector<WItem>& cluster, std::vector<WItem>& single,
+                        std::vector<WItem>& pairs) {
     const int tiles_per_item = (int)(((int64_t)a.n_rays * a.n_samples) / HN_TILE);
     bool want_w = false;
     for (int i = 0; i < 12; ++i) want_w = want_w || (a.dw[i] != nullptr);
@@ -222,27 +385,32 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     layers.push_back({W_R2, HN_FEAT, 0, 1, HN_BIAS_OFF_R2, HN_SLOT_X, 3, false, 0});
     layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});   // density pseudo layer
     auto active = [&](const LayerW& L) { return want_w || L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1; };
-    auto clustered = [&](const LayerW& L) { return want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
-    int pairs_single = 0, layers_cluster = 0;
+    // CTA pairs: 384 x 384 layers (six hidden X blocks, no PE block); their chunk 2 goes to the single-CTA list
+    auto paired = [&](const LayerW& L) { return want_w && n_pairs > 0 && L.n_out == HN_HIDDEN && L.n_xblk == 6 && !L.pe && a.dw[L.w_idx] != nullptr; };
+    auto clustered = [&](const LayerW& L) { return !paired(L) && want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
+    int pairs_single = 0, layers_cluster = 0, layers_pair = 0;
     for (const LayerW& L : layers) {
         if (!active(L)) continue;
-        if (clustered(L)) ++layers_cluster; else pairs_single += (L.n_out + 127) / 128;
+        if (paired(L)) { ++layers_pair; ++pairs_single; }
+        else if (clustered(L)) ++layers_cluster; else pairs_single += (L.n_out + 127) / 128;
     }
     auto pick = [&](int units, int workers) {
         if (units == 0) return 1;
         int sp = (2 * workers + units * a.B - 1) / (units * a.B);
         return sp < 1 ? 1 : (sp > tiles_per_item ? tiles_per_item : sp);
     };
-    const int splits_c = pick(layers_cluster, n_clusters), splits_s = pick(pairs_single, n_sm);
+    const int splits_c = pick(layers_cluster, n_clusters), splits_s = pick(pairs_single, n_sm), splits_p = pick(layers_pair, n_pairs);
     for (const LayerW& L : layers) {
         if (!active(L)) continue;
-        const bool cl = clustered(L);
-        const int splits = cl ? splits_c : splits_s;
-        std::vector<WItem>& out = cl ? cluster : single;
+        const bool cl = clustered(L), pr = paired(L);
         // cluster items: chunk index innermost (three consecutive entries share layer, item and sample range)
+        for (int pass = 0; pass < (pr ? 2 : 1); ++pass) {             // paired layers: pass 0 = the pair item (chunks 0+1), pass 1 = chunk 2 alone
+        const bool pair_item = pr && pass == 0;
+        const int splits = pair_item ? splits_p : (cl ? splits_c : splits_s);
+        std::vector<WItem>& out = pair_item ? pairs : (cl ? cluster : single);
         for (int b = 0; b < a.B; ++b)
             for (int sp = 0; sp < splits; ++sp)
-                for (int j = 0; j * 128 < L.n_out; ++j) {
+                for (int j = (pr && pass == 1) ? 2 : 0; j * 128 < (pair_item ? 128 : L.n_out); ++j) {
                     WItem w{};
                     w.w_idx = (int16_t)((want_w && a.dw[L.w_idx]) ? L.w_idx : -1);
                     w.row0 = (int16_t)(128 * j);
@@ -261,6 +429,7 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
                     w.n_x = (int16_t)n;
                     if (w.tile1 > w.tile0) out.push_back(w);
                 }
+        }
     }
 }
 
@@ -281,6 +450,7 @@ static int launch_wgrad(const WArgs& k, int cl, int grid, cudaStream_t st) {
 }
 
 static int g_w_clusters[64] = {};
+static int g_w_pairs[64] = {};
 
 }  // namespace hn
 
@@ -311,20 +481,35 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
             if (env && atoi(env) == 0) n = 0;
             else if (cudaOccupancyMaxActiveClusters(&n, mlp_wgrad_kernel<3>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
             g_w_clusters[dev] = n;
+            // resident CTA pairs of the pair kernel.  Opt-in (HN_WGRAD_PAIRS=1): validated by the same parity tests, but measured
+            // SLOWER on B200 (2.90 vs 2.21 ms per Reso64 batch-2 pass) - what bounds this kernel is L2 -> SM read traffic, which the
+            // 3-CTA multicast clusters already cut to the compulsory 32 KiB per chunk and stage; a pair reads 40 KiB and strands chunk 2.
+            int np = 0;
+            const char* envp = getenv("HN_WGRAD_PAIRS");
+            if (envp && atoi(envp) != 0) {
+                e = cudaFuncSetAttribute(mlp_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
+                if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+                cfg.gridDim = dim3(2 * 74); cfg.dynamicSmemBytes = kPairSmem;
+                attr.val.clusterDim.x = 2;
+                if (cudaOccupancyMaxActiveClusters(&np, mlp_wgrad_pair_kernel, &cfg) != cudaSuccess) { np = 0; cudaGetLastError(); }
+            }
+            g_w_pairs[dev] = np;
             g_w_ready[dev] = true;
         }
     }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_clusters = dev < 64 ? g_w_clusters[dev] : 0;
-    std::vector<WItem> cluster, single;
-    build_items(*a, n_sm, n_clusters, cluster, single);
-    if (cluster.empty() && single.empty()) return HN_OK;
-    if ((cluster.size() + single.size()) * sizeof(WItem) > a->items_workspace_bytes)
+    const int n_pairs = dev < 64 ? g_w_pairs[dev] : 0;
+    std::vector<WItem> cluster, single, pairs;
+    build_items(*a, n_sm, n_clusters, n_pairs, cluster, single, pairs);
+    if (cluster.empty() && single.empty() && pairs.empty()) return HN_OK;
+    if ((cluster.size() + single.size() + pairs.size()) * sizeof(WItem) > a->items_workspace_bytes)
         return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: items workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<WItem> all(cluster);
     all.insert(all.end(), single.begin(), single.end());
+    all.insert(all.end(), pairs.begin(), pairs.end());
     // the item table is tiny (<100 KiB); pageable -> device copy is stream-ordered and returns after staging
     cudaError_t e = cudaMemcpyAsync(a->items_workspace, all.data(), all.size() * sizeof(WItem), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
@@ -335,6 +520,19 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     k.dbias = a->dbias;
     k.n_tiles = (int)(total_samples(a->B, a->n_rays, a->n_samples) / HN_TILE);
     k.status = a->status;
+    if (!pairs.empty()) {
+        k.items = (const WItem*)a->items_workspace + cluster.size() + single.size(); k.n_items = (int)pairs.size();
+        const int np = k.n_items < n_pairs ? k.n_items : n_pairs;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * np); cfg.blockDim = dim3(kWThreads); cfg.dynamicSmemBytes = kPairSmem; cfg.stream = st;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        cudaError_t pe = cudaLaunchKernelEx(&cfg, mlp_wgrad_pair_kernel, k);
+        if (pe != cudaSuccess) return set_error((int)pe, cudaGetErrorString(pe));
+        if (int rc = check_launch("hn_mlp_bwd_weights (CTA pairs)")) return rc;
+    }
     if (!cluster.empty()) {
         k.items = (const WItem*)a->items_workspace; k.n_items = (int)cluster.size() / 3;
         const int nc = k.n_items < n_clusters ? k.n_items : n_clusters;
@@ -350,5 +548,5 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
 
 extern "C" size_t hn_wgrad_workspace_bytes(int B) {
     // upper bound: 35 (layer, chunk) pairs x B x splits, splits chosen so that items <= 2*SMs + pairs*B
-    return (size_t)(35 * (size_t)(B > 0 ? B : 1) + 2 * 160 + 64) * 2 * sizeof(hn::WItem);
+    return (size_t)(35 * (size_t)(B > 0 ? B : 1) + 3 * 160 + 64) * 2 * sizeof(hn::WItem);
 }
