@@ -213,10 +213,23 @@ class HeadNeRFNet(nn.Module):
         fg_feat = Fm.permute(0, 2, 1).reshape(batch_size, C, fs, fs)
         bg_alpha = bg.view(batch_size, 1, fs, fs)
         bg_featmap = self.neural_render.get_bg_featmap()
-        bg_img = self.neural_render(bg_featmap)
+        bg_img = self._bg_image(bg_featmap)
         merge_featmap = fg_feat + bg_alpha * bg_featmap
         merge_img = self.neural_render(merge_featmap)
         return {"coarse_dict": {"merge_img": merge_img, "bg_img": bg_img}}
+
+    def _bg_image(self, bg_featmap):
+        """bg_img = neural_render(bg_featmap) (HeadNeRFNet.py:109) depends on parameters only: when none of them can receive a
+        gradient (inference, the fitting loop with frozen weights) it is computed once per parameter version."""
+        params = list(self.neural_render.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return self.neural_render(bg_featmap)
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_bg_cache_key", None) != key:
+            with torch.no_grad():
+                self._bg_cache = self.neural_render(bg_featmap)
+            self._bg_cache_key = key
+        return self._bg_cache
 
     def forward(self, mode, batch_xy, batch_uv, audiostyle, bg_code, shape_code, appea_code,
                 batch_Rmats, batch_Tvecs, batch_inv_inmats, dist_expr=False, **kwargs):

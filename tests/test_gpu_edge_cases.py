@@ -61,6 +61,37 @@ def test_ragged_rays_and_sample_counts(hn, ns, n_rays, B, jitter, precision):
     assert worst[0] >= 0.999, worst
 
 
+def test_gaze_columns(hn):
+    """include_gaze=True (HeadNeRFNet.py:49-52; talker_trainer.py:736-747): eye_gaze_dim extra columns ride at the end of the
+    shape/expression code and of the folded column blocks of FeaExt_module_0 / _5.  Oracle: the same algebra with a 2-wider code."""
+    opt = O.OracleOptions(featmap_size=8, pred_img_size=32, expr_code_dims=79 + 2)
+    net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": 8, "featmap_nc": 256, "pred_img_size": 32}), False, False, include_gaze=True, eye_gaze_dim=2)
+    sd = O.formula_state_dict(opt, "trained")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).eval()
+    inp = O.synthetic_inputs(opt, 2, seed=21)
+    assert inp["shape_code"].shape[1] == 181
+    sdo = {k: v.clone().requires_grad_(k.startswith("fg_CD_predictor")) for k, v in sd.items()}
+    xo = {k: v.clone().requires_grad_(k in CODES) for k, v in inp.items()}
+    r = O.render_features(sdo, opt, "test", xo["batch_xy"], xo["audiostyle"], xo["shape_code"], xo["appea_code"],
+                          xo["batch_Rmats"], xo["batch_Tvecs"], xo["batch_inv_inmats"])
+    gen = torch.Generator().manual_seed(2)
+    gF, gb = torch.randn(r["F"].shape, generator=gen), torch.randn(r["bg_alpha"].shape, generator=gen)
+    torch.autograd.backward([r["F"], r["bg_alpha"]], [gF, gb])
+    xc = {k: v.to(DEV).requires_grad_(k in CODES) for k, v in inp.items()}
+    Fm, bg = net.render_rays("test", xc["batch_xy"], xc["audiostyle"], xc["shape_code"], xc["appea_code"],
+                             xc["batch_Rmats"], xc["batch_Tvecs"], xc["batch_inv_inmats"])
+    torch.autograd.backward([Fm, bg], [gF.permute(0, 2, 1).contiguous().to(DEV), gb[:, 0].contiguous().to(DEV)])
+    hn.ops.check_status(net.last_meta["last_status"], "gaze")
+    errF = (Fm.detach().cpu() - r["F"].detach().permute(0, 2, 1)).abs().max().item()
+    scale = max(1.0, float(r["F"].abs().max()))
+    assert errF <= 1e-3 * scale, errF
+    worst = min([(cosine(xc[k].grad, xo[k].grad), k) for k in CODES] +
+                [(cosine(p.grad, sdo["fg_CD_predictor." + n].grad), n) for n, p in net.fg_CD_predictor.named_parameters()])
+    print(f"gaze: F err {errF:.1e} (|F|max {scale:.2f}), worst gradient cosine {worst[0]:.6f} ({worst[1]})")
+    assert worst[0] >= 0.999, worst
+
+
 def test_error_behaviour(hn):
     with pytest.raises(hn._lib.HeadNeRFLibraryError):           # 48 samples per ray: outside what the kernels are specialised for
         opt, sd, net = _net(hn, 8, 48)

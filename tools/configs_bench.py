@@ -85,6 +85,25 @@ torch.cuda.synchronize(); dt = time.perf_counter() - t0
 M = 1024 * 64
 print(f"| 4 | fitting loop, 500 iterations, Reso32 (32x32 x 64), grads to codes + camera only | {dt / 500 * 1e3:.3f} (total {dt:.2f} s) | {M * 500 / dt:.3e} |")
 hn.ops.check_status(net.last_meta["last_status"], "config 4")
+net.precision = "high"                      # split-operand mode: camera-gradient cosine 0.99999 instead of 0.998
+for _ in range(5):
+    fit_iter()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(500):
+    fit_iter()
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print(f"| 4 | same loop, precision=\"high\" (hi+lo split operands, fp32 activations) | {dt / 500 * 1e3:.3f} (total {dt:.2f} s) | {M * 500 / dt:.3e} |")
+hn.ops.check_status(net.last_meta["last_status"], "config 4 high")
+net.precision = "fast"
+def fit_hot():
+    xs = {k: (x[k] + off[k]) for k in off}
+    Fm, bg = net.render_rays("test", x["batch_xy"], x["audiostyle"], xs["shape_code"], xs["appea_code"], x["batch_Rmats"] + 0 * d_euler.sum(), x["batch_Tvecs"] + d_T, x["batch_inv_inmats"])
+    (Fm.sum() + bg.sum()).backward()
+for prec in ("fast", "high"):
+    net.precision = prec
+    ms = timed(fit_hot, 50)
+    print(f"| 4 | hot path only of one fitting iteration (fwd + bwd to codes and camera), precision={prec} | {ms:.3f} | {M / ms * 1e3:.3e} |")
+net.precision = "fast"
 
 # ---- config 5: forward-only sweep
 for ns in (32, 64, 128):
