@@ -8,12 +8,17 @@
 // bias gradient (= per-item column sums of dZ, from which the host derives the latent-code and folded
 // weight-column gradients), then flushes once with atomic adds.  The density head rides along as a
 // one-channel pseudo layer (its gradient block is written by hn_mlp_bwd_data).
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
 #include "hn_api.h"
 #include "hn_mlp_sched.h"
 #include "hn_tc.cuh"
+
+#ifndef HN_WEXP
+#define HN_WEXP 0
+#endif
 
 namespace hn {
 
@@ -25,6 +30,7 @@ constexpr uint32_t kWOffOnes = kWStages * kWStageBytes;
 constexpr uint32_t kWgradSmem = kWOffOnes + 2048 + 1024;
 constexpr int kWThreads = 192;                              // warp 0 producer, warp 1 MMA (+TMEM alloc), warps 2..5 flush
 constexpr uint32_t kBiasCol = 448;
+constexpr int kWProd = 5;                                   // producer lanes (see the producer role)
 
 struct WItem {
     int16_t w_idx;            // destination weight (index into dw[]), -1: none
@@ -99,11 +105,16 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
     const uint32_t tmem_base = sh.tmem_base;
 
     if (warp == 0) {
-        // ======================= producer =======================
-        if (lane == 0) {
+        // ======================= producers =======================
+        // The bulk copies of ONE thread complete one after the other (~700 cycles apiece under load, whatever their size), and a
+        // stage is 4-9 copies of 8 KiB: a lone producer thread caps the kernel at ~2400 cycles per stage.  kWProd lanes walk the
+        // same schedule and take the stage's copies round-robin; lane 0 posts the byte count (a copy that lands before that only
+        // drives the transaction count negative for a moment: the phase cannot complete before lane 0's arrival).
+        if (lane < kWProd) {
             uint32_t sc = 0;
             for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
                 const WItem w = a.items[it * CL + rank];
+                if (w.tile1 <= w.tile0) continue;                  // padding entry of the balanced schedule
                 const uint8_t* gsrc = w.g_dfeat ? a.dfeat_image : a.grads;
                 const uint32_t bytes = (2 + w.n_x) * kHalfBytes;
                 for (int tile = w.tile0; tile < w.tile1; ++tile) {
@@ -111,14 +122,22 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                         const uint32_t stage = sc % kWStages, par = (sc / kWStages) & 1;
                         if (!wwait(&sh.empty[stage], par ^ 1, &sh.abort, a.status, 701)) break;
                         const uint32_t fb = smem_u32(&sh.full[stage]);
-                        mbar_arrive_expect_tx(fb, bytes);
+#if HN_WEXP == 2                                                    // diagnostic build: no operand loads (MMA path alone)
+                        if (lane == 0) mbar_arrive(fb);
+                        continue;
+#endif
+                        if (lane == 0) mbar_arrive_expect_tx(fb, bytes);
                         const uint32_t dst = smem + stage * kWStageBytes;
+                        int j = 0;
                         for (int k = 0; k < 2; ++k)
-                            bulk_g2s(dst + k * kHalfBytes, gsrc + ((size_t)(w.g_blk + k) * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
+                            if ((j++ % kWProd) == lane)
+                                bulk_g2s(dst + k * kHalfBytes, gsrc + ((size_t)(w.g_blk + k) * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
                         for (int k = 0; k < w.n_x; ++k) {
+                            if (CL > 1 && k % CL != (int)rank) continue;
+                            if ((j++ % kWProd) != lane) continue;
                             const uint8_t* xs = a.act + ((size_t)w.x_blk[k] * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes;
                             if (CL == 1) bulk_g2s(dst + (2 + k) * kHalfBytes, xs, kHalfBytes, fb);
-                            else if (k % CL == (int)rank) bulk_g2s_multicast(dst + (2 + k) * kHalfBytes, xs, kHalfBytes, fb, kMask);
+                            else bulk_g2s_multicast(dst + (2 + k) * kHalfBytes, xs, kHalfBytes, fb, kMask);
                         }
                     }
                 }
@@ -129,9 +148,11 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
         if (lane == 0) {
             uint32_t sc = 0, n_item = 0;
             const uint32_t idesc_bias = umma_idesc(128, 16, kF16, kF16, 1, 0);
-            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride, ++n_item) {
+            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
                 const WItem w = a.items[it * CL + rank];
+                if (w.tile1 <= w.tile0) continue;
                 bool ok = wwait(&sh.acc_empty, (n_item & 1) ^ 1, &sh.abort, a.status, 710);
+                ++n_item;
                 bool first = true;
                 for (int tile = w.tile0; tile < w.tile1 && ok; ++tile) {
                     for (int half = 0; half < 2; ++half, ++sc) {
@@ -141,6 +162,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                         tc_fence_after_sync();
                         const uint32_t g_addr = smem + stage * kWStageBytes;
                         const uint32_t x_addr = g_addr + 2 * kHalfBytes;
+#if HN_WEXP != 1                                                    // diagnostic build 1: no MMAs (load path alone)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint64_t ad = umma_desc_mnmajor(g_addr, ks, kHalfBytes);
@@ -151,6 +173,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                             }
                             umma_f16(tmem_base + kBiasCol, ad, umma_desc_kmajor(smem + kWOffOnes, ks), idesc_bias, !(first && ks == 0));
                         }
+#endif
                         first = false;
                         if (CL == 1) umma_commit(smem_u32(&sh.empty[stage]));
                         else umma_commit_multicast(smem_u32(&sh.empty[stage]), kMask);     // a stage is refilled by all peers: all must release it
@@ -165,9 +188,11 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float inv_scale = 1.0f / __ldg(a.grad_scale);
         uint32_t n_item = 0;
-        for (int it = item0; it < a.n_items && !sh.abort; it += item_stride, ++n_item) {
+        for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
             const WItem w = a.items[it * CL + rank];
+            if (w.tile1 <= w.tile0) continue;
             wwait(&sh.acc_full, n_item & 1, &sh.abort, a.status, 720);
+            ++n_item;
             tc_fence_after_sync();
             const bool row_ok = row < w.rows;
             for (int k = 0; k < w.n_x; ++k) {
@@ -388,46 +413,116 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     // CTA pairs: 384 x 384 layers (six hidden X blocks, no PE block); their chunk 2 goes to the single-CTA list
     auto paired = [&](const LayerW& L) { return want_w && n_pairs > 0 && L.n_out == HN_HIDDEN && L.n_xblk == 6 && !L.pe && a.dw[L.w_idx] != nullptr; };
     auto clustered = [&](const LayerW& L) { return !paired(L) && want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
-    int pairs_single = 0, layers_cluster = 0, layers_pair = 0;
-    for (const LayerW& L : layers) {
-        if (!active(L)) continue;
-        if (paired(L)) { ++layers_pair; ++pairs_single; }
-        else if (clustered(L)) ++layers_cluster; else pairs_single += (L.n_out + 127) / 128;
-    }
-    auto pick = [&](int units, int workers) {
-        if (units == 0) return 1;
-        int sp = (2 * workers + units * a.B - 1) / (units * a.B);
-        return sp < 1 ? 1 : (sp > tiles_per_item ? tiles_per_item : sp);
+    // A unit = one layer (cluster list: its three chunks side by side) or one chunk (single list) of one batch item, over all of
+    // the item's tiles, with a cost per tile ~ MMA cycles / operand bytes of a stage.  The units of a list are laid end to end and
+    // cut into one equal-cost share per worker (a 3-CTA cluster or a CTA): a worker gets one or two sample ranges, every worker
+    // finishes at the same time, and each accumulator is flushed (atomics) only once or twice.  [Equal sample splits per layer
+    // left 108 equal items for 45 resident clusters: a makespan of 3 items against a mean of 2.4.]
+    // Measured (no-MMA / no-load diagnostic builds, ncu): a stage takes ~2400 cycles almost regardless of how many operand
+    // blocks it carries - the kernel is bound by DRAM latency against the bytes three stages keep in flight, not by tensor or
+    // byte throughput - so a tile costs about the same whatever the layer width; the block count only adds a small slope.
+    static const double slope = [] { const char* e = getenv("HN_WGRAD_SLOPE"); return e ? atof(e) : 40.0; }();   // tuning knob (cycles per operand block)
+    auto stage_cost = [](int n_x) { return 1000.0 + slope * n_x; };
+    struct Unit { std::vector<WItem> tmpl; int b; double cost; };
+    std::vector<Unit> units_c, units_s;
+    int layers_pair = 0;
+    auto make_item = [&](const LayerW& L, int j, int b) {
+        WItem w{};
+        w.w_idx = (int16_t)((want_w && a.dw[L.w_idx]) ? L.w_idx : -1);
+        w.row0 = (int16_t)(128 * j);
+        w.rows = (int16_t)std::min(128, L.n_out - 128 * j);
+        w.g_blk = L.g_blk + 2 * j;
+        w.g_dfeat = (int16_t)L.g_dfeat;
+        w.bias_off = (int16_t)(L.bias_off + 128 * j);
+        w.b = b;
+        int n = 0;
+        if (w.w_idx >= 0) {
+            for (int k = 0; k < L.n_xblk; ++k) { w.x_blk[n] = L.x_slot + k; w.x_col[n] = (int16_t)(L.x_col0 + 64 * k); w.x_valid[n] = 64; ++n; }
+            if (L.pe) { w.x_blk[n] = HN_SLOT_PE; w.x_col[n] = 0; w.x_valid[n] = HN_PE; ++n; }
+        }
+        w.n_x = (int16_t)n;
+        return w;
     };
-    const int splits_c = pick(layers_cluster, n_clusters), splits_s = pick(pairs_single, n_sm), splits_p = pick(layers_pair, n_pairs);
     for (const LayerW& L : layers) {
         if (!active(L)) continue;
         const bool cl = clustered(L), pr = paired(L);
-        // cluster items: chunk index innermost (three consecutive entries share layer, item and sample range)
-        for (int pass = 0; pass < (pr ? 2 : 1); ++pass) {             // paired layers: pass 0 = the pair item (chunks 0+1), pass 1 = chunk 2 alone
-        const bool pair_item = pr && pass == 0;
-        const int splits = pair_item ? splits_p : (cl ? splits_c : splits_s);
-        std::vector<WItem>& out = pair_item ? pairs : (cl ? cluster : single);
-        for (int b = 0; b < a.B; ++b)
-            for (int sp = 0; sp < splits; ++sp)
-                for (int j = (pr && pass == 1) ? 2 : 0; j * 128 < (pair_item ? 128 : L.n_out); ++j) {
-                    WItem w{};
-                    w.w_idx = (int16_t)((want_w && a.dw[L.w_idx]) ? L.w_idx : -1);
-                    w.row0 = (int16_t)(128 * j);
-                    w.rows = (int16_t)std::min(128, L.n_out - 128 * j);
-                    w.g_blk = L.g_blk + 2 * j;
-                    w.g_dfeat = (int16_t)L.g_dfeat;
-                    w.bias_off = (int16_t)(L.bias_off + 128 * j);
-                    w.b = b;
-                    w.tile0 = b * tiles_per_item + (int)((int64_t)tiles_per_item * sp / splits);
-                    w.tile1 = b * tiles_per_item + (int)((int64_t)tiles_per_item * (sp + 1) / splits);
-                    int n = 0;
-                    if (w.w_idx >= 0) {
-                        for (int k = 0; k < L.n_xblk; ++k) { w.x_blk[n] = L.x_slot + k; w.x_col[n] = (int16_t)(L.x_col0 + 64 * k); w.x_valid[n] = 64; ++n; }
-                        if (L.pe) { w.x_blk[n] = HN_SLOT_PE; w.x_col[n] = 0; w.x_valid[n] = HN_PE; ++n; }
-                    }
-                    w.n_x = (int16_t)n;
-                    if (w.tile1 > w.tile0) out.push_back(w);
+        if (pr) ++layers_pair;
+        for (int b = 0; b < a.B; ++b) {
+            if (cl) {
+                Unit u; u.b = b;
+                for (int j = 0; j < 3; ++j) u.tmpl.push_back(make_item(L, j, b));
+                u.cost = stage_cost(u.tmpl[0].n_x);
+                units_c.push_back(u);
+            } else {
+                for (int j = pr ? 2 : 0; j * 128 < L.n_out; ++j) {
+                    Unit u; u.b = b;
+                    u.tmpl.push_back(make_item(L, j, b));
+                    u.cost = stage_cost(u.tmpl[0].n_x);
+                    units_s.push_back(u);
+                }
+            }
+        }
+    }
+    auto partition = [&](const std::vector<Unit>& units, int workers, int group, std::vector<WItem>& out) {
+        if (units.empty() || workers <= 0) return;
+        double total = 0;
+        for (const Unit& u : units) total += u.cost * tiles_per_item;
+        const double quota = total / workers;
+        std::vector<std::vector<WItem>> lists(workers);               // `group` consecutive entries per piece
+        int wk = 0;
+        double need = quota;
+        for (const Unit& u : units) {
+            int t = 0;
+            while (t < tiles_per_item) {
+                int take = (int)(need / u.cost + 0.5);
+                take = take < 1 ? 1 : take;
+                if (take > tiles_per_item - t || wk == workers - 1) take = tiles_per_item - t;
+                if (tiles_per_item - t - take > 0 && (tiles_per_item - t - take) * u.cost < 0.03 * quota) take = tiles_per_item - t;   // no crumbs
+                for (int r = 0; r < group; ++r) {
+                    WItem w = u.tmpl[r];
+                    w.tile0 = u.b * tiles_per_item + t;
+                    w.tile1 = w.tile0 + take;
+                    lists[wk].push_back(w);
+                }
+                need -= take * u.cost;
+                t += take;
+                if (need < 0.03 * quota && wk < workers - 1) { ++wk; need += quota; }
+            }
+        }
+        size_t rounds = 0;
+        for (const auto& l : lists) rounds = std::max(rounds, l.size() / group);
+        if (getenv("HN_WGRAD_DEBUG")) {
+            for (int w = 0; w < workers; ++w) {
+                double c = 0;
+                fprintf(stderr, "worker %d:", w);
+                for (size_t i = 0; i < lists[w].size(); i += group) {
+                    const WItem& it = lists[w][i];
+                    c += stage_cost(it.n_x) * (it.tile1 - it.tile0);
+                    fprintf(stderr, " [w%d b%d g%d nx%d tiles %d-%d]", it.w_idx, it.b, it.g_blk, it.n_x, it.tile0, it.tile1);
+                }
+                fprintf(stderr, "  cost %.0f (quota %.0f)\n", c, quota);
+            }
+        }
+        // round-robin order: the j-th piece of worker w sits at index j * workers + w (padding entries have no tiles)
+        for (size_t j = 0; j < rounds; ++j)
+            for (int w = 0; w < workers; ++w)
+                for (int r = 0; r < group; ++r)
+                    out.push_back(j * group + r < lists[w].size() ? lists[w][j * group + r] : WItem{});
+    };
+    partition(units_c, n_clusters, 3, cluster);
+    partition(units_s, n_sm, 1, single);
+    // opt-in CTA-pair items (uniform sample splits)
+    if (layers_pair > 0) {
+        int sp = (2 * n_pairs + layers_pair * a.B - 1) / (layers_pair * a.B);
+        sp = sp < 1 ? 1 : (sp > tiles_per_item ? tiles_per_item : sp);
+        for (const LayerW& L : layers) {
+            if (!active(L) || !paired(L)) continue;
+            for (int b = 0; b < a.B; ++b)
+                for (int q = 0; q < sp; ++q) {
+                    WItem w = make_item(L, 0, b);
+                    w.tile0 = b * tiles_per_item + (int)((int64_t)tiles_per_item * q / sp);
+                    w.tile1 = b * tiles_per_item + (int)((int64_t)tiles_per_item * (q + 1) / sp);
+                    if (w.tile1 > w.tile0) pairs.push_back(w);
                 }
         }
     }
@@ -535,12 +630,12 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     }
     if (!cluster.empty()) {
         k.items = (const WItem*)a->items_workspace; k.n_items = (int)cluster.size() / 3;
-        const int nc = k.n_items < n_clusters ? k.n_items : n_clusters;
+        const int nc = n_clusters;                                  // the balanced schedule has one column per resident cluster
         if (int rc = launch_wgrad(k, 3, 3 * nc, st)) return rc;
     }
     if (!single.empty()) {
         k.items = (const WItem*)a->items_workspace + cluster.size(); k.n_items = (int)single.size();
-        const int grid = k.n_items < n_sm ? k.n_items : n_sm;
+        const int grid = n_sm;
         if (int rc = launch_wgrad(k, 1, grid, st)) return rc;
     }
     return HN_OK;
@@ -548,5 +643,6 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
 
 extern "C" size_t hn_wgrad_workspace_bytes(int B) {
     // upper bound: 35 (layer, chunk) pairs x B x splits, splits chosen so that items <= 2*SMs + pairs*B
-    return (size_t)(35 * (size_t)(B > 0 ? B : 1) + 3 * 160 + 64) * 2 * sizeof(hn::WItem);
+    // upper bound: per list (#workers + #units) pieces, padded to whole rounds: clusters 3 * 3 * (49 + 9 B), single 3 * (160 + 9 B), pairs
+    return (size_t)(160 * (size_t)(B > 0 ? B : 1) + 1600) * sizeof(hn::WItem);
 }
