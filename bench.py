@@ -97,8 +97,7 @@ def build_inputs(O, opt, B, seed, device):
 
 
 def run_ours(args):
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"           # keeps NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / debug log must not share stdout with the ONE JSON line
     hn = importlib.import_module("nerf-3dtalker-code_b200")
     from oracle import headnerf_oracle as O          # input factory only (synthetic_inputs); never on the timed path
     dist_mod = hn.dist
