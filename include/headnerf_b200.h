@@ -108,6 +108,12 @@ typedef struct {
 int hn_sample_rays(const hn_camera_t* cam, float* pts /*[M,3]*/, float* zvals /*[M]*/, float* z_dists /*[M]*/,
                    float* ray_d /*[B*n_rays,3]*/, float* ray_l /*[B*n_rays]*/, void* stream);
 
+/* Backward of the ray set-up (autograd of NetWorks/utils.py:147-158): the per-ray gradients produced by hn_mlp_bwd_data /
+ * hn_mlp_bwd_data_precise (w.r.t. ray origin, ray_d * ray_l and ray_l) -> dL/dRmats [B,3,3], dL/dTvecs [B,3],
+ * dL/dinv_inmats [B,3,3], accumulated (+=, caller zero-initialises); any output may be NULL.              */
+int hn_camera_bwd(const hn_camera_t* cam, const float* g_ray_o /*[B*n_rays,3]*/, const float* g_ray_v /*[B*n_rays,3]*/,
+                  const float* g_ray_l /*[B*n_rays]*/, float* dR, float* dT, float* dKinv, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused sampling + positional encoding + MLP forward.
  * NetWorks/utils.py:43-51,147-161 ; NetWorks/HeadNeRFNet.py:139-152,84-95 ; NetWorks/models.py:62-87  */

@@ -81,7 +81,7 @@ EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pac
            "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
            "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes",
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
-           "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale"]
+           "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd"]
 
 _lib = None
 
@@ -118,6 +118,7 @@ def load():
     lib.hn_fold_bias.argtypes = [C.POINTER(Fold), _p, _p]
     lib.hn_fold_bias_bwd.argtypes = [C.POINTER(Fold), _p, C.POINTER(FoldGrads), _p]
     lib.hn_loss_scale.argtypes = [_p, C.c_int64, C.c_float, _p, _p, _p]
+    lib.hn_camera_bwd.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p, _p]
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
     lib.hn_mlp_fwd.argtypes = [C.POINTER(MlpFwd), _p]
     lib.hn_composite_fwd.argtypes = [C.POINTER(CompositeFwd), _p]
@@ -126,7 +127,7 @@ def load():
     lib.hn_mlp_bwd_weights.argtypes = [C.POINTER(MlpBwdWeights), _p]
     for name in ("hn_pack_weights", "hn_sample_rays", "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd",
                  "hn_mlp_bwd_data", "hn_mlp_bwd_weights", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
-                 "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale"):
+                 "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd"):
         getattr(lib, name).restype = C.c_int
     if lib.hn_abi_version() != 1:
         raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")

@@ -430,26 +430,32 @@ class RenderFunction(torch.autograd.Function):
 
 
 def _camera_chain(xy, R, T, Kinv, g_o, g_v, g_l, need, T_shape):
-    """Per-ray gradients (origin, direction*length, length) -> dL/dR, dL/dT, dL/dK^-1 through NetWorks/utils.py:147-158."""
+    """Per-ray gradients (origin, direction*length, length) -> dL/dR, dL/dT, dL/dK^-1 through NetWorks/utils.py:147-158
+    (hn_camera_bwd: one launch)."""
+    lib = L.load()
     B, _, n_rays = xy.shape
-    gR = gT = gK = None
-    with torch.enable_grad():
-        Rr = R.detach().requires_grad_(need[1])
-        Tr = T.detach().requires_grad_(need[2])
-        Kr = Kinv.detach().requires_grad_(need[3])
-        o, v, l = ray_params_torch(xy, Rr, Tr, Kr)
-        outs = [o, v, l]
-        gouts = [g_o.view(B, n_rays, 3).permute(0, 2, 1), g_v.view(B, n_rays, 3).permute(0, 2, 1), g_l.view(B, 1, n_rays)]
-        ins = [t for t, n in ((Rr, need[1]), (Tr, need[2]), (Kr, need[3])) if n]
-        gs = list(torch.autograd.grad(outs, ins, gouts, allow_unused=True))
-    if need[1]:
-        gR = gs.pop(0)
-    if need[2]:
-        gT = gs.pop(0)
-        gT = gT.reshape(T_shape) if gT is not None else None
-    if need[3]:
-        gK = gs.pop(0)
+    out = torch.zeros(B, 21, device=xy.device)
+    gR, gT, gK = out[:, :9], out[:, 9:12], out[:, 12:]
+    cam = _camera(xy, R, T, Kinv, None, 1, 0.0, 0.0)
+    zeros21 = out.data_ptr()
+    _call("hn_camera_bwd", lib.hn_camera_bwd, C.byref(cam), _ptr(g_o), _ptr(g_v), _ptr(g_l),
+          C.c_void_p(zeros21) if need[1] else None, C.c_void_p(zeros21 + 4 * 9 * B) if need[2] else None,
+          C.c_void_p(zeros21 + 4 * 12 * B) if need[3] else None, _stream())
+    flat = out.view(-1)                                                # laid out [B*9 | B*3 | B*9]
+    gR = flat[:9 * B].view(B, 3, 3) if need[1] else None
+    gT = flat[9 * B:12 * B].view(B, 3).reshape(T_shape) if need[2] else None
+    gK = flat[12 * B:].view(B, 3, 3) if need[3] else None
     return gR, gT, gK
+
+
+def camera_chain_torch(xy, R, T, Kinv, g_o, g_v, g_l):
+    """Reference statement of the same chain with torch autograd (tests only)."""
+    B, _, n_rays = xy.shape
+    with torch.enable_grad():
+        Rr, Tr, Kr = R.detach().requires_grad_(True), T.detach().requires_grad_(True), Kinv.detach().requires_grad_(True)
+        o, v, l = ray_params_torch(xy, Rr, Tr, Kr)
+        gouts = [g_o.view(B, n_rays, 3).permute(0, 2, 1), g_v.view(B, n_rays, 3).permute(0, 2, 1), g_l.view(B, 1, n_rays)]
+        return torch.autograd.grad([o, v, l], [Rr, Tr, Kr], gouts)
 
 
 def pack_weights_precise(weights12, l5_hidden_col, out=None):

@@ -143,3 +143,19 @@ def test_fused_grad_accumulation_matches_autograd(hn):
     assert (flat_a - flat_f).abs().max() <= 2e-4 * flat_a.abs().max(), float((flat_a - flat_f).abs().max() / flat_a.abs().max())
     for k in codes_a:
         assert cosine(codes_a[k], codes_f[k]) > 0.99999
+
+
+def test_camera_chain_kernel_matches_autograd(hn):
+    """hn_camera_bwd (per-ray gradients -> dL/dR, dL/dT, dL/dK^-1) against torch autograd of the same ray set-up
+    (NetWorks/utils.py:147-158)."""
+    opt = O.OracleOptions(featmap_size=16, pred_img_size=64)
+    inp = {k: v.to(DEV) for k, v in O.synthetic_inputs(opt, 3, seed=5, n_rays=777).items()}
+    gen = torch.Generator().manual_seed(2)
+    g_o, g_v, g_l = (torch.randn(3 * 777, 3, generator=gen).to(DEV), torch.randn(3 * 777, 3, generator=gen).to(DEV),
+                     torch.randn(3 * 777, generator=gen).to(DEV))
+    xy, R, T, K = inp["batch_xy"].contiguous(), inp["batch_Rmats"].contiguous(), inp["batch_Tvecs"].reshape(3, 3).contiguous(), inp["batch_inv_inmats"].contiguous()
+    gR, gT, gK = hn.ops._camera_chain(xy, R, T, K, g_o, g_v, g_l, [False, True, True, True], (3, 3, 1))
+    rR, rT, rK = hn.ops.camera_chain_torch(xy, R, T, K, g_o, g_v, g_l)
+    assert gT.shape == (3, 3, 1)
+    for got, ref in ((gR, rR), (gT.reshape(3, 3), rT.reshape(3, 3)), (gK, rK)):
+        assert (got - ref).abs().max() <= 2e-4 * ref.abs().max(), float((got - ref).abs().max() / ref.abs().max())
