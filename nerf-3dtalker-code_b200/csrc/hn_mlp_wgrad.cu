@@ -30,6 +30,11 @@ constexpr uint32_t kWOffOnes = kWStages * kWStageBytes;
 constexpr uint32_t kWgradSmem = kWOffOnes + 2048 + 1024;
 constexpr int kWThreads = 192;                              // warp 0 producer, warp 1 MMA (+TMEM alloc), warps 2..5 flush
 constexpr uint32_t kBiasCol = 448;
+#ifndef HN_WPREFETCH
+#define HN_WPREFETCH 0
+#endif
+constexpr int kWPrefetch = HN_WPREFETCH;                    // L2 prefetch distance in 64-sample stages.  0 = off: measured SLOWER with it (2.24 ms at 4 stages, 2.39 at 8,
+                                                            // 2.63 at 32, against 2.11 without) - the memory system is already saturated
 constexpr int kWProd = 5;                                   // producer lanes (see the producer role)
 
 struct WItem {
@@ -122,22 +127,30 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                         const uint32_t stage = sc % kWStages, par = (sc / kWStages) & 1;
                         if (!wwait(&sh.empty[stage], par ^ 1, &sh.abort, a.status, 701)) break;
                         const uint32_t fb = smem_u32(&sh.full[stage]);
-#if HN_WEXP == 2                                                    // diagnostic build: no operand loads (MMA path alone)
+#if HN_WEXP == 2 || HN_WEXP == 4                                    // diagnostic builds: no operand loads (MMA path alone)
                         if (lane == 0) mbar_arrive(fb);
                         continue;
 #endif
                         if (lane == 0) mbar_arrive_expect_tx(fb, bytes);
                         const uint32_t dst = smem + stage * kWStageBytes;
+                        // the same pieces kWPrefetch stages ahead are pulled DRAM -> L2 now: shared memory holds only three stages, far
+                        // too few bytes in flight to cover DRAM latency, but L2 has room for dozens
+                        const int ahead = 2 * (tile - w.tile0) + half + kWPrefetch;
+                        const int pf_tile = w.tile0 + (ahead >> 1), pf_half = ahead & 1;
+                        const bool pf = kWPrefetch > 0 && pf_tile < w.tile1;
                         int j = 0;
                         for (int k = 0; k < 2; ++k)
-                            if ((j++ % kWProd) == lane)
+                            if ((j++ % kWProd) == lane) {
                                 bulk_g2s(dst + k * kHalfBytes, gsrc + ((size_t)(w.g_blk + k) * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
+                                if (pf) bulk_prefetch_l2(gsrc + ((size_t)(w.g_blk + k) * a.n_tiles + pf_tile) * kUnitBytes + pf_half * kHalfBytes, kHalfBytes);
+                            }
                         for (int k = 0; k < w.n_x; ++k) {
                             if (CL > 1 && k % CL != (int)rank) continue;
                             if ((j++ % kWProd) != lane) continue;
                             const uint8_t* xs = a.act + ((size_t)w.x_blk[k] * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes;
                             if (CL == 1) bulk_g2s(dst + (2 + k) * kHalfBytes, xs, kHalfBytes, fb);
                             else bulk_g2s_multicast(dst + (2 + k) * kHalfBytes, xs, kHalfBytes, fb, kMask);
+                            if (pf) bulk_prefetch_l2(a.act + ((size_t)w.x_blk[k] * a.n_tiles + pf_tile) * kUnitBytes + pf_half * kHalfBytes, kHalfBytes);
                         }
                     }
                 }
@@ -145,36 +158,44 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
+        // One thread issues 12 MMAs per 64-sample stage; measured with the no-load diagnostic build, a generic issue loop
+        // (64-bit descriptors rebuilt per MMA, runtime block loop) took ~2000 cycles per stage - more than the MMAs themselves.
+        // Here the low descriptor words are computed once per stage and stepped with an add (K step of 16 samples = 2 KiB = 128
+        // in descriptor units), and the block loop is resolved per item into at most two MMAs of fixed N.
         if (lane == 0) {
             uint32_t sc = 0, n_item = 0;
             const uint32_t idesc_bias = umma_idesc(128, 16, kF16, kF16, 1, 0);
+            const uint32_t ones_lo = desc_lo(smem + kWOffOnes, 16);
             for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
                 const WItem w = a.items[it * CL + rank];
                 if (w.tile1 <= w.tile0) continue;
                 bool ok = wwait(&sh.acc_empty, (n_item & 1) ^ 1, &sh.abort, a.status, 710);
                 ++n_item;
-                bool first = true;
+                const int n1 = w.n_x < 4 ? w.n_x : 4, n2 = w.n_x - n1;              // X blocks of the first / second MMA
+                const uint32_t idesc1 = umma_idesc(128, (uint32_t)(n1 > 0 ? n1 : 1) * 64, kF16, kF16, 1, 1);
+                const uint32_t idesc2 = umma_idesc(128, (uint32_t)(n2 > 0 ? n2 : 1) * 64, kF16, kF16, 1, 1);
+                uint32_t first = 0;                                                   // accumulate flag of the item's first K step
                 for (int tile = w.tile0; tile < w.tile1 && ok; ++tile) {
                     for (int half = 0; half < 2; ++half, ++sc) {
                         const uint32_t stage = sc % kWStages, par = (sc / kWStages) & 1;
                         ok = wwait(&sh.full[stage], par, &sh.abort, a.status, 711);
                         if (!ok) break;
                         tc_fence_after_sync();
-                        const uint32_t g_addr = smem + stage * kWStageBytes;
-                        const uint32_t x_addr = g_addr + 2 * kHalfBytes;
 #if HN_WEXP != 1                                                    // diagnostic build 1: no MMAs (load path alone)
+                        const uint32_t g_addr = smem + stage * kWStageBytes;
+                        const uint32_t g_lo = desc_lo(g_addr, kHalfBytes);
+                        const uint32_t x_lo = desc_lo(g_addr + 2 * kHalfBytes, kHalfBytes), x2_lo = desc_lo(g_addr + 6 * kHalfBytes, kHalfBytes);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t ad = umma_desc_mnmajor(g_addr, ks, kHalfBytes);
-                            for (int x0 = 0; x0 < w.n_x; x0 += 4) {
-                                const int nb = min(4, w.n_x - x0);
-                                umma_f16(tmem_base + x0 * 64, ad, umma_desc_mnmajor(x_addr + x0 * kHalfBytes, ks, kHalfBytes),
-                                         umma_idesc(128, nb * 64, kF16, kF16, 1, 1), !(first && ks == 0));
-                            }
-                            umma_f16(tmem_base + kBiasCol, ad, umma_desc_kmajor(smem + kWOffOnes, ks), idesc_bias, !(first && ks == 0));
+                        for (uint32_t ks = 0; ks < 4; ++ks) {
+                            const uint32_t acc = ks == 0 ? first : 1u;
+                            if (n1 > 0) umma_f16_lohi(tmem_base, g_lo + ks * 128, x_lo + ks * 128, idesc1, acc);
+                            if (n2 > 0) umma_f16_lohi(tmem_base + 256, g_lo + ks * 128, x2_lo + ks * 128, idesc2, acc);
+#if HN_WEXP != 4
+                            umma_f16_lohi(tmem_base + kBiasCol, g_lo + ks * 128, ones_lo + ks * 2, idesc_bias, acc);
+#endif
                         }
 #endif
-                        first = false;
+                        first = 1;
                         if (CL == 1) umma_commit(smem_u32(&sh.empty[stage]));
                         else umma_commit_multicast(smem_u32(&sh.empty[stage]), kMask);     // a stage is refilled by all peers: all must release it
                     }
