@@ -84,8 +84,10 @@ class HeadNeRFNet(nn.Module):
         self._packed_hl_key = None
         self.last_meta = None
         # "fast": fused single-pass half-precision-operand kernels (fp32 accumulate); "high": split-operand (hi+lo) tensor-core
-        # GEMMs with fp32 activations, ~fp32 accuracy at ~3x the tensor work.  Not part of the state dict.
-        self.precision = os.environ.get("HN_PRECISION", "fast")
+        # GEMMs with fp32 activations, ~fp32 accuracy at ~3x the tensor work; "auto" (default): "high"
+        # exactly when a camera input (batch_Rmats / batch_Tvecs / batch_inv_inmats) requires a gradient - the fitting loop,
+        # whose ill-conditioned camera gradients need it - and "fast" otherwise (training, inference).  Not part of the state dict.
+        self.precision = os.environ.get("HN_PRECISION", "auto")
         self._fuse_grads = False
 
     # ------------------------------------------------------------------ weights -> kernel operands
@@ -180,13 +182,15 @@ class HeadNeRFNet(nn.Module):
             t_rand = torch.rand(B, n_r, ns + 1, device=batch_xy.device, dtype=torch.float32)
         if t_rand is not None and pad:
             t_rand = torch.cat([t_rand, t_rand[:, -1:, :].expand(B, pad, ns + 1)], dim=1)
-        if self.precision not in ("fast", "high"):
-            raise ValueError(f"precision must be 'fast' or 'high', got {self.precision!r}")
-        high = self.precision == "high"
+        if self.precision not in ("auto", "fast", "high"):
+            raise ValueError(f"precision must be 'auto', 'fast' or 'high', got {self.precision!r}")
+        camera_grad = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad
+                                                      for t in (batch_Rmats, batch_Tvecs, batch_inv_inmats))
+        high = self.precision == "high" or (self.precision == "auto" and camera_grad)
         grad_into = self._grad_into()
         bias = self._fold_biases_cuda(shape_code.float(), appea_code.float(), audiostyle.float(), grad_into)
         meta = {"n_samples": ns, "world_z1": self.opt.world_z1, "world_z2": self.opt.world_z2,
-                "l5_hidden_col": L.PE + self.shape_dims, "precision": self.precision, "grad_into": None if high else grad_into,
+                "l5_hidden_col": L.PE + self.shape_dims, "precision": "high" if high else "fast", "grad_into": None if high else grad_into,
                 "grad_target": float(getattr(self, "grad_target", 1024.0 if high else 64.0))}
         if high:
             ws, meta["packed_hl"] = self._packed_weights_precise()

@@ -31,12 +31,14 @@ def _oracle_grads(g):
     return {k: x[k].grad for k in LEAVES}, {k: v.grad for k, v in sd.items() if v.grad is not None}
 
 
-def _cuda_grads(hn, g, leaves=LEAVES, param_grads=True):
+def _cuda_grads(hn, g, leaves=LEAVES, param_grads=True, precision="fast"):
     opt = g["opt"]
     net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": opt.featmap_size, "featmap_nc": 256, "pred_img_size": opt.pred_img_size}),
                          include_vd=False, hier_sampling=False)
     net.load_state_dict(O.formula_state_dict(opt, g["variant"]), strict=True)
     net = net.to(DEV).eval()
+    assert net.precision == "auto"                                 # the default
+    net.precision = precision                                       # these tests pin the single-pass kernels unless told otherwise
     if not param_grads:
         for p in net.parameters():
             p.requires_grad_(False)
@@ -89,6 +91,31 @@ def test_fitting_config_no_weight_grads(hn):
         c = cosine(cl[k], ol[k])
         print(f"fitting {k:14s} cos {c:.6f}")
         assert c >= (GATE_CAMERA if k in CAMERA else GATE), k
+
+
+def test_default_precision_meets_the_gate_on_every_leaf(hn):
+    """precision="auto" (the default): camera inputs that require a gradient select the split-operand kernels, so the drop-in
+    clears cosine >= 0.999 on EVERY leaf - batch_Rmats / batch_Tvecs included - without the caller doing anything; without
+    camera gradients the same module runs the fast kernels."""
+    g = load_golden("fs16_test_trained")
+    ol, _ = _oracle_grads(g)
+    cl, _ = _cuda_grads(hn, g, param_grads=False, precision="auto")
+    for k in LEAVES:
+        c = cosine(cl[k], ol[k])
+        print(f"auto {k:14s} cos {c:.6f}")
+        assert c >= GATE, (k, c)
+    opt = g["opt"]
+    net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": opt.featmap_size, "featmap_nc": 256, "pred_img_size": opt.pred_img_size}), False, False).to(DEV)
+    x = {k: v.to(DEV) for k, v in g["inp"].items()}
+    for cam_grad, want in ((False, "fast"), (True, "high")):
+        R = x["batch_Rmats"].clone().requires_grad_(cam_grad)
+        sc = x["shape_code"].clone().requires_grad_(True)
+        net.render_rays("test", x["batch_xy"], x["audiostyle"], sc, x["appea_code"], R, x["batch_Tvecs"], x["batch_inv_inmats"])
+        assert net.last_meta["precision"] == want
+    with torch.no_grad():
+        net.render_rays("test", x["batch_xy"], x["audiostyle"], x["shape_code"], x["appea_code"], x["batch_Rmats"].clone().requires_grad_(True),
+                        x["batch_Tvecs"], x["batch_inv_inmats"])
+    assert net.last_meta["precision"] == "fast"
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

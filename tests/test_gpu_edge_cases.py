@@ -84,7 +84,7 @@ def test_gaze_columns(hn):
     torch.autograd.backward([Fm, bg], [gF.permute(0, 2, 1).contiguous().to(DEV), gb[:, 0].contiguous().to(DEV)])
     hn.ops.check_status(net.last_meta["last_status"], "gaze")
     errF = (Fm.detach().cpu() - r["F"].detach().permute(0, 2, 1)).abs().max().item()
-    scale = max(1.0, float(r["F"].abs().max()))
+    scale = max(1.0, float(r["F"].detach().abs().max()))
     assert errF <= 1e-3 * scale, errF
     worst = min([(cosine(xc[k].grad, xo[k].grad), k) for k in CODES] +
                 [(cosine(p.grad, sdo["fg_CD_predictor." + n].grad), n) for n, p in net.fg_CD_predictor.named_parameters()])

@@ -60,6 +60,7 @@ hn.ops.check_status(net.last_meta["last_status"], "config 3")
 # ---- config 4: fitting loop (FittingSingleImage_new.py:826-903 shape), 500 iterations
 opt, net, x = make(32, 256, 1)
 net.eval()
+net.precision = "fast"                      # (the default "auto" would pick "high" here: camera gradients are requested)
 for p in net.parameters():
     p.requires_grad_(False)
 off = {k: torch.zeros_like(x[k], requires_grad=True) for k in ("shape_code", "appea_code")}
