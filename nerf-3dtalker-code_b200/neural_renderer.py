@@ -1,13 +1,18 @@
 """NeuralRenderer — the consumer of the composited feature map (reference: NetWorks/neural_renderer.py:11-91,
-NetWorks/PixelShuffleUpsample.py:8-45).  Outside the CUDA hot path: kept as plain
-PyTorch modules whose parameter names, shapes and registration order reproduce the reference state dict
-(`neural_render.*` keys) and its seeded initialisation.  The 3x3 binomial blur restates
-kornia.filters.filter2d(normalized=True, border 'reflect') with a depthwise convolution."""
+NetWorks/PixelShuffleUpsample.py:8-45).  Outside the CUDA hot path: modules whose parameter
+names, shapes and registration order reproduce the reference state dict (`neural_render.*` keys) and its seeded
+initialisation.  The 1x1 convolutions are library GEMMs; on CUDA tensors the memory-bound tails of the up-sampling
+blocks (leaky-relu + residual + pixel shuffle + blur; bilinear x2 + blur) run as single library kernels each way
+(ops.UpsampleTailFunction / ops.RgbUpsampleFunction, csrc/hn_render2d.cu) - `FUSED_TAILS = False` or CPU tensors
+take the plain PyTorch statement, which is also what the fused kernels are tested against.  The 3x3 binomial blur
+restates kornia.filters.filter2d(normalized=True, border 'reflect') with a depthwise convolution."""
 from math import log2
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+FUSED_TAILS = True      # module-level switch (tests compare both paths)
 
 
 class Blur(nn.Module):
@@ -20,6 +25,17 @@ class Blur(nn.Module):
         k = (k / k.abs().sum()).to(x.dtype)
         c = x.shape[1]
         return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), k.expand(c, 1, 3, 3), groups=c)
+
+    def taps(self):
+        """The three taps on the host (cached per buffer version: reading them is a device sync)."""
+        key = (self.f.data_ptr(), self.f._version)
+        if getattr(self, "_taps_key", None) != key:
+            self._taps_val, self._taps_key = tuple(float(v) for v in self.f.detach().cpu()), key
+        return self._taps_val
+
+
+def _fused(x):
+    return FUSED_TAILS and x.is_cuda and x.dtype == torch.float32
 
 
 class PixelShuffleUpsample(nn.Module):
@@ -34,6 +50,9 @@ class PixelShuffleUpsample(nn.Module):
 
     def forward(self, x):
         h = F.leaky_relu(self.layer_1(x), 0.2)
+        if _fused(x):
+            from . import ops
+            return ops.UpsampleTailFunction.apply(self.layer_2(h), x, self.blur_layer.taps())
         h = F.leaky_relu(self.layer_2(h), 0.2)
         h = F.pixel_shuffle(h + x.repeat(1, 4, 1, 1), 2)
         return self.blur_layer(h)
@@ -63,12 +82,18 @@ class NeuralRenderer(nn.Module):
     def get_bg_featmap(self):
         return self.bg_featmap
 
+    def _rgb_up(self, rgb):
+        if _fused(rgb):
+            from . import ops
+            return ops.RgbUpsampleFunction.apply(rgb, self.rgb_upsample[1].taps())
+        return self.rgb_upsample(rgb)
+
     def forward(self, x):
-        rgb = self.rgb_upsample(self.feat_2_rgb_list[0](x))
+        rgb = self._rgb_up(self.feat_2_rgb_list[0](x))
         net = x
         for i in range(self.n_blocks):
             net = F.leaky_relu(self.feat_layers[i](self.feat_upsample_list[i](net)), 0.2)
             rgb = rgb + self.feat_2_rgb_list[i + 1](net)
             if i < self.n_blocks - 1:
-                rgb = self.rgb_upsample(rgb)
+                rgb = self._rgb_up(rgb)
         return torch.sigmoid(rgb) if self.final_actvn else rgb

@@ -572,6 +572,65 @@ class RenderFunctionPrecise(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------------
+# consumer side (first pieces): fused tails of NeuralRenderer's up-sampling blocks
+# ---------------------------------------------------------------------------------------------------
+def _taps(f3):
+    return (C.c_float * 3)(*[float(v) for v in f3])
+
+
+class UpsampleTailFunction(torch.autograd.Function):
+    """(z2 [B,4C,H,W], x [B,C,H,W], taps) -> blur(pixel_shuffle(leaky_relu(z2, 0.2) + repeat(x, 4), 2)) [B,C,2H,2W]
+    (NetWorks/PixelShuffleUpsample.py:36-45) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, z2, x, f3):
+        lib = L.load()
+        z2, x = _dev_f32(z2, "z2"), _dev_f32(x, "x")
+        B, C4, H, W = z2.shape
+        if C4 != 4 * x.shape[1] or x.shape[0] != B or tuple(x.shape[2:]) != (H, W):
+            raise ValueError("upsample tail: z2 must be [B,4C,H,W] and x [B,C,H,W]")
+        y = torch.empty(B, C4 // 4, 2 * H, 2 * W, device=z2.device)
+        _call("hn_upsample_tail_fwd", lib.hn_upsample_tail_fwd, _ptr(z2), _ptr(x), _taps(f3), _ptr(y), B, C4 // 4, H, W, _stream())
+        ctx.save_for_backward(z2)
+        ctx.f3 = tuple(f3)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        (z2,) = ctx.saved_tensors
+        B, C4, H, W = z2.shape
+        dy = dy.contiguous().float()
+        dz2 = torch.empty_like(z2) if ctx.needs_input_grad[0] else None
+        dx = torch.empty(B, C4 // 4, H, W, device=z2.device) if ctx.needs_input_grad[1] else None
+        _call("hn_upsample_tail_bwd", lib.hn_upsample_tail_bwd, _ptr(dy), _ptr(z2), _taps(ctx.f3), _ptr(dz2), _ptr(dx), B, C4 // 4, H, W, _stream())
+        return dz2, dx, None
+
+
+class RgbUpsampleFunction(torch.autograd.Function):
+    """x [B,K,H,W] -> blur(bilinear x2, align_corners=False) [B,K,2H,2W] (NetWorks/neural_renderer.py:47-50)."""
+
+    @staticmethod
+    def forward(ctx, x, f3):
+        lib = L.load()
+        x = _dev_f32(x, "rgb")
+        B, K, H, W = x.shape
+        y = torch.empty(B, K, 2 * H, 2 * W, device=x.device)
+        _call("hn_rgb_upsample_fwd", lib.hn_rgb_upsample_fwd, _ptr(x), _taps(f3), _ptr(y), B * K, H, W, _stream())
+        ctx.shape, ctx.f3 = (B, K, H, W), tuple(f3)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        B, K, H, W = ctx.shape
+        dy = dy.contiguous().float()
+        dx = torch.zeros(B, K, H, W, device=dy.device)
+        _call("hn_rgb_upsample_bwd", lib.hn_rgb_upsample_bwd, _ptr(dy), _taps(ctx.f3), _ptr(dx), B * K, H, W, _stream())
+        return dx, None
+
+
+# ---------------------------------------------------------------------------------------------------
 # debugging / test helpers: decode operand images (csrc/hn_tc.cuh layout) back to dense matrices
 # ---------------------------------------------------------------------------------------------------
 def _image_index(device):

@@ -1,0 +1,81 @@
+"""GPU tests of the consumer-side kernels (first pieces; csrc/hn_render2d.cu): the fused tails
+of NeuralRenderer's up-sampling blocks against the plain PyTorch statement of the reference modules
+(NetWorks/PixelShuffleUpsample.py:36-45, NetWorks/neural_renderer.py:47-50,72-91), values and every gradient."""
+import importlib
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _nr(hn):
+    return importlib.import_module(hn.__name__ + ".neural_renderer")
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 8, 8), (1, 64, 5, 7), (3, 256, 2, 2), (1, 32, 64, 64)])
+def test_upsample_tail_matches_pytorch(hn, B, C, H, W):
+    nr = _nr(hn)
+    torch.manual_seed(B * 1000 + C + H)
+    blk = nr.PixelShuffleUpsample(C).to(DEV)
+    x = torch.randn(B, C, H, W, device=DEV)
+    gy = torch.randn(B, C, 2 * H, 2 * W, device=DEV)
+    res = []
+    for fused in (False, True):
+        nr.FUSED_TAILS = fused
+        blk.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        y = blk(xi)
+        (y * gy).sum().backward()
+        res.append((y.detach(), xi.grad, [p.grad.clone() for p in blk.parameters()]))
+    nr.FUSED_TAILS = True
+    (y0, gx0, gp0), (y1, gx1, gp1) = res
+    assert (y0 - y1).abs().max() <= 1e-5 * (1 + y0.abs().max())
+    assert (gx0 - gx1).abs().max() <= 1e-4 * (1 + gx0.abs().max())
+    for a, b in zip(gp0, gp1):
+        assert (a - b).abs().max() <= 2e-4 * (1 + a.abs().max())
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 8, 8), (1, 5, 9), (2, 2, 2), (1, 128, 128)])
+def test_rgb_upsample_matches_pytorch(hn, B, H, W):
+    nr = _nr(hn)
+    torch.manual_seed(B + H)
+    net = nr.NeuralRenderer(featmap_size=8, img_size=32).to(DEV)
+    x = torch.randn(B, 3, H, W, device=DEV)
+    gy = torch.randn(B, 3, 2 * H, 2 * W, device=DEV)
+    out = []
+    for fused in (False, True):
+        nr.FUSED_TAILS = fused
+        xi = x.clone().requires_grad_(True)
+        y = net._rgb_up(xi)
+        (y * gy).sum().backward()
+        out.append((y.detach(), xi.grad))
+    nr.FUSED_TAILS = True
+    assert (out[0][0] - out[1][0]).abs().max() <= 1e-5 * (1 + out[0][0].abs().max())
+    assert (out[0][1] - out[1][1]).abs().max() <= 1e-4 * (1 + out[0][1].abs().max())
+
+
+@pytest.mark.parametrize("fs,S", [(8, 32), (16, 128), (32, 512)])
+def test_neural_renderer_fused_vs_plain(hn, fs, S):
+    """The whole consumer, fused tails against the plain modules: image and every gradient (input feature map, all parameters)."""
+    nr = _nr(hn)
+    torch.manual_seed(fs)
+    net = nr.NeuralRenderer(featmap_size=fs, img_size=S).to(DEV)
+    x = torch.randn(2, 256, fs, fs, device=DEV)
+    tgt = torch.rand(2, 3, S, S, device=DEV)
+    res = []
+    for fused in (False, True):
+        nr.FUSED_TAILS = fused
+        net.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        img = net(xi)
+        ((img - tgt) ** 2).mean().backward()
+        res.append((img.detach(), xi.grad, {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+    nr.FUSED_TAILS = True
+    (i0, g0, p0), (i1, g1, p1) = res
+    assert (i0 - i1).abs().max() <= 2e-5
+    assert (g0 - g1).abs().max() <= 1e-3 * g0.abs().max()
+    assert set(p0) == set(p1)
+    for k in p0:
+        assert (p0[k] - p1[k]).abs().max() <= 2e-3 * (p0[k].abs().max() + 1e-12), k
