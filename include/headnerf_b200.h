@@ -299,7 +299,8 @@ int hn_mlp_bwd_data_precise(const hn_mlp_bwd_data_precise_t* a, void* stream);
  * blocks as single kernels, NCHW fp32 like the reference modules; the 1x1 convolutions around them stay library GEMMs.
  * `f3_host` = the three taps of the blur buffer (`blur_layer.f` / `rgb_upsample.1.f`, normally [1,2,1]) on the HOST.
  *   hn_upsample_tail_*  : y = blur(pixel_shuffle(leaky_relu(z2, 0.2) + repeat(x, 4), 2))    NetWorks/PixelShuffleUpsample.py:36-45
- *                         z2 [B,4C,H,W] (layer_2 pre-activation), x [B,C,H,W], y / dy [B,C,2H,2W]; dz2 / dx may be NULL
+ *                         z2 [B,4C,H,W] (layer_2 pre-activation), x [B,C,H,W], y / dy [B,C,2H,2W]; dz2 / dx may be NULL;
+ *                         dx is accumulated (+=, caller zero-initialises)
  *   hn_rgb_upsample_*   : y = blur(bilinear x2, align_corners=False)                         NetWorks/neural_renderer.py:47-50
  *                         x [planes,H,W], y / dy [planes,2H,2W]; dx is accumulated (+=, caller zero-initialises)            */
 int hn_upsample_tail_fwd(const float* z2, const float* x, const float* f3_host, float* y, int B, int C, int H, int W, void* stream);

@@ -23,20 +23,37 @@ __device__ __forceinline__ float shuffled(const float* __restrict__ z2, const fl
     return lrelu(__ldg(z2 + ((size_t)b * 4 * C + k) * H * W + pix), slope) + __ldg(x + ((size_t)b * C + (k % C)) * H * W + pix);
 }
 
+// Block = one (item, channel) plane x one tile of 32 x 32 output pixels (16 x 16 input pixels).  The shuffled tensor
+// s = pixel_shuffle(leaky_relu(z2) + repeat(x, 4)) of the tile plus a one-pixel halo (reflected at the image border) is
+// built ONCE in shared memory - 2.3 global loads per output instead of 18 - and the 3 x 3 filter runs from there.
+constexpr int kT = 32;                                            // output tile edge
 __global__ void __launch_bounds__(256) upsample_tail_fwd_kernel(const float* __restrict__ z2, const float* __restrict__ x, Taps3 f,
                                                                 float* __restrict__ y, int B, int C, int H, int W, float slope) {
+    __shared__ float s[kT + 2][kT + 3];
     const int H2 = 2 * H, W2 = 2 * W;
-    const size_t n = (size_t)B * C * H2 * W2;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const int X = (int)(t % W2), Y = (int)((t / W2) % H2), c = (int)((t / ((size_t)W2 * H2)) % C), b = (int)(t / ((size_t)W2 * H2 * C));
+    const int tiles_x = (W2 + kT - 1) / kT;
+    const int X0 = (blockIdx.x % tiles_x) * kT, Y0 = (blockIdx.x / tiles_x) * kT;
+    const int c = blockIdx.y, b = blockIdx.z;
+    for (int e = threadIdx.x; e < (kT + 2) * (kT + 2); e += 256) {
+        const int sy = e / (kT + 2), sx = e % (kT + 2);
+        const int Y = Y0 - 1 + sy, X = X0 - 1 + sx;
+        float v = 0.f;
+        if (Y <= H2 && X <= W2) v = shuffled(z2, x, b, c, reflect_idx(Y, H2), reflect_idx(X, W2), C, H, W, slope);   // (<=: row n - 1 needs the reflected row n)
+        s[sy][sx] = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;
+    float* plane = y + ((size_t)b * C + c) * H2 * W2;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ty = ty0 + 8 * r, Y = Y0 + ty, X = X0 + tx;
+        if (Y >= H2 || X >= W2) continue;
         float acc = 0.f;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const int yy = reflect_idx(Y + a - 1, H2);
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) acc = fmaf(f.w[a] * f.w[e], shuffled(z2, x, b, c, yy, reflect_idx(X + e - 1, W2), C, H, W, slope), acc);
-        }
-        y[t] = acc;
+            for (int e = 0; e < 3; ++e) acc = fmaf(f.w[a] * f.w[e], s[ty + a][tx + e], acc);
+        plane[(size_t)Y * W2 + X] = acc;
     }
 }
 
@@ -59,23 +76,52 @@ __device__ __forceinline__ float blur_adjoint_at(const float* __restrict__ dy_pl
     return acc;
 }
 
-// one thread per element (b, m, i, j) of x: the four shuffled positions that received x[m] (k = m, m+C, m+2C, m+3C)
+// Backward: block = one (item, channel) plane x 64 x 16 output pixels (32 x 8 input pixels, one per thread, a full warp along
+// the row).  The dy tile (+ halo, zero outside the image) goes to shared memory.  The adjoint of the reflect-padded filter is
+// again a 3-tap filter whose outer weights pick up the reflected tap next to the border (position 1 also receives what row -1
+// read, position n-2 what row n read), so ds needs no index lists: 9 shared-memory taps per output position.
+// dz2 = ds * leaky_relu'(z2) for the pixel's four sub-channels; ds is added to the x channel it came from (x[m] feeds the four
+// shuffled channels m, m+C, m+2C, m+3C: atomics, dx zero-initialised).
+constexpr int kBX = 64, kBY = 16;
+__device__ __forceinline__ void adjoint_weights(int Y, int n, const Taps3& f, float* cm, float* c0, float* cp) {
+    *cm = f.w[2] + (Y == 1 ? f.w[0] : 0.f);          // coefficient of dy[Y - 1]
+    *c0 = f.w[1];
+    *cp = f.w[0] + (Y == n - 2 ? f.w[2] : 0.f);      // coefficient of dy[Y + 1]
+}
 __global__ void __launch_bounds__(256) upsample_tail_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z2, Taps3 f,
                                                                 float* __restrict__ dz2, float* __restrict__ dx, int B, int C, int H, int W, float slope) {
+    __shared__ float g[kBY + 2][kBX + 3];
     const int H2 = 2 * H, W2 = 2 * W;
-    const size_t n = (size_t)B * C * H * W;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(t % W), i = (int)((t / W) % H), m = (int)((t / ((size_t)W * H)) % C), b = (int)(t / ((size_t)W * H * C));
-        float gx = 0.f;
+    const int tiles_x = (W2 + kBX - 1) / kBX;
+    const int X0 = (blockIdx.x % tiles_x) * kBX, Y0 = (blockIdx.x / tiles_x) * kBY;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const float* plane = dy + ((size_t)b * C + c) * H2 * W2;
+    for (int e = threadIdx.x; e < (kBY + 2) * (kBX + 2); e += 256) {
+        const int sy = e / (kBX + 2), sx = e % (kBX + 2);
+        const int Y = Y0 - 1 + sy, X = X0 - 1 + sx;
+        g[sy][sx] = (Y >= 0 && Y < H2 && X >= 0 && X < W2) ? __ldg(plane + (size_t)Y * W2 + X) : 0.f;
+    }
+    __syncthreads();
+    const int lj = threadIdx.x & 31, li = threadIdx.x >> 5;
+    const int j = (X0 >> 1) + lj, i = (Y0 >> 1) + li;
+    if (i >= H || j >= W) return;
+    const size_t pix = (size_t)i * W + j;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int k = m + r * C, c = k >> 2;
-            const float ds = blur_adjoint_at(dy + ((size_t)b * C + c) * H2 * W2, 2 * i + ((k >> 1) & 1), 2 * j + (k & 1), H2, W2, f);
-            const size_t zi = (((size_t)b * 4 * C + k) * H + i) * W + j;
-            if (dz2) dz2[zi] = __ldg(z2 + zi) > 0.f ? ds : ds * slope;
-            gx += ds;
+    for (int q = 0; q < 4; ++q) {
+        const int ly = 2 * li + (q >> 1), lx = 2 * lj + (q & 1);     // position inside the tile; shared-memory index = +1
+        float ym, y0, yp, xm, x0, xp;
+        adjoint_weights(Y0 + ly, H2, f, &ym, &y0, &yp);
+        adjoint_weights(X0 + lx, W2, f, &xm, &x0, &xp);
+        const float r0 = xm * g[ly][lx] + x0 * g[ly][lx + 1] + xp * g[ly][lx + 2];
+        const float r1 = xm * g[ly + 1][lx] + x0 * g[ly + 1][lx + 1] + xp * g[ly + 1][lx + 2];
+        const float r2 = xm * g[ly + 2][lx] + x0 * g[ly + 2][lx + 1] + xp * g[ly + 2][lx + 2];
+        const float ds = ym * r0 + y0 * r1 + yp * r2;
+        const int k = 4 * c + q;
+        if (dz2) {
+            const size_t zi = ((size_t)b * 4 * C + k) * H * W + pix;
+            dz2[zi] = __ldg(z2 + zi) > 0.f ? ds : ds * slope;
         }
-        if (dx) dx[t] = gx;
+        if (dx) atomicAdd(dx + ((size_t)b * C + (k % C)) * H * W + pix, ds);
     }
 }
 
@@ -148,14 +194,18 @@ extern "C" int hn_upsample_tail_fwd(const float* z2, const float* x, const float
     using namespace hn;
     Taps3 t;
     if (!z2 || !x || !y || !f3_host || B <= 0 || C <= 0 || H < 2 || W < 2 || !taps_from(f3_host, &t)) return set_error(HN_E_BADARG, "hn_upsample_tail_fwd: bad argument");
-    upsample_tail_fwd_kernel<<<grid_for((size_t)B * C * 4 * H * W), 256, 0, (cudaStream_t)stream>>>(z2, x, t, y, B, C, H, W, 0.2f);
+    if (C > 65535 || B > 65535) return set_error(HN_E_UNSUPPORTED, "hn_upsample_tail_fwd: more than 65535 channels or items");
+    const dim3 grid((unsigned)(((2 * W + kT - 1) / kT) * ((2 * H + kT - 1) / kT)), (unsigned)C, (unsigned)B);
+    upsample_tail_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z2, x, t, y, B, C, H, W, 0.2f);
     return check_launch("hn_upsample_tail_fwd");
 }
 extern "C" int hn_upsample_tail_bwd(const float* dy, const float* z2, const float* f3_host, float* dz2, float* dx, int B, int C, int H, int W, void* stream) {
     using namespace hn;
     Taps3 t;
     if (!dy || !z2 || !f3_host || B <= 0 || C <= 0 || H < 2 || W < 2 || !taps_from(f3_host, &t)) return set_error(HN_E_BADARG, "hn_upsample_tail_bwd: bad argument");
-    upsample_tail_bwd_kernel<<<grid_for((size_t)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
+    if (C > 65535 || B > 65535) return set_error(HN_E_UNSUPPORTED, "hn_upsample_tail_bwd: more than 65535 channels or items");
+    const dim3 grid((unsigned)(((2 * W + kBX - 1) / kBX) * ((2 * H + kBY - 1) / kBY)), (unsigned)C, (unsigned)B);
+    upsample_tail_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
     return check_launch("hn_upsample_tail_bwd");
 }
 extern "C" int hn_rgb_upsample_fwd(const float* x, const float* f3_host, float* y, int planes, int H, int W, void* stream) {

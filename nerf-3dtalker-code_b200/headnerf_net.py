@@ -217,9 +217,15 @@ class HeadNeRFNet(nn.Module):
         fg_feat = Fm.permute(0, 2, 1).reshape(batch_size, C, fs, fs)
         bg_alpha = bg.view(batch_size, 1, fs, fs)
         bg_featmap = self.neural_render.get_bg_featmap()
-        bg_img = self._bg_image(bg_featmap)
         merge_featmap = fg_feat + bg_alpha * bg_featmap
-        merge_img = self.neural_render(merge_featmap)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.neural_render.parameters()):
+            # the two renderer calls of the reference (HeadNeRFNet.py:109,113) as ONE pass over B + 1 feature maps: every
+            # operator of the renderer acts per item, so the images are the same and the launch count halves
+            imgs = self.neural_render(torch.cat([merge_featmap, bg_featmap], dim=0))
+            merge_img, bg_img = imgs[:batch_size], imgs[batch_size:]
+        else:
+            bg_img = self._bg_image(bg_featmap)
+            merge_img = self.neural_render(merge_featmap)
         return {"coarse_dict": {"merge_img": merge_img, "bg_img": bg_img}}
 
     def _bg_image(self, bg_featmap):

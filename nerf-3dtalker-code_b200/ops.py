@@ -602,7 +602,7 @@ class UpsampleTailFunction(torch.autograd.Function):
         B, C4, H, W = z2.shape
         dy = dy.contiguous().float()
         dz2 = torch.empty_like(z2) if ctx.needs_input_grad[0] else None
-        dx = torch.empty(B, C4 // 4, H, W, device=z2.device) if ctx.needs_input_grad[1] else None
+        dx = torch.zeros(B, C4 // 4, H, W, device=z2.device) if ctx.needs_input_grad[1] else None      # accumulated with atomics
         _call("hn_upsample_tail_bwd", lib.hn_upsample_tail_bwd, _ptr(dy), _ptr(z2), _taps(ctx.f3), _ptr(dz2), _ptr(dx), B, C4 // 4, H, W, _stream())
         return dz2, dx, None
 
