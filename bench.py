@@ -297,7 +297,7 @@ def run_ours(args):
         out["high_precision"] = high
     if world == 1:
         out["cpu_baseline"] = cpu_baseline(sample_rays=1024, repeats=2)
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
 
 
 def _reference_pass(O, opt, sd, inp, n_rays_sample):
@@ -364,10 +364,19 @@ def run_reference(args):
            "cpu_baseline": {"value": round(value, 1), "unit": "ray*samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 1), "unit": "ray*samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
+
+
+RESULT_OUT = sys.stdout
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON result): file descriptor 1 is pointed at stderr for the whole run, so that
+    # library chatter (NCCL's version banner, torchrun notices, ...) cannot end up in front of it
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
