@@ -127,7 +127,7 @@ __device__ __forceinline__ void produce_pe_row(const hn_camera_t cam, float* del
     const float p[3] = {q.px, q.py, q.pz};
     float v[64];
     v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[63] = 0.f;
-#ifdef HN_EXP_PE0                                                   // diagnostic build: no trigonometry (timing only)
+#ifdef HN_DIAG_NO_PE_TRIG                                            // diagnostic build (timing only): no trigonometry
 #pragma unroll
     for (int k = 0; k < 60; ++k) v[3 + k] = p[k % 3];
 #else
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_chain_kernel(const ChainAr
                             for (int i = 0; i < 16; ++i) pk[i] = pack_sat(y[2 * i], y[2 * i + 1]);
                             return;
                         }
-#ifdef HN_EXP_X4
+#ifdef HN_DIAG_NO_EPILOGUE_MATH                                     // diagnostic build (timing only): measured 0.2 ms of the forward
                         for (int i = 0; i < 16; ++i) pk[i] = v[i] ^ v[i + 16];
                         return;
 #endif
@@ -499,11 +499,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_chain_kernel(const ChainAr
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float4 bb;
-#ifdef HN_EXP_X2
-                            bb = make_float4(0.5f, 0.25f, 0.125f, 1.f);
-#else
                             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(bp + pc * 128 + i * 16));
-#endif
                             y[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
                             y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
                             y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
@@ -555,10 +551,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_chain_kernel(const ChainAr
                     } else {
                         // every warp has read its part of this accumulator (and, after a held chunk, of the previous one): stores
                         // into in-place or neighbouring columns are safe now
-#ifndef HN_EXP_X1
                         wait_spin(&sh.loaded[n & 7], (n >> 3) & 1, &sh.abort, a.status, 330);
                         tc_fence_after_sync();
-#endif
                         if (holding) {
                             // chunk 0's output first, signalled at once: the next layer's first K blocks are what the MMA
                             // issuer will ask for as soon as chunk 2 is issued
