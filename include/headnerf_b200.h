@@ -308,6 +308,14 @@ int hn_upsample_tail_bwd(const float* dy, const float* z2, const float* f3_host,
 int hn_rgb_upsample_fwd(const float* x, const float* f3_host, float* y, int planes, int H, int W, void* stream);
 int hn_rgb_upsample_bwd(const float* dy, const float* f3_host, float* dx_zeroed, int planes, int H, int W, void* stream);
 
+/* Merge (NetWorks/HeadNeRFNet.py:103-113): merge[b,c,r] = F[b,r,c] + bg_alpha[b,r] * bg_featmap[c,r], ray r <-> pixel (r / fs, r % fs).
+ * F [B,n_rays,C] and bg_alpha [B,n_rays] are the outputs of hn_composite_fwd; merge / g_merge are channel-major [B,C,n_rays]
+ * (= [B,C,fs,fs]); bg_featmap [C,n_rays].  Backward: gF written, g_bg and g_bgfeat accumulated (+=, caller zero-initialises);
+ * any of the three may be NULL.                                                                                          */
+int hn_merge_fwd(const float* F, const float* bg_alpha, const float* bg_featmap, float* merge, int B, int n_rays, int C, void* stream);
+int hn_merge_bwd(const float* g_merge, const float* bg_alpha, const float* bg_featmap, float* gF, float* g_bg_zeroed, float* g_bgfeat_zeroed,
+                 int B, int n_rays, int C, void* stream);
+
 /* Bytes of the saved-for-backward buffers for M samples. */
 size_t hn_act_bytes(int64_t M);
 size_t hn_grads_bytes(int64_t M);

@@ -82,7 +82,7 @@ EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pac
            "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes",
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
            "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
-           "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd"]
+           "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd"]
 
 _lib = None
 
@@ -125,6 +125,8 @@ def load():
     lib.hn_upsample_tail_bwd.argtypes = [_p, _p, f3, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]
     lib.hn_rgb_upsample_fwd.argtypes = [_p, f3, _p, C.c_int, C.c_int, C.c_int, _p]
     lib.hn_rgb_upsample_bwd.argtypes = [_p, f3, _p, C.c_int, C.c_int, C.c_int, _p]
+    lib.hn_merge_fwd.argtypes = [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p]
+    lib.hn_merge_bwd.argtypes = [_p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p]
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
     lib.hn_mlp_fwd.argtypes = [C.POINTER(MlpFwd), _p]
     lib.hn_composite_fwd.argtypes = [C.POINTER(CompositeFwd), _p]
@@ -134,7 +136,7 @@ def load():
     for name in ("hn_pack_weights", "hn_sample_rays", "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd",
                  "hn_mlp_bwd_data", "hn_mlp_bwd_weights", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
                  "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
-                 "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd"):
+                 "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd"):
         getattr(lib, name).restype = C.c_int
     if lib.hn_abi_version() != 1:
         raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")

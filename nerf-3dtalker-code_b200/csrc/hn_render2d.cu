@@ -222,3 +222,83 @@ extern "C" int hn_rgb_upsample_bwd(const float* dy, const float* f3_host, float*
     rgb_upsample_bwd_kernel<<<grid_for((size_t)planes * 4 * H * W), 256, 0, (cudaStream_t)stream>>>(dy, t, dx_zeroed, planes, H, W);
     return check_launch("hn_rgb_upsample_bwd");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Merge (NetWorks/HeadNeRFNet.py:103-113): the composited ray-major features F [B, N_r, C] and bg_alpha [B, N_r]
+// become the channel-major map the renderer consumes, merge[b, c, r] = F[b, r, c] + bg_alpha[b, r] * bg_featmap[c, r]
+// (ray r <-> pixel (r / fs, r % fs)): one transposing kernel instead of permute-copy + multiply + add, and its adjoint.
+namespace hn {
+
+__global__ void __launch_bounds__(256) merge_fwd_kernel(const float* __restrict__ F, const float* __restrict__ bg, const float* __restrict__ bgfeat,
+                                                        float* __restrict__ out, int n_rays, int C) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + tx;
+        tile[ty + 8 * k][tx] = (r < n_rays && c < C) ? __ldg(F + ((size_t)b * n_rays + r) * C + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;
+        if (r < n_rays && c < C)
+            out[((size_t)b * C + c) * n_rays + r] = fmaf(__ldg(bg + (size_t)b * n_rays + r), __ldg(bgfeat + (size_t)c * n_rays + r), tile[tx][ty + 8 * k]);
+    }
+}
+
+// g [B, C, N_r] -> gF [B, N_r, C] (transpose), g_bg[b, r] += sum_c g * bg_featmap, g_bgfeat[c, r] += sum_b g * bg_alpha
+__global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict__ g, const float* __restrict__ bg, const float* __restrict__ bgfeat,
+                                                        float* __restrict__ gF, float* __restrict__ g_bg, float* __restrict__ g_bgfeat, int n_rays, int C) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    float part = 0.f;                                             // this thread's share of sum_c g * bg_featmap for ray r0 + tx
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, r = r0 + tx;
+        float v = 0.f;
+        if (r < n_rays && c < C) {
+            v = __ldg(g + ((size_t)b * C + c) * n_rays + r);
+            part = fmaf(v, __ldg(bgfeat + (size_t)c * n_rays + r), part);
+            if (g_bgfeat) atomicAdd(g_bgfeat + (size_t)c * n_rays + r, v * __ldg(bg + (size_t)b * n_rays + r));
+        }
+        tile[ty + 8 * k][tx] = v;                                 // [c][r]
+    }
+    __syncthreads();
+    if (gF) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + ty + 8 * k, c = c0 + tx;
+            if (r < n_rays && c < C) gF[((size_t)b * n_rays + r) * C + c] = tile[tx][ty + 8 * k];
+        }
+    }
+    if (g_bg) {
+        __syncthreads();
+        tile[ty][tx] = part;                                      // 8 partial sums per ray
+        __syncthreads();
+        if (ty == 0 && r0 + tx < n_rays) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += tile[k][tx];
+            atomicAdd(g_bg + (size_t)b * n_rays + r0 + tx, s);
+        }
+    }
+}
+
+}  // namespace hn
+
+extern "C" int hn_merge_fwd(const float* F, const float* bg_alpha, const float* bg_featmap, float* merge, int B, int n_rays, int C, void* stream) {
+    using namespace hn;
+    if (!F || !bg_alpha || !bg_featmap || !merge || B <= 0 || n_rays <= 0 || C <= 0 || B > 65535) return set_error(HN_E_BADARG, "hn_merge_fwd: bad argument");
+    merge_fwd_kernel<<<dim3((n_rays + 31) / 32, (C + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(F, bg_alpha, bg_featmap, merge, n_rays, C);
+    return check_launch("hn_merge_fwd");
+}
+extern "C" int hn_merge_bwd(const float* g_merge, const float* bg_alpha, const float* bg_featmap, float* gF, float* g_bg_zeroed, float* g_bgfeat_zeroed,
+                            int B, int n_rays, int C, void* stream) {
+    using namespace hn;
+    if (!g_merge || !bg_alpha || !bg_featmap || B <= 0 || n_rays <= 0 || C <= 0 || B > 65535) return set_error(HN_E_BADARG, "hn_merge_bwd: bad argument");
+    merge_bwd_kernel<<<dim3((n_rays + 31) / 32, (C + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(g_merge, bg_alpha, bg_featmap, gF, g_bg_zeroed, g_bgfeat_zeroed, n_rays, C);
+    return check_launch("hn_merge_bwd");
+}

@@ -214,10 +214,8 @@ class HeadNeRFNet(nn.Module):
         assert n_r == fs * fs, "HeadNeRFNet.forward renders a full featmap (HeadNeRFNet.py:103-106); use render_rays otherwise"
         Fm, bg = self.render_rays("train" if for_train else "test", batch_xy, audiostyle, shape_code, appea_code,
                                   batch_Rmats, batch_Tvecs, batch_inv_inmats)
-        fg_feat = Fm.permute(0, 2, 1).reshape(batch_size, C, fs, fs)
-        bg_alpha = bg.view(batch_size, 1, fs, fs)
         bg_featmap = self.neural_render.get_bg_featmap()
-        merge_featmap = fg_feat + bg_alpha * bg_featmap
+        merge_featmap = ops.MergeFunction.apply(Fm, bg, bg_featmap)       # F^T + bg_alpha * bg_featmap (HeadNeRFNet.py:103-113)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.neural_render.parameters()):
             # the two renderer calls of the reference (HeadNeRFNet.py:109,113) as ONE pass over B + 1 feature maps: every
             # operator of the renderer acts per item, so the images are the same and the launch count halves

@@ -572,6 +572,42 @@ class RenderFunctionPrecise(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------------
+# a7 merge (NetWorks/HeadNeRFNet.py:103-113)
+# ---------------------------------------------------------------------------------------------------
+class MergeFunction(torch.autograd.Function):
+    """(F [B,N_r,C] ray-major, bg_alpha [B,N_r], bg_featmap [1,C,fs,fs]) -> merge featmap [B,C,fs,fs] = F^T + bg_alpha * bg_featmap
+    (hn_merge_fwd / hn_merge_bwd: one transposing kernel each way)."""
+
+    @staticmethod
+    def forward(ctx, Fm, bg, bgfeat):
+        lib = L.load()
+        Fm, bg, bgfeat = _dev_f32(Fm, "F"), _dev_f32(bg, "bg_alpha"), _dev_f32(bgfeat, "bg_featmap")
+        B, n_r, Cc = Fm.shape
+        fs = bgfeat.shape[-1]
+        if tuple(bg.shape) != (B, n_r) or tuple(bgfeat.shape) != (1, Cc, fs, fs) or fs * fs != n_r:
+            raise ValueError("merge: F [B,fs*fs,C], bg_alpha [B,fs*fs], bg_featmap [1,C,fs,fs]")
+        out = torch.empty(B, Cc, fs, fs, device=Fm.device)
+        _call("hn_merge_fwd", lib.hn_merge_fwd, _ptr(Fm), _ptr(bg), _ptr(bgfeat), _ptr(out), B, n_r, Cc, _stream())
+        ctx.save_for_backward(bg, bgfeat)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        bg, bgfeat = ctx.saved_tensors
+        B, n_r = bg.shape
+        Cc = bgfeat.shape[1]
+        g = g.contiguous().float()
+        need = ctx.needs_input_grad
+        gF = torch.empty(B, n_r, Cc, device=g.device) if need[0] else None
+        zb = torch.zeros(B * n_r + Cc * n_r, device=g.device) if (need[1] or need[2]) else None
+        g_bg = zb[:B * n_r].view(B, n_r) if need[1] else None
+        g_feat = zb[B * n_r:].view(bgfeat.shape) if need[2] else None
+        _call("hn_merge_bwd", lib.hn_merge_bwd, _ptr(g), _ptr(bg), _ptr(bgfeat), _ptr(gF), _ptr(g_bg), _ptr(g_feat), B, n_r, Cc, _stream())
+        return gF, g_bg, g_feat
+
+
+# ---------------------------------------------------------------------------------------------------
 # consumer side (SURVEY.md section 8f row 1, first pieces): fused tails of NeuralRenderer's up-sampling blocks
 # ---------------------------------------------------------------------------------------------------
 def _taps(f3):

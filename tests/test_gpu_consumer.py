@@ -79,3 +79,24 @@ def test_neural_renderer_fused_vs_plain(hn, fs, S):
     assert set(p0) == set(p1)
     for k in p0:
         assert (p0[k] - p1[k]).abs().max() <= 2e-3 * (p0[k].abs().max() + 1e-12), k
+
+
+@pytest.mark.parametrize("B,fs,C", [(2, 8, 256), (1, 5, 96), (3, 64, 256)])
+def test_merge_kernel_matches_pytorch(hn, B, fs, C):
+    """hn_merge_fwd / hn_merge_bwd against merge = F.permute + bg_alpha * bg_featmap (NetWorks/HeadNeRFNet.py:103-113)."""
+    torch.manual_seed(fs)
+    n_r = fs * fs
+    Fm, bg, feat = torch.randn(B, n_r, C, device=DEV), torch.rand(B, n_r, device=DEV), torch.randn(1, C, fs, fs, device=DEV)
+    gout = torch.randn(B, C, fs, fs, device=DEV)
+    res = []
+    for fused in (False, True):
+        xs = [t.clone().requires_grad_(True) for t in (Fm, bg, feat)]
+        if fused:
+            out = hn.ops.MergeFunction.apply(*xs)
+        else:
+            out = xs[0].permute(0, 2, 1).reshape(B, C, fs, fs) + xs[1].view(B, 1, fs, fs) * xs[2]
+        (out * gout).sum().backward()
+        res.append((out.detach(), [t.grad for t in xs]))
+    assert torch.equal(res[0][0], res[1][0]) or (res[0][0] - res[1][0]).abs().max() <= 1e-6
+    for a, b in zip(res[0][1], res[1][1]):
+        assert (a - b).abs().max() <= 1e-4 * (1 + a.abs().max())
