@@ -316,6 +316,53 @@ int hn_merge_fwd(const float* F, const float* bg_alpha, const float* bg_featmap,
 int hn_merge_bwd(const float* g_merge, const float* bg_alpha, const float* bg_featmap, float* gF, float* g_bg_zeroed, float* g_bgfeat_zeroed,
                  int B, int n_rays, int C, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The whole hot path behind one call per direction (fast kernels): NetWorks/HeadNeRFNet.py:123-160 up to the composited
+ * features, and its autograd.  All buffers caller-owned; "zeroed" = the caller zero-initialises (the kernels accumulate).   */
+typedef struct {
+    hn_camera_t cam;
+    hn_fold_t fold;           /* latent codes, folded weights, bias vectors (fold.B == cam.B)                     */
+    const float* w_density;   /* [384]                                                                            */
+    const void* packed;       /* from hn_pack_weights                                                             */
+    float* bias_eff;          /* [B, HN_BIAS_STRIDE] workspace (kept for backward)                                */
+    float* feat;              /* [M,256] workspace (kept for backward)                                            */
+    float* sigma;             /* [M]                                                                              */
+    float* delta;             /* [M]                                                                              */
+    void* act;                /* hn_act_bytes(M), or NULL when no backward follows                                */
+    uint32_t* masks;          /* hn_mask_bytes(M), or NULL (together with act)                                    */
+    float* F;                 /* [B*n_rays, 256] out                                                              */
+    float* bg_alpha;          /* [B*n_rays] out                                                                   */
+    int* status;              /* zeroed device int[64]                                                            */
+} hn_render_fwd_t;
+
+int hn_render_fwd(const hn_render_fwd_t* a, void* stream);
+
+typedef struct {
+    hn_camera_t cam;
+    hn_fold_t fold;
+    const float* w_density;
+    const void* packed;
+    const float* feat; const float* sigma; const float* delta; const void* act; const uint32_t* masks;   /* from hn_render_fwd */
+    const float* gF;          /* [B*n_rays, 256] upstream gradient                                                 */
+    const float* g_bg;        /* [B*n_rays]                                                                        */
+    float grad_target;        /* target magnitude of the scaled gradients (<= 0: 64)                               */
+    void* dfeat_image;        /* hn_dfeat_image_bytes(M) workspace                                                 */
+    float* dsigma;            /* [M] workspace                                                                     */
+    float* ddelta;            /* [M] workspace, camera gradients only                                              */
+    void* grads;              /* hn_grads_bytes(M) workspace (parameter / code gradients)                          */
+    float* scale;             /* device float workspace                                                            */
+    void* scale_scratch8;     /* 8 zero bytes (see hn_loss_scale)                                                  */
+    float* dbias_eff;         /* [B, HN_BIAS_STRIDE] zeroed workspace                                              */
+    void* items_workspace; size_t items_workspace_bytes;   /* hn_wgrad_workspace_bytes(B)                          */
+    float* g_ray_o; float* g_ray_v; float* g_ray_l;        /* zeroed workspaces, camera gradients only             */
+    float* dw[12]; int ld[12]; int l5_hidden_col;          /* zeroed weight-gradient outputs (NULL entries skipped) */
+    hn_fold_grads_t fold_grads;                            /* code gradients (=), folded columns / biases (+=)      */
+    float* dR; float* dT; float* dKinv;                    /* zeroed [B,3,3] / [B,3] / [B,3,3], or NULL             */
+    int* status;
+} hn_render_bwd_t;
+
+int hn_render_bwd(const hn_render_bwd_t* a, void* stream);
+
 /* Bytes of the saved-for-backward buffers for M samples. */
 size_t hn_act_bytes(int64_t M);
 size_t hn_grads_bytes(int64_t M);

@@ -77,12 +77,26 @@ class FoldGrads(C.Structure):
     _fields_ = [("dshape", _p), ("daudio", _p), ("dappea", _p), ("dw0", _p), ("dw5", _p), ("dwr1", _p), ("dbias", _p * 12)]
 
 
+class RenderFwd(C.Structure):
+    _fields_ = [("cam", Camera), ("fold", Fold), ("w_density", _p), ("packed", _p), ("bias_eff", _p), ("feat", _p), ("sigma", _p),
+                ("delta", _p), ("act", _p), ("masks", _p), ("F", _p), ("bg_alpha", _p), ("status", _p)]
+
+
+class RenderBwd(C.Structure):
+    _fields_ = [("cam", Camera), ("fold", Fold), ("w_density", _p), ("packed", _p), ("feat", _p), ("sigma", _p), ("delta", _p),
+                ("act", _p), ("masks", _p), ("gF", _p), ("g_bg", _p), ("grad_target", C.c_float), ("dfeat_image", _p), ("dsigma", _p),
+                ("ddelta", _p), ("grads", _p), ("scale", _p), ("scale_scratch8", _p), ("dbias_eff", _p), ("items_workspace", _p),
+                ("items_workspace_bytes", C.c_size_t), ("g_ray_o", _p), ("g_ray_v", _p), ("g_ray_l", _p), ("dw", _p * 12),
+                ("ld", C.c_int * 12), ("l5_hidden_col", C.c_int), ("fold_grads", FoldGrads), ("dR", _p), ("dT", _p), ("dKinv", _p),
+                ("status", _p)]
+
+
 EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pack_weights", "hn_sample_rays",
            "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
            "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes",
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
            "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
-           "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd"]
+           "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd"]
 
 _lib = None
 
@@ -126,6 +140,8 @@ def load():
     lib.hn_rgb_upsample_fwd.argtypes = [_p, f3, _p, C.c_int, C.c_int, C.c_int, _p]
     lib.hn_rgb_upsample_bwd.argtypes = [_p, f3, _p, C.c_int, C.c_int, C.c_int, _p]
     lib.hn_merge_fwd.argtypes = [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p]
+    lib.hn_render_fwd.argtypes = [C.POINTER(RenderFwd), _p]
+    lib.hn_render_bwd.argtypes = [C.POINTER(RenderBwd), _p]
     lib.hn_merge_bwd.argtypes = [_p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p]
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
     lib.hn_mlp_fwd.argtypes = [C.POINTER(MlpFwd), _p]
@@ -136,7 +152,7 @@ def load():
     for name in ("hn_pack_weights", "hn_sample_rays", "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd",
                  "hn_mlp_bwd_data", "hn_mlp_bwd_weights", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
                  "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
-                 "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd"):
+                 "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd"):
         getattr(lib, name).restype = C.c_int
     if lib.hn_abi_version() != 1:
         raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")
