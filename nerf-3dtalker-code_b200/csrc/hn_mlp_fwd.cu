@@ -431,7 +431,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_chain_kernel(const ChainAr
                 const uint32_t sb = sidx & 1;                      // staging buffer of this saved chunk
                 if (!BWD && op.kind == EPI_FEAT) {
                     // final features: stage 32 rows x 32 columns per piece in shared memory (swizzled 16-byte chunks), then write
-                    // whole 128-byte row segments (8 lanes each) instead of 32 scattered 16-byte pieces.  Scratch = the staging
+                    // whole 128-byte row segments (8 lanes each) instead of 32 scattered 16-byte pieces (every thread storing its
+                    // own row directly was re-measured on this kernel: 1.86 vs 1.73 ms - these stores sit on the tile-boundary path).  Scratch = the staging
                     // buffer whose last saved chunk is the older one (chunk 29 -> buffer of chunk 27, chunk 30 -> of chunk 28).
                     const uint32_t fb = (sidx + (uint32_t)(e & 1 ? 0 : 1)) & 1;     // e = 29: sidx & 1;  e = 30: (sidx + 1) & 1
                     const uint32_t fidx = sidx + (uint32_t)(e & 1 ? 0 : 1);
