@@ -416,8 +416,10 @@ static bool g_w_ready[64] = {};
 
 // host: enumerate work items.  `cluster` = items for the 3-CTA multicast kernel (three consecutive entries = the three
 // 128-channel chunks of one layer over one sample range); `single` = everything else.
-static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters, int n_pairs, std::vector<WItem>& cluster, std::vector<WItem>& single,
-                        std::vector<WItem>& pairs) {
+// `side` / n_side: single-CTA items for the SMs the resident 3-CTA clusters leave idle (148 - 3 * 45 = 13 on this part): they run on
+// a second stream while the cluster kernel runs, the rest of the single-CTA work (`single`) follows on all SMs.
+static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters, int n_pairs, int n_side, std::vector<WItem>& cluster,
+                        std::vector<WItem>& single, std::vector<WItem>& pairs, std::vector<WItem>& side) {
     const int tiles_per_item = (int)(((int64_t)a.n_rays * a.n_samples) / HN_TILE);
     bool want_w = false;
     for (int i = 0; i < 12; ++i) want_w = want_w || (a.dw[i] != nullptr);
@@ -444,7 +446,7 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     // byte throughput - so a tile costs about the same whatever the layer width; the block count only adds a small slope.
     static const double slope = [] { const char* e = getenv("HN_WGRAD_SLOPE"); return e ? atof(e) : 40.0; }();   // tuning knob (cycles per operand block)
     auto stage_cost = [](int n_x) { return 1000.0 + slope * n_x; };
-    struct Unit { std::vector<WItem> tmpl; int b; double cost; };
+    struct Unit { std::vector<WItem> tmpl; int b; double cost; int t0, t1; };      // tiles [t0, t1) of batch item b
     std::vector<Unit> units_c, units_s;
     int layers_pair = 0;
     auto make_item = [&](const LayerW& L, int j, int b) {
@@ -470,13 +472,13 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
         if (pr) ++layers_pair;
         for (int b = 0; b < a.B; ++b) {
             if (cl) {
-                Unit u; u.b = b;
+                Unit u; u.b = b; u.t0 = 0; u.t1 = tiles_per_item;
                 for (int j = 0; j < 3; ++j) u.tmpl.push_back(make_item(L, j, b));
                 u.cost = stage_cost(u.tmpl[0].n_x);
                 units_c.push_back(u);
             } else {
                 for (int j = pr ? 2 : 0; j * 128 < L.n_out; ++j) {
-                    Unit u; u.b = b;
+                    Unit u; u.b = b; u.t0 = 0; u.t1 = tiles_per_item;
                     u.tmpl.push_back(make_item(L, j, b));
                     u.cost = stage_cost(u.tmpl[0].n_x);
                     units_s.push_back(u);
@@ -487,18 +489,18 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     auto partition = [&](const std::vector<Unit>& units, int workers, int group, std::vector<WItem>& out) {
         if (units.empty() || workers <= 0) return;
         double total = 0;
-        for (const Unit& u : units) total += u.cost * tiles_per_item;
+        for (const Unit& u : units) total += u.cost * (u.t1 - u.t0);
         const double quota = total / workers;
         std::vector<std::vector<WItem>> lists(workers);               // `group` consecutive entries per piece
         int wk = 0;
         double need = quota;
         for (const Unit& u : units) {
-            int t = 0;
-            while (t < tiles_per_item) {
+            int t = u.t0;
+            while (t < u.t1) {
                 int take = (int)(need / u.cost + 0.5);
                 take = take < 1 ? 1 : take;
-                if (take > tiles_per_item - t || wk == workers - 1) take = tiles_per_item - t;
-                if (tiles_per_item - t - take > 0 && (tiles_per_item - t - take) * u.cost < 0.03 * quota) take = tiles_per_item - t;   // no crumbs
+                if (take > u.t1 - t || wk == workers - 1) take = u.t1 - t;
+                if (u.t1 - t - take > 0 && (u.t1 - t - take) * u.cost < 0.03 * quota) take = u.t1 - t;   // no crumbs
                 for (int r = 0; r < group; ++r) {
                     WItem w = u.tmpl[r];
                     w.tile0 = u.b * tiles_per_item + t;
@@ -531,7 +533,25 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
                     out.push_back(j * group + r < lists[w].size() ? lists[w][j * group + r] : WItem{});
     };
     partition(units_c, n_clusters, 3, cluster);
-    partition(units_s, n_sm, 1, single);
+    if (n_side > 0 && !units_c.empty() && !units_s.empty()) {
+        // share of the single-CTA work that n_side SMs finish in about the time the cluster kernel takes (cost ~ stages)
+        double cost_c = 0, cost_s = 0;
+        for (const Unit& u : units_c) cost_c += u.cost * 3 * (u.t1 - u.t0);
+        for (const Unit& u : units_s) cost_s += u.cost * (u.t1 - u.t0);
+        static const double tune = [] { const char* e = getenv("HN_WGRAD_SIDE"); return e ? atof(e) : 0.85; }();
+        double f = tune * (cost_c / (3.0 * n_clusters)) * n_side / cost_s;          // (time of the cluster phase) x n_side / (single work)
+        f = f > 0.9 ? 0.9 : f;
+        std::vector<Unit> first, rest;
+        for (const Unit& u : units_s) {
+            const int cut = u.t0 + (int)((u.t1 - u.t0) * f);
+            if (cut > u.t0) { Unit p = u; p.t1 = cut; first.push_back(p); }
+            if (cut < u.t1) { Unit p = u; p.t0 = cut; rest.push_back(p); }
+        }
+        partition(first, n_side, 1, side);
+        partition(rest, n_sm, 1, single);
+    } else {
+        partition(units_s, n_sm, 1, single);
+    }
     // opt-in CTA-pair items (uniform sample splits)
     if (layers_pair > 0) {
         int sp = (2 * n_pairs + layers_pair * a.B - 1) / (layers_pair * a.B);
@@ -567,6 +587,8 @@ static int launch_wgrad(const WArgs& k, int cl, int grid, cudaStream_t st) {
 
 static int g_w_clusters[64] = {};
 static int g_w_pairs[64] = {};
+static cudaStream_t g_w_side[64] = {};
+static cudaEvent_t g_w_fork[64] = {}, g_w_join[64] = {};
 
 }  // namespace hn
 
@@ -610,6 +632,14 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
                 if (cudaOccupancyMaxActiveClusters(&np, mlp_wgrad_pair_kernel, &cfg) != cudaSuccess) { np = 0; cudaGetLastError(); }
             }
             g_w_pairs[dev] = np;
+            // a second stream (+ two events) per device: the single-CTA items that fill the SMs the clusters leave idle run on it,
+            // forked from and joined back into the caller's stream (HN_WGRAD_SIDE=0 disables it)
+            const char* envs = getenv("HN_WGRAD_SIDE");
+            if (!(envs && atof(envs) == 0.0)) {
+                if (cudaStreamCreateWithFlags(&g_w_side[dev], cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&g_w_fork[dev], cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&g_w_join[dev], cudaEventDisableTiming) != cudaSuccess) { g_w_side[dev] = nullptr; cudaGetLastError(); }
+            }
             g_w_ready[dev] = true;
         }
     }
@@ -617,15 +647,19 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_clusters = dev < 64 ? g_w_clusters[dev] : 0;
     const int n_pairs = dev < 64 ? g_w_pairs[dev] : 0;
-    std::vector<WItem> cluster, single, pairs;
-    build_items(*a, n_sm, n_clusters, n_pairs, cluster, single, pairs);
-    if (cluster.empty() && single.empty() && pairs.empty()) return HN_OK;
-    if ((cluster.size() + single.size() + pairs.size()) * sizeof(WItem) > a->items_workspace_bytes)
+    std::vector<WItem> cluster, single, pairs, side;
+    cudaStream_t side_stream = dev < 64 ? g_w_side[dev] : nullptr;
+    const int n_idle = n_sm - 3 * n_clusters;
+    const int n_side = (side_stream && n_pairs == 0 && n_clusters > 0 && n_idle >= 4) ? n_idle : 0;
+    build_items(*a, n_sm, n_clusters, n_pairs, n_side, cluster, single, pairs, side);
+    if (cluster.empty() && single.empty() && pairs.empty() && side.empty()) return HN_OK;
+    if ((cluster.size() + single.size() + pairs.size() + side.size()) * sizeof(WItem) > a->items_workspace_bytes)
         return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: items workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<WItem> all(cluster);
     all.insert(all.end(), single.begin(), single.end());
     all.insert(all.end(), pairs.begin(), pairs.end());
+    all.insert(all.end(), side.begin(), side.end());
     // the item table is tiny (<100 KiB); pageable -> device copy is stream-ordered and returns after staging
     cudaError_t e = cudaMemcpyAsync(a->items_workspace, all.data(), all.size() * sizeof(WItem), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
@@ -649,10 +683,21 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
         if (pe != cudaSuccess) return set_error((int)pe, cudaGetErrorString(pe));
         if (int rc = check_launch("hn_mlp_bwd_weights (CTA pairs)")) return rc;
     }
+    const bool forked = !side.empty() && !cluster.empty();
+    if (forked && cudaEventRecord(g_w_fork[dev], st) != cudaSuccess) return set_error(HN_E_PROTOCOL, "hn_mlp_bwd_weights: event record failed");
     if (!cluster.empty()) {
         k.items = (const WItem*)a->items_workspace; k.n_items = (int)cluster.size() / 3;
         const int nc = n_clusters;                                  // the balanced schedule has one column per resident cluster
         if (int rc = launch_wgrad(k, 3, 3 * nc, st)) return rc;
+    }
+    if (forked) {
+        // the idle SMs' share, concurrently with the clusters (launched after them: it can only take what they leave free)
+        cudaStreamWaitEvent(side_stream, g_w_fork[dev], 0);
+        WArgs ks = k;
+        ks.items = (const WItem*)a->items_workspace + cluster.size() + single.size() + pairs.size(); ks.n_items = (int)side.size();
+        if (int rc = launch_wgrad(ks, 1, n_side, side_stream)) return rc;
+        cudaEventRecord(g_w_join[dev], side_stream);
+        cudaStreamWaitEvent(st, g_w_join[dev], 0);
     }
     if (!single.empty()) {
         k.items = (const WItem*)a->items_workspace + cluster.size(); k.n_items = (int)single.size();
@@ -665,5 +710,5 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
 extern "C" size_t hn_wgrad_workspace_bytes(int B) {
     // upper bound: 35 (layer, chunk) pairs x B x splits, splits chosen so that items <= 2*SMs + pairs*B
     // upper bound: per list (#workers + #units) pieces, padded to whole rounds: clusters 3 * 3 * (49 + 9 B), single 3 * (160 + 9 B), pairs
-    return (size_t)(160 * (size_t)(B > 0 ? B : 1) + 1600) * sizeof(hn::WItem);
+    return (size_t)(200 * (size_t)(B > 0 ? B : 1) + 2000) * sizeof(hn::WItem);
 }

@@ -419,7 +419,7 @@ class RenderFunction(torch.autograd.Function):
             w.l5_hidden_col = meta["l5_hidden_col"]
             w.dbias, w.status = _ptr(dbias), _ptr(status)
             # with weight gradients the library launches two kernels: 3-CTA clusters for the 384-wide layers, then the rest
-            _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=2 if need_w else 1)
+            _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=3 if need_w else 1)
         if _DEBUG_SYNC:
             check_status(status, "hn_mlp_bwd")
         meta["last_status"] = status
@@ -562,7 +562,7 @@ class RenderFunctionPrecise(torch.autograd.Function):
                 w.ld[i] = wt.numel() // wt.shape[0]
             w.l5_hidden_col = meta["l5_hidden_col"]
             w.dbias, w.status = _ptr(dbias), _ptr(status)
-            _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=2)
+            _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=3)
         if _DEBUG_SYNC:
             check_status(status, "hn_mlp_bwd_precise")
         meta["last_status"] = status
