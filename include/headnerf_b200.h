@@ -8,7 +8,10 @@
  * Conventions
  *  - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
  *  - the caller owns all memory (inputs, outputs, saved-for-backward, workspace); the library never
- *    allocates, never synchronises, and launches on the stream passed as `stream` (a cudaStream_t);
+ *    synchronises and launches on the stream passed as `stream` (a cudaStream_t).  Its only own device
+ *    resources, created once per device on first use and never freed: immutable schedule tables (constant
+ *    memory, plus one < 64 KiB table for hn_pack_weights_precise) and, for hn_mlp_bwd_weights, one
+ *    non-blocking side stream with two events that is forked from and joined back into `stream`;
  *  - every function returns 0 on success, a negative HN_E_* code on a bad argument, or a positive
  *    cudaError_t value; hn_last_error() returns a thread-local human-readable message;
  *  - samples are indexed m = (b*n_rays + r)*n_samples + s; M = B*n_rays*n_samples must be a multiple
