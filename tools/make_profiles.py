@@ -44,6 +44,7 @@ with open(os.path.join(prof, f"{tag}_ncu_full_summary.md"), "w") as f:
     f.write(f"# ncu --set full summary, {title} (bench.py --steps 3 --warmup 3; Reso64 batch 2)\n\n")
     f.write("Source: `ncu --set full --clock-control none --import-source on -k regex:\"mlp_|composite\" -s 12 -c 6` on a B200 (gpurun); the .ncu-rep is not committed.\n")
     f.write("Times under ncu are cold-cache and serialised; the bench's CUDA-event times are the reported ones.\n")
+    f.write("Captured with HN_WGRAD_SIDE=0 (the second-stream split of the weight-gradient pass is meaningless under ncu's serialisation).\n")
     for r in rr[2:]:
         kname = r[h.index("Kernel Name")]
         short = re.sub(r"\(.*", "", kname)
