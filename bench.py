@@ -253,7 +253,7 @@ def run_ours(args):
     # DRAM traffic per launch comes from the committed ncu --set full capture of this workload (profiles/)
     traffic = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r01g_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01h_traffic.json")) as f:
             traffic = {k: v["dram_gbytes_per_launch"] * 1e9 for k, v in json.load(f)["kernels"].items()}
     except Exception:
         pass
@@ -269,14 +269,14 @@ def run_ours(args):
     if dom_bytes is not None and flops[dom] / dom_bytes < ridge:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs_algorithmic"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic.get(dom),
-                    "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01g_traffic.json)", "peak_source": peaks["src"],
+                    "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01h_traffic.json)", "peak_source": peaks["src"],
                     "arithmetic_intensity_flop_per_byte": round(flops[dom] / dom_bytes, 1), "ridge_flop_per_byte": round(ridge, 1),
                     "algorithmic_bytes_per_launch": dom_bytes, "tensor_frac_same_kernel": kernels[dom]["frac_of_tensor_peak"],
                     "step_tflops_algorithmic": round(FLOP_STEP * M / (ms_step * 1e-3) / 1e12, 1)}
     else:
         roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops_algorithmic"], "peak": peaks["tflops"],
                     "unit": "TFLOP/s", "frac": kernels[dom]["frac_of_tensor_peak"], "traffic": traffic.get(dom),
-                    "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01g_traffic.json)", "peak_source": peaks["src"],
+                    "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01h_traffic.json)", "peak_source": peaks["src"],
                     "step_tflops_algorithmic": round(FLOP_STEP * M / (ms_step * 1e-3) / 1e12, 1)}
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     d2h = (rays * C_FEAT + rays) * 4 + sum(host[k].numel() for k in code_keys) * 4
