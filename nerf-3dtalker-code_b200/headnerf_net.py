@@ -219,12 +219,40 @@ class HeadNeRFNet(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.neural_render.parameters()):
             # the two renderer calls of the reference (HeadNeRFNet.py:109,113) as ONE pass over B + 1 feature maps: every
             # operator of the renderer acts per item, so the images are the same and the launch count halves
-            imgs = self.neural_render(torch.cat([merge_featmap, bg_featmap], dim=0))
+            imgs = self._render_both(torch.cat([merge_featmap, bg_featmap], dim=0))
             merge_img, bg_img = imgs[:batch_size], imgs[batch_size:]
         else:
             bg_img = self._bg_image(bg_featmap)
             merge_img = self.neural_render(merge_featmap)
         return {"coarse_dict": {"merge_img": merge_img, "bg_img": bg_img}}
+
+    def capture_consumer_graph(self, batch_size):
+        """Opt-in: capture NeuralRenderer's forward and backward over `batch_size` + 1 feature maps (the merged maps and the
+        background map, see _forward) into CUDA graphs (torch.cuda.make_graphed_callables).  The consumer is ~130 small launches per
+        training step and bound by the host's launch rate (3.4 ms of GPU work in 5.4 ms of wall time at Reso32HR); replaying
+        two graphs removes that.  Shapes, the training mode and the parameters' requires_grad flags must not change afterwards;
+        `release_consumer_graph()` returns to eager launches."""
+        dev = self.neural_render.bg_featmap.device
+        if dev.type != "cuda":
+            raise RuntimeError("capture_consumer_graph needs the module on a CUDA device")
+        fs, C = self.featmap_size, self.featmap_nc
+        sample = torch.randn(batch_size + 1, C, fs, fs, device=dev, requires_grad=True)
+        for blk in self.neural_render.feat_upsample_list:          # host copies of the blur taps are read once, outside the capture
+            blk.blur_layer.taps()
+        self.neural_render.rgb_upsample[1].taps()
+        self._consumer_graph = torch.cuda.make_graphed_callables(self.neural_render, (sample,), allow_unused_input=True)   # bg_featmap is a parameter the module itself never reads
+        self._consumer_graph_batch = batch_size
+        return self
+
+    def release_consumer_graph(self):
+        self._consumer_graph = None
+        self._consumer_graph_batch = None
+
+    def _render_both(self, both):
+        g = getattr(self, "_consumer_graph", None)
+        if g is not None and both.shape[0] == self._consumer_graph_batch + 1 and torch.is_grad_enabled():
+            return g(both)
+        return self.neural_render(both)
 
     def _bg_image(self, bg_featmap):
         """bg_img = neural_render(bg_featmap) (HeadNeRFNet.py:109) depends on parameters only: when none of them can receive a

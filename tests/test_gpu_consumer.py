@@ -100,3 +100,30 @@ def test_merge_kernel_matches_pytorch(hn, B, fs, C):
     assert torch.equal(res[0][0], res[1][0]) or (res[0][0] - res[1][0]).abs().max() <= 1e-6
     for a, b in zip(res[0][1], res[1][1]):
         assert (a - b).abs().max() <= 1e-4 * (1 + a.abs().max())
+
+
+def test_consumer_graph_capture_matches_eager(hn):
+    """capture_consumer_graph(): NeuralRenderer forward + backward replayed from CUDA graphs give the eager images and gradients."""
+    from oracle import headnerf_oracle as O
+    torch.manual_seed(1)
+    opt = O.OracleOptions(featmap_size=16, pred_img_size=64)
+    net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": 16, "featmap_nc": 256, "pred_img_size": 64}), False, False).to(DEV)
+    x = {k: v.to(DEV) for k, v in O.synthetic_inputs(opt, 2, seed=3).items()}
+    tgt = torch.rand(2, 3, 64, 64, device=DEV)
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        out = net("test", x["batch_xy"], None, x["audiostyle"], None, x["shape_code"], x["appea_code"], x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"])
+        loss = ((out["coarse_dict"]["merge_img"] - tgt) ** 2).mean() + ((out["coarse_dict"]["bg_img"] - 1.0) ** 2).mean()
+        loss.backward()
+        return out["coarse_dict"]["merge_img"].detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    img0, g0 = step()
+    net.capture_consumer_graph(2)
+    for _ in range(2):                                            # replay twice: static buffers must be refreshed every time
+        img1, g1 = step()
+    net.release_consumer_graph()
+    assert (img0 - img1).abs().max() <= 1e-5
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert (g0[k] - g1[k]).abs().max() <= 2e-3 * (g0[k].abs().max() + 1e-12), k

@@ -50,6 +50,10 @@ def train_step():
 ms = timed(train_step, 20)
 M = 2 * 1024 * 64
 print(f"| 3 | Reso32HR (32x32 rays x 64, 512 px) full training step incl. NeuralRenderer + MSE + Adam, batch 2 | {ms:.3f} | {M / ms * 1e3:.3e} |")
+net.capture_consumer_graph(2)               # NeuralRenderer fwd + bwd as two CUDA graphs
+ms = timed(train_step, 20)
+print(f"| 3 | same full training step, consumer captured in CUDA graphs (capture_consumer_graph) | {ms:.3f} | {M / ms * 1e3:.3e} |")
+net.release_consumer_graph()
 def hot_only():
     Fm, bg = net.render_rays("train", x["batch_xy"], x["audiostyle"], x["shape_code"], x["appea_code"], x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"])
     (Fm.sum() + bg.sum()).backward()
