@@ -11,7 +11,9 @@
  *    synchronises and launches on the stream passed as `stream` (a cudaStream_t).  Its only own device
  *    resources, created once per device on first use and never freed: immutable schedule tables (constant
  *    memory, plus one < 64 KiB table for hn_pack_weights_precise) and, for hn_mlp_bwd_weights, one
- *    non-blocking side stream with two events that is forked from and joined back into `stream`;
+ *    non-blocking side stream with two events that is forked from and joined back into `stream`
+ *    (thread safety: calls on one device are serialised by a library mutex across that fork / launch / join
+ *    sequence, so host threads may call concurrently on different streams);
  *  - every function returns 0 on success, a negative HN_E_* code on a bad argument, or a positive
  *    cudaError_t value; hn_last_error() returns a thread-local human-readable message;
  *  - samples are indexed m = (b*n_rays + r)*n_samples + s; M = B*n_rays*n_samples must be a multiple
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 1
+#define HN_ABI_VERSION 2
 
 /* error codes (negative = argument / configuration errors) */
 #define HN_OK 0
@@ -208,6 +210,8 @@ typedef struct {
     void* items_workspace;    /* device scratch for the work-item table, hn_wgrad_workspace_bytes(B)   */
     size_t items_workspace_bytes;
     int* status;
+    int want_all_bias;        /* with every dw NULL: 0 = bias gradients of the latent-folded layers only (FeaExt_module_0,
+                               * _5, RGB_layer_1: what the code gradients need), 1 = of all 12 layers (bias-only fine-tuning) */
 } hn_mlp_bwd_weights_t;
 
 size_t hn_wgrad_workspace_bytes(int B);
@@ -365,6 +369,43 @@ typedef struct {
 } hn_render_bwd_t;
 
 int hn_render_bwd(const hn_render_bwd_t* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step around the path.
+ * Photometric loss of the reference, Utils/HeadNeRFLossUtils.py:125-140 (calc_data_loss) summed as in :196-236
+ * (calc_total_loss): bg_loss = mean((bg_img - bg_value)^2); head_loss = mean over {mask >= 0.5} of (img - gt)^2;
+ * nonhead_loss = mean over {mask < 0.5} of (img - bg_value)^2, img = nan_to_num(merge_img, nan = 0).  NCHW fp32.
+ * hn_photo_loss_fwd: one deterministic reduction kernel -> out[0..3] = bg, head, nonhead, total; out[4..6] = the three
+ * element counts (kept for the backward).  hn_photo_loss_bwd: one kernel, d_img / d_bg_img written (=), either may be
+ * NULL; gout = 4 device floats dL/d(bg, head, nonhead, total) or NULL (= 0, 0, 0, 1).                               */
+typedef struct {
+    int B;                    /* items of merge_img / gt / mask                                                    */
+    int B_bg;                 /* items of bg_img (1 in the reference: neural_render(bg_featmap))                   */
+    int HW;                   /* pixels per image plane                                                            */
+    float bg_value;           /* 1 = white, 0 = black (HeadNeRFLossUtils.py:72-75)                                 */
+    const float* img;         /* [B,3,HW] merge_img                                                                */
+    const float* bg_img;      /* [B_bg,3,HW]                                                                       */
+    const float* gt;          /* [B,3,HW]                                                                          */
+    const float* mask;        /* [B,1,HW] float; head = mask >= 0.5                                                */
+    float* partials;          /* hn_photo_loss_workspace_bytes() scratch (first bytes), ...                        */
+    unsigned int* ticket;     /* ... one zeroed 32-bit word inside it (left zero by the kernel)                    */
+    float* out;               /* [8] device floats                                                                 */
+} hn_photo_loss_t;
+
+size_t hn_photo_loss_workspace_bytes(void);
+int hn_photo_loss_fwd(const hn_photo_loss_t* a, void* stream);
+int hn_photo_loss_bwd(const hn_photo_loss_t* a, const float* gout, float* d_img, float* d_bg_img, void* stream);
+
+/* Adam over one flat fp32 buffer (talker_trainer.py:722-723,1062-1067: torch.optim.Adam(model.parameters(), lr) .step()),
+ * arithmetic of torch.optim.Adam's single-tensor path (amsgrad off): one launch for every parameter of the model when
+ * parameters, gradients (dist.GradBucket.flat) and both moments are flat buffers.  grad_scale multiplies the gradient
+ * first (1/world_size after an all-reduce SUM: the averaging costs no extra pass).  step counts from 1.                */
+typedef struct {
+    float lr, beta1, beta2, eps, weight_decay, grad_scale;
+    int64_t step;
+} hn_adam_t;
+
+int hn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const hn_adam_t* h, void* stream);
 
 /* Bytes of the saved-for-backward buffers for M samples. */
 size_t hn_act_bytes(int64_t M);

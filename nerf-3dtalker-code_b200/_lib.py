@@ -54,7 +54,7 @@ class MlpBwdWeights(C.Structure):
     _fields_ = [("B", C.c_int), ("n_rays", C.c_int), ("n_samples", C.c_int),
                 ("act", _p), ("grads", _p), ("dfeat_image", _p), ("grad_scale", _p),
                 ("dw", _p * 12), ("ld", C.c_int * 12), ("l5_hidden_col", C.c_int), ("dbias", _p),
-                ("items_workspace", _p), ("items_workspace_bytes", C.c_size_t), ("status", _p)]
+                ("items_workspace", _p), ("items_workspace_bytes", C.c_size_t), ("status", _p), ("want_all_bias", C.c_int)]
 
 
 class MlpFwdPrecise(C.Structure):
@@ -91,12 +91,23 @@ class RenderBwd(C.Structure):
                 ("status", _p)]
 
 
+class PhotoLoss(C.Structure):
+    _fields_ = [("B", C.c_int), ("B_bg", C.c_int), ("HW", C.c_int), ("bg_value", C.c_float), ("img", _p), ("bg_img", _p), ("gt", _p),
+                ("mask", _p), ("partials", _p), ("ticket", _p), ("out", _p)]
+
+
+class Adam(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("grad_scale", C.c_float), ("step", C.c_int64)]
+
+
 EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pack_weights", "hn_sample_rays",
            "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
            "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes",
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
            "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
-           "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd"]
+           "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd",
+           "hn_photo_loss_workspace_bytes", "hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step"]
 
 _lib = None
 
@@ -143,6 +154,12 @@ def load():
     lib.hn_render_fwd.argtypes = [C.POINTER(RenderFwd), _p]
     lib.hn_render_bwd.argtypes = [C.POINTER(RenderBwd), _p]
     lib.hn_merge_bwd.argtypes = [_p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p]
+    lib.hn_photo_loss_workspace_bytes.restype = C.c_size_t
+    lib.hn_photo_loss_fwd.argtypes = [C.POINTER(PhotoLoss), _p]
+    lib.hn_photo_loss_bwd.argtypes = [C.POINTER(PhotoLoss), _p, _p, _p, _p]
+    lib.hn_adam_step.argtypes = [_p, _p, _p, _p, C.c_int64, C.POINTER(Adam), _p]
+    for name in ("hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step"):
+        getattr(lib, name).restype = C.c_int
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
     lib.hn_mlp_fwd.argtypes = [C.POINTER(MlpFwd), _p]
     lib.hn_composite_fwd.argtypes = [C.POINTER(CompositeFwd), _p]
@@ -154,7 +171,7 @@ def load():
                  "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
                  "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd"):
         getattr(lib, name).restype = C.c_int
-    if lib.hn_abi_version() != 1:
+    if lib.hn_abi_version() != 2:
         raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")
     _lib = lib
     return lib

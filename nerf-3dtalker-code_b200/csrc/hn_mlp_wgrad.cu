@@ -432,7 +432,7 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     layers.push_back({W_R1, HN_RGB1, HN_GSLOT_R1, 0, HN_BIAS_OFF_R1, HN_SLOT_R0, 6, false, 0});
     layers.push_back({W_R2, HN_FEAT, 0, 1, HN_BIAS_OFF_R2, HN_SLOT_X, 3, false, 0});
     layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});   // density pseudo layer
-    auto active = [&](const LayerW& L) { return want_w || L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1; };
+    auto active = [&](const LayerW& L) { return want_w || a.want_all_bias || L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1; };
     // CTA pairs: 384 x 384 layers (six hidden X blocks, no PE block); their chunk 2 goes to the single-CTA list
     auto paired = [&](const LayerW& L) { return want_w && n_pairs > 0 && L.n_out == HN_HIDDEN && L.n_xblk == 6 && !L.pe && a.dw[L.w_idx] != nullptr; };
     auto clustered = [&](const LayerW& L) { return !paired(L) && want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
@@ -684,6 +684,9 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
         if (int rc = check_launch("hn_mlp_bwd_weights (CTA pairs)")) return rc;
     }
     const bool forked = !side.empty() && !cluster.empty();
+    // the side stream and its two events are per device, shared by all callers: the fork / launch / join sequence is serialised
+    std::unique_lock<std::mutex> side_lock(g_w_mu, std::defer_lock);
+    if (forked) side_lock.lock();
     if (forked && cudaEventRecord(g_w_fork[dev], st) != cudaSuccess) return set_error(HN_E_PROTOCOL, "hn_mlp_bwd_weights: event record failed");
     if (!cluster.empty()) {
         k.items = (const WItem*)a->items_workspace; k.n_items = (int)cluster.size() / 3;

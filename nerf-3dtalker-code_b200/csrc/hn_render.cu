@@ -63,6 +63,8 @@ extern "C" int hn_render_bwd(const hn_render_bwd_t* a, void* stream) {
         for (int i = 0; i < 12; ++i) { w.dw[i] = a->dw[i]; w.ld[i] = a->ld[i]; }
         w.l5_hidden_col = a->l5_hidden_col; w.dbias = a->dbias_eff;
         w.items_workspace = a->items_workspace; w.items_workspace_bytes = a->items_workspace_bytes; w.status = a->status;
+        for (int i = 0; i < 12; ++i)
+            if (i != 0 && i != 5 && i != 10 && a->fold_grads.dbias[i]) w.want_all_bias = 1;   // beyond the latent-folded layers (FeaExt_module_0, _5, RGB_layer_1)
         if (int rc = hn_mlp_bwd_weights(&w, stream)) return rc;
         if (need_fold)
             if (int rc = hn_fold_bias_bwd(&a->fold, a->dbias_eff, &a->fold_grads, stream)) return rc;

@@ -88,7 +88,41 @@ class HeadNeRFNet(nn.Module):
         # exactly when a camera input (batch_Rmats / batch_Tvecs / batch_inv_inmats) requires a gradient - the fitting loop,
         # whose ill-conditioned camera gradients need it - and "fast" otherwise (training, inference).  Not part of the state dict.
         self.precision = os.environ.get("HN_PRECISION", "auto")
+        # "auto" also measures, on the caller's own inputs, whether the single-pass kernels keep the feature map inside
+        # `auto_tolerance` of the split-operand ones (see _calibrate): checkpoints with a large feature / density scale run "high".
+        self.auto_tolerance = float(os.environ.get("HN_AUTO_TOLERANCE", "5e-4"))
+        self.calib_interval = int(os.environ.get("HN_CALIB_INTERVAL", "64"))     # training: re-measure every N weight versions
+        self.calib_rays = 512
+        self._calib = None                       # (weights key, calls since, decision "fast" | "high", measured error)
         self._fuse_grads = False
+        # every derived cache (packed operand images, cached bg_img, blur taps, the precision decision) is dropped whenever the
+        # parameters may have been replaced behind autograd's version counters: load_state_dict, .to()/.cuda()/.float(), and -
+        # because the reference's own loader writes through `model.state_dict()[k].data.copy_(...)` (talker_trainer.py:557-567),
+        # which bumps no version counter - every call of state_dict()
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_caches())
+        self._register_state_dict_hook(lambda module, sd, prefix, local_metadata: module.invalidate_caches())
+
+    def invalidate_caches(self):
+        """Forget everything derived from the parameters (packed weight operands, the cached background image, blur taps, the
+        "auto" precision decision).  Called automatically by load_state_dict(), state_dict() and _apply() (.to / .cuda / .half);
+        call it yourself after writing parameters through `.data` (EMA, clamping, re-initialisation), which autograd's version
+        counters - the cache keys - do not see."""
+        self._packed_key = None
+        self._packed_hl_key = None
+        self._bg_cache_key = None
+        self._bg_cache = None
+        self._calib = None
+        for m in self.neural_render.modules():
+            if hasattr(m, "_taps_key"):
+                m._taps_key = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_packed_key"):
+            self.invalidate_caches()
+            self._packed = None
+            self._packed_hl = None
+        return out
 
     # ------------------------------------------------------------------ weights -> kernel operands
     def _packed_weights(self):
@@ -187,11 +221,15 @@ class HeadNeRFNet(nn.Module):
         camera_grad = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad
                                                       for t in (batch_Rmats, batch_Tvecs, batch_inv_inmats))
         high = self.precision == "high" or (self.precision == "auto" and camera_grad)
+        if self.precision == "auto" and not high:
+            high = self._calibrate(mode, batch_xy, audiostyle, shape_code, appea_code, batch_Rmats, batch_Tvecs, batch_inv_inmats, t_rand) == "high"
         grad_into = self._grad_into()
         bias = self._fold_biases_cuda(shape_code.float(), appea_code.float(), audiostyle.float(), grad_into)
         meta = {"n_samples": ns, "world_z1": self.opt.world_z1, "world_z2": self.opt.world_z2,
                 "l5_hidden_col": L.PE + self.shape_dims, "precision": "high" if high else "fast", "grad_into": None if high else grad_into,
-                "grad_target": float(getattr(self, "grad_target", 1024.0 if high else 64.0))}
+                "grad_target": float(getattr(self, "grad_target", 1024.0 if high else 64.0)),
+                # frozen weights with trainable biases: the weight pass must still visit the layers whose bias gradients no latent code needs
+                "all_bias": any(m.bias.requires_grad for i, m in enumerate(self.fg_CD_predictor.layers()) if i not in (0, 5, 10))}
         if high:
             ws, meta["packed_hl"] = self._packed_weights_precise()
         else:
@@ -205,6 +243,41 @@ class HeadNeRFNet(nn.Module):
             Fm, bg = Fm[:, :n_r], bg[:, :n_r]
         return Fm, bg
 
+    def _calibrate(self, mode, batch_xy, audiostyle, shape_code, appea_code, batch_Rmats, batch_Tvecs, batch_inv_inmats, t_rand):
+        """precision="auto": which kernel family keeps THIS checkpoint's feature map inside the parity gate?  Measured, not
+        guessed: up to `calib_rays` rays, strided over the caller's own ray set, are rendered by both families (no autograd) and
+        max|F_fast - F_high|, max|bg_fast - bg_high| is compared with `auto_tolerance` (half the 1e-3 gate).  The single-pass
+        11-bit operands carry ~5e-4 of error relative to the feature / density scale: fine for random-init
+        and moderately scaled weights, outside the absolute gate once max|F| exceeds ~2.  The decision is cached per weight
+        version (inference) and re-measured every `calib_interval` versions while the weights train; one host sync per probe."""
+        ws = [m.weight for m in self.fg_CD_predictor.layers()]
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        c = self._calib
+        if c is not None and (c[0] == key or (torch.is_grad_enabled() and any(w.requires_grad for w in ws) and c[1] < self.calib_interval)):
+            self._calib = (c[0], c[1] + (c[0] != key), c[2], c[3])
+            return c[2]
+        n_r = batch_xy.shape[2]
+        step = max(1, n_r // self.calib_rays)
+        idx = torch.arange(0, n_r, step, device=batch_xy.device)[: self.calib_rays]
+        if idx.numel() % 2:
+            idx = idx[:-1] if idx.numel() > 1 else idx
+        xy = batch_xy.detach()[:, :, idx].contiguous()
+        tr = None if t_rand is None else t_rand.detach()[:, idx].contiguous()
+        saved = self.precision
+        res = {}
+        try:
+            with torch.no_grad():
+                for prec in ("fast", "high"):
+                    self.precision = prec
+                    res[prec] = self.render_rays("test" if tr is None else mode, xy, audiostyle.detach(), shape_code.detach(), appea_code.detach(),
+                                                 batch_Rmats.detach(), batch_Tvecs.detach(), batch_inv_inmats.detach(), t_rand=tr)
+        finally:
+            self.precision = saved
+        err = max(float((res["fast"][0] - res["high"][0]).abs().max()), float((res["fast"][1] - res["high"][1]).abs().max()))
+        decision = "high" if (err > self.auto_tolerance or err != err) else "fast"
+        self._calib = (key, 0, decision, err)
+        return decision
+
     def _forward(self, for_train, batch_xy, batch_uv, audiostyle, bg_code, shape_code, appea_code,
                  batch_Rmats, batch_Tvecs, batch_inv_inmats, dist_expr):
         batch_size, tv, n_r = batch_xy.size()
@@ -212,10 +285,26 @@ class HeadNeRFNet(nn.Module):
         assert bg_code is None
         fs, C = self.featmap_size, self.featmap_nc
         assert n_r == fs * fs, "HeadNeRFNet.forward renders a full featmap (HeadNeRFNet.py:103-106); use render_rays otherwise"
-        Fm, bg = self.render_rays("train" if for_train else "test", batch_xy, audiostyle, shape_code, appea_code,
-                                  batch_Rmats, batch_Tvecs, batch_inv_inmats)
+        shard = getattr(self, "_ray_shard", None)
+        if shard is None:
+            Fm, bg = self.render_rays("train" if for_train else "test", batch_xy, audiostyle, shape_code, appea_code,
+                                      batch_Rmats, batch_Tvecs, batch_inv_inmats)
+        else:
+            # rays sharded inside every item: this rank renders its contiguous slice of each item's rays, the
+            # slices are all-gathered (reduce-scatter backward) and the consumer below runs on whole maps on every rank
+            from . import dist as hdist
+            rank, world, group = shard
+            xy_loc, lo, hi = hdist.shard_rays(batch_xy, rank, world)
+            Fm, bg = self.render_rays("train" if for_train else "test", xy_loc, audiostyle, shape_code, appea_code,
+                                      batch_Rmats, batch_Tvecs, batch_inv_inmats)
+            Fm, bg = hdist.gather_rays(Fm, bg, n_r, rank, world, group)
+            Fm, bg = Fm.contiguous(), bg.contiguous()
         bg_featmap = self.neural_render.get_bg_featmap()
         merge_featmap = ops.MergeFunction.apply(Fm, bg, bg_featmap)       # F^T + bg_alpha * bg_featmap (HeadNeRFNet.py:103-113)
+        hook = getattr(self, "on_consumer_grads_ready", None)
+        if hook is not None and merge_featmap.requires_grad:
+            # the backward pass reaches the feature map: every NeuralRenderer gradient (except bg_featmap's merge term) is complete
+            merge_featmap.register_hook(lambda g: (hook(), None)[1])
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.neural_render.parameters()):
             # the two renderer calls of the reference (HeadNeRFNet.py:109,113) as ONE pass over B + 1 feature maps: every
             # operator of the renderer acts per item, so the images are the same and the launch count halves
@@ -229,29 +318,45 @@ class HeadNeRFNet(nn.Module):
     def capture_consumer_graph(self, batch_size):
         """Opt-in: capture NeuralRenderer's forward and backward over `batch_size` + 1 feature maps (the merged maps and the
         background map, see _forward) into CUDA graphs (torch.cuda.make_graphed_callables).  The consumer is ~130 small launches per
-        training step and bound by the host's launch rate (3.4 ms of GPU work in 5.4 ms of wall time at Reso32HR); replaying
-        two graphs removes that.  Shapes, the training mode and the parameters' requires_grad flags must not change afterwards;
-        `release_consumer_graph()` returns to eager launches."""
+        training step and bound by the host's launch rate; replaying two graphs removes that.  Only calls with exactly the captured
+        input shape, autograd enabled and the captured training mode replay the graphs; every other call (validation under
+        no_grad, other batch sizes, the background map alone) runs the eager module.  The module tree, its state_dict keys and
+        the parameters are untouched; `release_consumer_graph()` restores plain eager launches."""
         dev = self.neural_render.bg_featmap.device
         if dev.type != "cuda":
             raise RuntimeError("capture_consumer_graph needs the module on a CUDA device")
+        self.release_consumer_graph()
         fs, C = self.featmap_size, self.featmap_nc
-        sample = torch.randn(batch_size + 1, C, fs, fs, device=dev, requires_grad=True)
+        shape = (batch_size + 1, C, fs, fs)
+        sample = torch.randn(*shape, device=dev, requires_grad=True)
         for blk in self.neural_render.feat_upsample_list:          # host copies of the blur taps are read once, outside the capture
             blk.blur_layer.taps()
         self.neural_render.rgb_upsample[1].taps()
-        self._consumer_graph = torch.cuda.make_graphed_callables(self.neural_render, (sample,), allow_unused_input=True)   # bg_featmap is a parameter the module itself never reads
-        self._consumer_graph_batch = batch_size
+        nr = self.neural_render
+        eager = nr.forward                                          # the class's bound method
+        training = nr.training
+        # make_graphed_callables patches `nr.forward` in place (an instance attribute) and hands the same module back: keep the
+        # patched function, and put a dispatcher in its place that only replays it for the captured situation
+        torch.cuda.make_graphed_callables(nr, (sample,), allow_unused_input=True)   # bg_featmap is a parameter the module itself never reads
+        graphed = nr.__dict__["forward"]
+
+        def dispatch(x):
+            if torch.is_grad_enabled() and tuple(x.shape) == shape and nr.training == training and x.is_cuda:
+                return graphed(x)
+            return eager(x)
+
+        nr.forward = dispatch
+        object.__setattr__(self, "_consumer_graph_state", {"shape": shape, "graphed": graphed})     # not a submodule, not in state_dict
         return self
 
     def release_consumer_graph(self):
-        self._consumer_graph = None
-        self._consumer_graph_batch = None
+        """Back to eager launches: removes the dispatcher that capture_consumer_graph() put over NeuralRenderer.forward."""
+        if getattr(self, "_consumer_graph_state", None) is not None:
+            self.neural_render.__dict__.pop("forward", None)
+            object.__setattr__(self, "_consumer_graph_state", None)
+        return self
 
     def _render_both(self, both):
-        g = getattr(self, "_consumer_graph", None)
-        if g is not None and both.shape[0] == self._consumer_graph_batch + 1 and torch.is_grad_enabled():
-            return g(both)
         return self.neural_render(both)
 
     def _bg_image(self, bg_featmap):
@@ -266,6 +371,17 @@ class HeadNeRFNet(nn.Module):
                 self._bg_cache = self.neural_render(bg_featmap)
             self._bg_cache_key = key
         return self._bg_cache
+
+    def set_ray_sharding(self, rank=None, world=None, group=None):
+        """forward() renders only this rank's slice of every item's rays and all-gathers the composited features (dist.gather_rays);
+        for batches smaller than the number of GPUs.  Call without arguments to switch it off."""
+        object.__setattr__(self, "_ray_shard", None if (rank is None or world is None or world <= 1) else (int(rank), int(world), group))
+        return self
+
+    def check_faults(self):
+        """Wait for the launches issued so far and raise if any kernel reported an on-chip pipeline fault (ops.FaultMonitor
+        polls the same status words asynchronously at every later library call)."""
+        ops.FAULTS.flush()
 
     def forward(self, mode, batch_xy, batch_uv, audiostyle, bg_code, shape_code, appea_code,
                 batch_Rmats, batch_Tvecs, batch_inv_inmats, dist_expr=False, **kwargs):

@@ -9,16 +9,13 @@ from _util import GOLDEN_CASES, LEAVES, cosine, golden_loss, load_golden, probe_
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-# Gates.  North star: cosine >= 0.999 on every leaf.  Codes, every weight and bias and bg_featmap clear it with margin
-# (>= 0.99997).  The two camera leaves go through the positional encoding's 2^9 gain and a heavily cancelling sum over
-# all samples, which amplifies the per-sample rounding noise of the 11-bit (fp16 / TF32-class) operands to ~5 % of the
-# net gradient on these random-weight problems: measured 0.9981-0.9991.  They are gated at 0.995 here and the gap is
-# reported in DESIGN.md (precision section) - it is a property of single-pass half-precision operands, not of the
-# formulas (the same chain gives 0.99999 on every non-camera leaf).  The precision="high" mode clears 0.999 on the camera
-# leaves too (0.99999): tests/test_gpu_precise.py holds every leaf to the north-star gate.
+# Gate (north star): cosine >= 0.999 on EVERY leaf, no exceptions.  The single-pass kernels (precision="fast") are held to it on
+# the leaves they are the product path for: the codes, every weight and bias, bg_featmap.  Camera leaves (batch_Rmats /
+# batch_Tvecs) are never served by them in the product: precision="auto" (the default) switches to the split-operand kernels
+# whenever a camera input requires a gradient, and those are held to the same 0.999 here and in tests/test_gpu_precise.py.
 GATE = 0.999
-GATE_CAMERA = 0.995
 CAMERA = ("batch_Rmats", "batch_Tvecs")
+NON_CAMERA = [k for k in LEAVES if k not in CAMERA]
 
 
 def _oracle_grads(g):
@@ -50,7 +47,7 @@ def _cuda_grads(hn, g, leaves=LEAVES, param_grads=True, precision="fast"):
     merge = fg + bg.view(B, 1, fs, fs) * net.neural_render.get_bg_featmap()
     img = net.neural_render(merge)
     golden_loss(img).backward()
-    hn.ops.check_status(net.last_meta["last_status"], "render backward")
+    net.check_faults()
     gl = {k: x[k].grad.cpu() for k in leaves}
     gp = {k: p.grad.cpu() for k, p in net.named_parameters() if p.grad is not None}
     return gl, gp
@@ -60,15 +57,12 @@ def _cuda_grads(hn, g, leaves=LEAVES, param_grads=True, precision="fast"):
 def test_gradients_match_oracle_and_reference(hn, name):
     g = load_golden(name)
     ol, op = _oracle_grads(g)
-    cl, cp = _cuda_grads(hn, g)
+    cl, cp = _cuda_grads(hn, g, leaves=NON_CAMERA)
     worst = ("", 2.0)
-    for k in LEAVES:
+    for k in NON_CAMERA:
         c_or, c_ref = cosine(cl[k], ol[k]), cosine(cl[k], g["grads"][k])
         print(f"{name} {k:14s} cos(oracle) {c_or:.6f} cos(reference golden) {c_ref:.6f}  |g| {float(ol[k].norm()):.3e}")
-        if k in CAMERA:
-            assert min(c_or, c_ref) >= GATE_CAMERA, (k, c_or, c_ref)
-        else:
-            worst = min(worst, (k, min(c_or, c_ref)), key=lambda t: t[1])
+        worst = min(worst, (k, min(c_or, c_ref)), key=lambda t: t[1])
     for k, ref in op.items():
         assert k in cp, f"no gradient for {k}"
         c = cosine(cp[k], ref)
@@ -82,15 +76,16 @@ def test_gradients_match_oracle_and_reference(hn, name):
 
 
 def test_fitting_config_no_weight_grads(hn):
-    """FittingSingleImage_new.py:826-903 shape: grads only to codes and camera, network weights frozen."""
+    """FittingSingleImage_new.py:826-903 shape: grads only to codes and camera, network weights frozen; the product default
+    (precision="auto") against the reference's golden gradients and the oracle: 0.999 on every leaf, camera included."""
     g = load_golden("fs16_test_trained")
     ol, _ = _oracle_grads(g)
-    cl, cp = _cuda_grads(hn, g, param_grads=False)
+    cl, cp = _cuda_grads(hn, g, param_grads=False, precision="auto")
     assert not cp
     for k in LEAVES:
-        c = cosine(cl[k], ol[k])
-        print(f"fitting {k:14s} cos {c:.6f}")
-        assert c >= (GATE_CAMERA if k in CAMERA else GATE), k
+        c, c_ref = cosine(cl[k], ol[k]), cosine(cl[k], g["grads"][k])
+        print(f"fitting {k:14s} cos(oracle) {c:.6f} cos(reference golden) {c_ref:.6f}")
+        assert min(c, c_ref) >= GATE, k
 
 
 def test_default_precision_meets_the_gate_on_every_leaf(hn):
@@ -107,6 +102,7 @@ def test_default_precision_meets_the_gate_on_every_leaf(hn):
     opt = g["opt"]
     net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": opt.featmap_size, "featmap_nc": 256, "pred_img_size": opt.pred_img_size}), False, False).to(DEV)
     x = {k: v.to(DEV) for k, v in g["inp"].items()}
+    # a fresh (random-init) network: the single-pass kernels hold the feature-map gate, so only camera gradients select "high"
     for cam_grad, want in ((False, "fast"), (True, "high")):
         R = x["batch_Rmats"].clone().requires_grad_(cam_grad)
         sc = x["shape_code"].clone().requires_grad_(True)
@@ -116,6 +112,13 @@ def test_default_precision_meets_the_gate_on_every_leaf(hn):
         net.render_rays("test", x["batch_xy"], x["audiostyle"], x["shape_code"], x["appea_code"], x["batch_Rmats"].clone().requires_grad_(True),
                         x["batch_Tvecs"], x["batch_inv_inmats"])
     assert net.last_meta["precision"] == "fast"
+    assert net._calib[2] == "fast" and net._calib[3] <= net.auto_tolerance
+    # the trained-like checkpoint exceeds what 11-bit operands can hold to 1e-3: the probe must say so, and a reload must re-probe
+    net.load_state_dict(O.formula_state_dict(opt, "trained"), strict=True)
+    assert net._calib is None
+    with torch.no_grad():
+        net.render_rays("test", x["batch_xy"], x["audiostyle"], x["shape_code"], x["appea_code"], x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"])
+    assert net.last_meta["precision"] == "high" and net._calib[3] > net.auto_tolerance
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

@@ -69,6 +69,7 @@ def test_gaze_columns(hn):
     sd = O.formula_state_dict(opt, "trained")
     net.load_state_dict(sd, strict=True)
     net = net.to(DEV).eval()
+    assert net.precision == "auto"                               # trained-like weights: the default must hold the absolute gate
     inp = O.synthetic_inputs(opt, 2, seed=21)
     assert inp["shape_code"].shape[1] == 181
     sdo = {k: v.clone().requires_grad_(k.startswith("fg_CD_predictor")) for k, v in sd.items()}
@@ -82,10 +83,10 @@ def test_gaze_columns(hn):
     Fm, bg = net.render_rays("test", xc["batch_xy"], xc["audiostyle"], xc["shape_code"], xc["appea_code"],
                              xc["batch_Rmats"], xc["batch_Tvecs"], xc["batch_inv_inmats"])
     torch.autograd.backward([Fm, bg], [gF.permute(0, 2, 1).contiguous().to(DEV), gb[:, 0].contiguous().to(DEV)])
-    hn.ops.check_status(net.last_meta["last_status"], "gaze")
+    net.check_faults()
     errF = (Fm.detach().cpu() - r["F"].detach().permute(0, 2, 1)).abs().max().item()
-    scale = max(1.0, float(r["F"].detach().abs().max()))
-    assert errF <= 1e-3 * scale, errF
+    scale = float(r["F"].detach().abs().max())
+    assert errF <= 1e-3, errF
     worst = min([(cosine(xc[k].grad, xo[k].grad), k) for k in CODES] +
                 [(cosine(p.grad, sdo["fg_CD_predictor." + n].grad), n) for n, p in net.fg_CD_predictor.named_parameters()])
     print(f"gaze: F err {errF:.1e} (|F|max {scale:.2f}), worst gradient cosine {worst[0]:.6f} ({worst[1]})")

@@ -74,20 +74,36 @@ def _render_golden(hn, name, train_override=None):
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_feature_map_matches_reference_golden(hn, name):
+    """The product's default (precision="auto") against the real reference's outputs: the ABSOLUTE north-star gate, max-abs-err
+    <= 1e-3 on F and bg_alpha, on every fixture - random-init weights and the "trained" stress fixtures (output layers x6 / x12,
+    max|F| 3-5) alike.  "auto" measures on the caller's inputs whether the single-pass kernels hold the gate for this checkpoint
+    (HeadNeRFNet._calibrate) and runs the split-operand kernels when they do not."""
     g, net, x = _render_golden(hn, name)
+    assert net.precision == "auto"
     with torch.no_grad():
         Fm, bg = net.render_rays(g["mode"], x["batch_xy"], x["audiostyle"], x["shape_code"], x["appea_code"],
                                  x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"], t_rand=x.get("t_rand"))
-    hn.ops.check_status(net.last_meta["last_status"], "hn_mlp_fwd")
+    net.check_faults()
     F_ref = g["out"]["F"].permute(0, 2, 1)                      # [B,N_r,C]
     errF = (Fm.cpu() - F_ref).abs().max().item()
     errA = (bg.cpu() - g["out"]["bg_alpha"][:, 0]).abs().max().item()
-    print(f"{name}: F max-abs-err {errF:.2e} (|F|max {F_ref.abs().max():.2f}), bg_alpha err {errA:.2e}")
-    # Gate from BASELINE.json: max-abs-err <= 1e-3 (random-init weights: |F| <= ~0.6).  The "trained" stress
-    # fixtures scale the output layers until |F| ~ 3-4; single-pass fp16 operands (10-bit mantissa, the same as
-    # TF32) carry ~5e-4 error relative to the activation scale, so there the bound is taken relative to max|F|.
-    tolF = 1e-3 if g["variant"] == "init" else 1e-3 * max(1.0, float(F_ref.abs().max()))
-    assert errF <= tolF and errA <= 1e-3
+    print(f"{name}: precision auto -> {net.last_meta['precision']} (probe error {net._calib[3]:.2e}); F max-abs-err {errF:.2e} "
+          f"(|F|max {F_ref.abs().max():.2f}), bg_alpha err {errA:.2e}")
+    assert errF <= 1e-3 and errA <= 1e-3
+    if g["variant"] == "init":
+        assert net.last_meta["precision"] == "fast"            # random-init weights: the single-pass kernels hold the gate
+
+
+def test_single_pass_kernels_hold_the_gate_on_init_weights(hn):
+    """precision="fast" forced (the kernels bench.py times): absolute gate on the random-init fixture."""
+    g, net, x = _render_golden(hn, "fs8_test_init")
+    net.precision = "fast"
+    with torch.no_grad():
+        Fm, bg = net.render_rays(g["mode"], x["batch_xy"], x["audiostyle"], x["shape_code"], x["appea_code"],
+                                 x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"], t_rand=x.get("t_rand"))
+    net.check_faults()
+    assert (Fm.cpu() - g["out"]["F"].permute(0, 2, 1)).abs().max().item() <= 1e-3
+    assert (bg.cpu() - g["out"]["bg_alpha"][:, 0]).abs().max().item() <= 1e-3
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
