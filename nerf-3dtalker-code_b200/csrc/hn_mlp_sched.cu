@@ -1,5 +1,6 @@
 // hn_mlp_sched.cu — host-side generation of the fused-kernel schedules (see hn_mlp_sched.h).
 #include <cassert>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -139,6 +140,12 @@ struct FwdLayer {
     bool transposed = false;        // data-gradient chain: units hold W^T (rows = layer inputs, columns = layer outputs)
 };
 
+// HN_SPLIT_TAIL=0 restores the unsplit phase A (A/B measurements); read once, before the tables are built
+static bool split_tail_enabled() {
+    static const bool on = [] { const char* e = getenv("HN_SPLIT_TAIL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+
 // Generates the stage / pack / epilogue tables of a GEMM chain whose activations live in tensor memory.  `smem_kb` leading
 // K blocks of a layer come from shared memory: the forward's positional-encoding block (1, awaited once per tile) or the
 // data-gradient chain's streamed dL/dfeat blocks (4, each awaited).
@@ -175,18 +182,40 @@ void build_tmem_chain(const std::vector<FwdLayer>& layers, bool streamed_input, 
             const int kb = k - L.smem_kb;
             return (kb % 2 == 0) ? (uint8_t)(1 + kb / 2) : 0;
         };
-        // phase A: chunks 0 and 1 together, one stage per K block
-        for (int k = 0; k < n_k; ++k) {
+        // phase A: chunks 0 and 1 together, one stage per K block ...
+        // ... except the LAST TWO K blocks (split tail): they are the ones the previous layer's last epilogue releases, so everything
+        // issued after them sits on the layer-to-layer critical path (epilogue of layer l's last chunk -> these MMAs -> epilogue of
+        // layer l+1's first chunk).  Chunk 0 takes both of them alone (N = 128) and commits; chunk 1 follows (N = 128 / 64) and
+        // commits: chunk 0's epilogue starts half a tail (8 MMAs) earlier and chunk 1's remainder runs underneath it.
+        const bool split_tail = split_tail_enabled() && n_k >= 3 && !(a_src(n_k - 1) & kSrcSmem) && !(a_src(n_k - 2) & kSrcSmem);
+        const int n_full = split_tail ? n_k - 2 : n_k;
+        for (int k = 0; k < n_full; ++k) {
             StageOp s{};
             s.a_src0 = a_src(k); s.a_src1 = kSrcNone;
             s.acc_col = (uint16_t)B;
             s.n8 = (uint8_t)((L.widths[0] + L.widths[1]) / 8);
             s.first = (uint8_t)(k == 0);
-            s.commit = (uint8_t)(k == n_k - 1 ? 2 : 0);
+            s.commit = (uint8_t)((!split_tail && k == n_k - 1) ? 2 : 0);
             s.chunk = (uint8_t)chunk0;
             s.wait_src = wait_of(k);
             stages.push_back(s);
             pack_unit(L, 0, k); pack_unit(L, 1, k);
+        }
+        if (split_tail) {
+            const uint8_t w0 = wait_of(n_k - 2), w1 = wait_of(n_k - 1);
+            assert(!(w0 && w1));                                       // one input barrier per stage
+            for (int j = 0; j < 2; ++j) {
+                StageOp s{};
+                s.a_src0 = a_src(n_k - 2); s.a_src1 = a_src(n_k - 1);
+                s.acc_col = (uint16_t)(B + 128 * j);
+                s.n8 = (uint8_t)(L.widths[j] / 8);
+                s.first = 0;
+                s.commit = 1;
+                s.chunk = (uint8_t)(chunk0 + j);
+                s.wait_src = (uint8_t)(j == 0 ? (w0 ? w0 : w1) : 0);
+                stages.push_back(s);
+                pack_unit(L, j, n_k - 2); pack_unit(L, j, n_k - 1);
+            }
         }
         // phase B: chunk 2 alone over [B, B+128), two K blocks per stage (the PE block, read from shared memory, gets a stage
         // of its own next to an empty unit: the issuer handles one kind of A operand per stage)

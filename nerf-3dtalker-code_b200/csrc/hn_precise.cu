@@ -601,6 +601,8 @@ extern "C" int hn_mlp_fwd_precise(const hn_mlp_fwd_precise_t* a, void* stream) {
     if (!a || !a->cam.xy || !a->cam.Rmats || !a->cam.Tvecs || !a->cam.inv_inmats || !a->bias || !a->w_density ||
         !a->packed_hl || !a->feat || !a->sigma || !a->delta || !a->acts || !a->status)
         return set_error(HN_E_BADARG, "hn_mlp_fwd_precise: null pointer");
+    if ((((uintptr_t)a->w_density | (uintptr_t)a->bias | (uintptr_t)a->feat | (uintptr_t)a->acts) & 15) != 0)
+        return set_error(HN_E_BADARG, "hn_mlp_fwd_precise: w_density, bias, feat and acts must be 16-byte aligned (vector loads)");
     if (int rc = check_geometry(a->cam.B, a->cam.n_rays, a->cam.n_samples, "hn_mlp_fwd_precise")) return rc;
     int n_sm = 148;
     if (int rc = prepare_device(&n_sm)) return rc;
@@ -625,6 +627,8 @@ extern "C" int hn_mlp_bwd_data_precise(const hn_mlp_bwd_data_precise_t* a, void*
     if (!a || !a->cam.xy || !a->cam.Rmats || !a->cam.Tvecs || !a->cam.inv_inmats || !a->packed_hl || !a->w_density ||
         !a->dfeat || !a->dsigma || !a->sigma || !a->grad_scale || !a->acts || !a->gz || !a->status)
         return set_error(HN_E_BADARG, "hn_mlp_bwd_data_precise: null pointer");
+    if ((((uintptr_t)a->w_density | (uintptr_t)a->dfeat | (uintptr_t)a->acts | (uintptr_t)a->gz) & 15) != 0)
+        return set_error(HN_E_BADARG, "hn_mlp_bwd_data_precise: w_density, dfeat, acts and gz must be 16-byte aligned (vector loads)");
     if (int rc = check_geometry(a->cam.B, a->cam.n_rays, a->cam.n_samples, "hn_mlp_bwd_data_precise")) return rc;
     const bool with_pe = (a->g_ray_o != nullptr);
     if (with_pe && (!a->g_ray_v || !a->g_ray_l))

@@ -46,6 +46,19 @@ def shard_rays(batch_xy: torch.Tensor, rank: int, world: int, multiple: int = 2)
     return batch_xy[:, :, lo:hi].contiguous(), lo, hi
 
 
+FLAT_ALIGN = 64          # floats: every tensor of a flat buffer starts on a 256-byte boundary (vector loads, bulk copies, library GEMMs)
+
+
+def flat_layout(tensors, align: int = FLAT_ALIGN):
+    """Offsets (in elements) of `tensors` laid end to end with every start rounded up to `align`.  -> (offsets, total)."""
+    offs, off = [], 0
+    for t in tensors:
+        offs.append(off)
+        off += t.numel()
+        off += (-off) % align
+    return offs, off
+
+
 class GradBucket:
     """All parameter gradients live in ONE flat fp32 buffer (p.grad are views), so the training step needs a
     single memset and a single all-reduce — latency-bound on NVLink 5 (10.8–14 MB).
@@ -58,15 +71,17 @@ class GradBucket:
         ids = {id(p) for p in early}
         rest = [p for p in params if p.requires_grad and id(p) not in ids]
         self.params: List[torch.nn.Parameter] = early + rest
-        self.n_early = sum(p.numel() for p in early)
-        n = sum(p.numel() for p in self.params)
+        self.offsets, n = flat_layout(self.params)
+        self.n_early = self.offsets[len(early)] if (early and rest) else (n if early else 0)
         dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)      # the alignment gaps stay zero
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
         self._early_work = None
+
+    def compact(self):
+        """The gradients without the alignment gaps, concatenated in bucket order (tests, logging)."""
+        return torch.cat([self.flat[o:o + p.numel()] for p, o in zip(self.params, self.offsets)])
 
     def zero(self):
         self.flat.zero_()

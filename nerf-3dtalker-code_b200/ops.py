@@ -21,14 +21,17 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _dev_f32(t, name, shape=None):
+def _dev_f32(t, name, shape=None, align=4):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise L.HeadNeRFLibraryError(f"{name} must be a CUDA tensor: this path has no CPU implementation")
     if t.dtype != torch.float32:
         raise TypeError(f"{name} must be float32, got {t.dtype}")
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % align:                       # a view at an odd offset of somebody's flat buffer: the kernels use vector loads
+        t = t.clone()
+    return t
 
 
 class KernelTimer:
@@ -373,8 +376,8 @@ class RenderFunction(torch.autograd.Function):
         ns = meta["n_samples"]
         xy_c, R_c, T_c, K_c, tr_c = _check_camera(xy, R, T, Kinv, t_rand, ns)
         B, _, n_rays = xy_c.shape
-        bias_c = _dev_f32(bias_eff, "bias_eff", (B, L.BIAS_STRIDE))
-        wd = _dev_f32(w_density.reshape(-1), "w_density", (L.HIDDEN,))
+        bias_c = _dev_f32(bias_eff, "bias_eff", (B, L.BIAS_STRIDE), align=16)
+        wd = _dev_f32(w_density.reshape(-1), "w_density", (L.HIDDEN,), align=16)
         M = B * n_rays * ns
         dev = xy_c.device
         need_bwd = any(ctx.needs_input_grad)
@@ -539,8 +542,8 @@ class RenderFunctionPrecise(torch.autograd.Function):
         ns = meta["n_samples"]
         xy_c, R_c, T_c, K_c, tr_c = _check_camera(xy, R, T, Kinv, t_rand, ns)
         B, _, n_rays = xy_c.shape
-        bias_c = _dev_f32(bias_eff, "bias_eff", (B, L.BIAS_STRIDE))
-        wd = _dev_f32(weights[8].detach().reshape(-1), "w_density", (L.HIDDEN,))
+        bias_c = _dev_f32(bias_eff, "bias_eff", (B, L.BIAS_STRIDE), align=16)
+        wd = _dev_f32(weights[8].detach().reshape(-1), "w_density", (L.HIDDEN,), align=16)
         M = B * n_rays * ns
         dev = xy_c.device
         feat = torch.empty(M, L.FEAT, device=dev)

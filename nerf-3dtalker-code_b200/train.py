@@ -127,25 +127,22 @@ class FusedAdam(torch.optim.Optimizer):
         dev = ps[0].device
         if dev.type != "cuda" or any(p.dtype != torch.float32 or p.device != dev for p in ps):
             raise L.HeadNeRFLibraryError("FusedAdam needs float32 CUDA parameters on one device (there is no CPU implementation)")
-        n = sum(p.numel() for p in ps)
+        from .dist import flat_layout
+        self._offsets, n = flat_layout(ps)                      # every tensor starts on a 256-byte boundary; the gaps hold zeros
         self._n = n
         pad = 0
-        self.flat_params = torch.empty(n + pad, device=dev)
-        off = 0
-        for p in ps:
+        self.flat_params = torch.zeros(n, device=dev)
+        for p, off in zip(ps, self._offsets):
             self.flat_params[off:off + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.flat_params[off:off + p.numel()].view_as(p)
-            off += p.numel()
         if bucket is not None:
-            if [id(p) for p in bucket.params] != [id(p) for p in ps]:
+            if [id(p) for p in bucket.params] != [id(p) for p in ps] or list(bucket.offsets) != list(self._offsets):
                 raise ValueError("FusedAdam: the gradient bucket must hold the same parameters in the same order")
             self.flat_grads = bucket.flat
         else:
-            self.flat_grads = torch.zeros(n + pad, device=dev)
-            off = 0
-            for p in ps:
+            self.flat_grads = torch.zeros(n, device=dev)
+            for p, off in zip(ps, self._offsets):
                 p.grad = self.flat_grads[off:off + p.numel()].view_as(p)
-                off += p.numel()
         self.exp_avg = torch.zeros(n + pad, device=dev)
         self.exp_avg_sq = torch.zeros(n + pad, device=dev)
         self._step = 0
@@ -153,12 +150,10 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _publish_state(self):
         """torch.optim.Adam's per-parameter state layout, as views of the flat moments (so state_dict() is interchangeable)."""
-        off = 0
-        for p in self.param_groups[0]["params"]:
+        for p, off in zip(self.param_groups[0]["params"], self._offsets):
             k = p.numel()
             self.state[p] = {"step": torch.tensor(float(self._step)), "exp_avg": self.exp_avg[off:off + k].view_as(p),
                              "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p)}
-            off += k
 
     def zero_grad(self, set_to_none: bool = False):
         self.flat_grads.zero_()                                 # one memset; the views stay in place
@@ -187,8 +182,8 @@ class FusedAdam(torch.optim.Optimizer):
     def load_state_dict(self, state_dict):
         """Accepts torch.optim.Adam's state dict (the checkpoints' "optim_state", talker_trainer.py:932) and this class's own."""
         super().load_state_dict(state_dict)                     # replaces self.state[p] tensors by loaded copies ...
-        off, step = 0, 0
-        for p in self.param_groups[0]["params"]:
+        step = 0
+        for p, off in zip(self.param_groups[0]["params"], self._offsets):
             st = self.state.get(p, {})
             k = p.numel()
             if "exp_avg" in st:                                 # ... which go back into the flat buffers
@@ -198,7 +193,6 @@ class FusedAdam(torch.optim.Optimizer):
             else:
                 self.exp_avg[off:off + k].zero_()
                 self.exp_avg_sq[off:off + k].zero_()
-            off += k
         self._step = step
         self._publish_state()
 

@@ -26,7 +26,8 @@ def _worker(rank, world, port, ret):
     lo, hi = hn.dist.shard_range(8, rank, world)
     bucket.zero()
     lin(xs[lo:hi]).pow(2).sum().backward()                 # accumulates INTO the bucket views
-    flat = bucket.all_reduce(average=False).clone()
+    bucket.all_reduce(average=False)
+    flat = bucket.compact()
     # reference: single-process gradient over the full batch
     ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
     ref.load_state_dict(lin.state_dict())
@@ -107,6 +108,7 @@ def test_grad_bucket_early_range_layout():
     hn = importlib.import_module("nerf-3dtalker-code_b200")
     a, b, c = (torch.nn.Parameter(torch.randn(n)) for n in (3, 5, 7))
     bucket = hn.dist.GradBucket([a, b, c], early=[c])
-    assert bucket.params[0] is c and bucket.n_early == 7 and bucket.flat.numel() == 15
-    assert c.grad.data_ptr() == bucket.flat.data_ptr()
+    assert bucket.params[0] is c and bucket.n_early == 64 and bucket.offsets == [0, 64, 128] and bucket.flat.numel() == 192
+    assert c.grad.data_ptr() == bucket.flat.data_ptr() and bucket.compact().numel() == 15
+    assert all(p.grad.data_ptr() % 256 == 0 for p in (a, b, c))          # every tensor starts on a 256-byte boundary
     bucket.all_reduce_early(); bucket.all_reduce()              # no process group: no-ops

@@ -8,6 +8,7 @@ hn = importlib.import_module("nerf-3dtalker-code_b200")
 dev = "cuda:0"
 opt = O.OracleOptions(featmap_size=64, pred_img_size=512)
 net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": 64, "featmap_nc": 256, "pred_img_size": 512}), False, False).to(dev)
+net.precision = "fast"
 x = {k: v.to(dev) for k, v in O.synthetic_inputs(opt, 2, seed=0).items()}
 for need_grad in (False, True):
     xs = {k: v.clone().requires_grad_(need_grad and k == "shape_code") for k, v in x.items()}

@@ -11,6 +11,7 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "infer"
 dev = "cuda:0"
 opt = O.OracleOptions(featmap_size=64, pred_img_size=512)
 net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": 64, "featmap_nc": 256, "pred_img_size": 512}), False, False).to(dev)
+net.precision = "fast"
 x = {k: v.to(dev) for k, v in O.synthetic_inputs(opt, 2, seed=0).items()}
 with (torch.no_grad() if mode == "infer" else contextlib.nullcontext()):
     for _ in range(3):
