@@ -4,10 +4,14 @@
 // (contraction over the 128 sample rows of a block), so nothing is transposed or re-laid-out.
 //
 // Work item = (layer, 128-channel chunk of dZ, batch item, sample split).  A CTA accumulates the item's
-// [128 x K_in] slice of dW in TMEM over all its tiles, plus a 16-column "ones" product that yields the
-// bias gradient (= per-item column sums of dZ, from which the host derives the latent-code and folded
-// weight-column gradients), then flushes once with atomic adds.  The density head rides along as a
-// one-channel pseudo layer (its gradient block is written by hn_mlp_bwd_data).
+// [128 x K_in] slice of dW in TMEM over all its tiles and flushes it once with atomic adds.  While the tensor
+// core works through a stage, the four otherwise idle flush warps read the same shared-memory stage on the
+// CUDA cores: the column sums of dZ (= the bias gradient, per item, from which the host derives the
+// latent-code and folded weight-column gradients) and, in RGB_layer_0's items, the density head's weight
+// gradient sum_m dsigma_m * h7_m (h7 is RGB_layer_0's layer input, already in shared memory) - no ones-operand
+// MMAs, no separate pass over h7.  [Round 1 spent 17 % of the MMA time on N = 16 bias products and re-read
+// h7 (6 blocks per tile) for a one-row "density pseudo layer"; that layer survives only as the fallback when
+// RGB_layer_0's own weight gradient is not requested.]
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -22,20 +26,36 @@
 
 namespace hn {
 
-constexpr int kWStages = 3;
-constexpr int kHalfBytes = kUnitBytes / 2;                  // 64 sample rows of a block
+// A ring stage holds kPieceRows sample rows of every operand block of the item: 64 rows x 3 stages by default.  32-row stages (6 of
+// them, HN_WPIECES=4) keep five sixths instead of two thirds of the ring in flight, but were measured much SLOWER on B200 (3.0 vs
+// 1.79 ms): a stage costs ~1500 cycles of producer / barrier / commit latency almost whatever it carries, so halving it doubles that.
+#ifndef HN_WPIECES
+#define HN_WPIECES 2
+#endif
+constexpr int kWPieces = HN_WPIECES;                         // stages per 128-sample tile: 2 or 4
+constexpr int kPieceRows = 128 / kWPieces;
+constexpr int kWKSteps = kPieceRows / 16;                    // MMA K steps (16 samples) per stage
+constexpr int kWStages = 3 * kWPieces / 2;
+constexpr int kHalfBytes = kUnitBytes / kWPieces;            // bytes of one operand block's share of a stage (8 KiB or 4 KiB)
 constexpr int kWMaxX = 7;
-constexpr uint32_t kWStageBytes = (2 + kWMaxX) * kHalfBytes;  // 72 KiB
+constexpr uint32_t kWStageBytes = (2 + kWMaxX) * kHalfBytes;  // 72 KiB / 36 KiB
+// Where the bias gradient (column sums of dZ) comes from: 0 = the CUDA-core readers, 1 = a 16-column "ones" product of the tensor core
+// (round 1's way: one more read of the A operand per K step, but no LSU traffic on the operand stage), 2 = readers with half-precision
+// partial sums over the 8 rows a thread owns.  Measured on B200 (Reso64 batch 2): see DESIGN.md.
+#ifndef HN_WBIAS
+#define HN_WBIAS 1
+#endif
 constexpr uint32_t kWOffOnes = kWStages * kWStageBytes;
 constexpr uint32_t kWgradSmem = kWOffOnes + 2048 + 1024;
-constexpr int kWThreads = 192;                              // warp 0 producer, warp 1 MMA (+TMEM alloc), warps 2..5 flush
 constexpr uint32_t kBiasCol = 448;
+constexpr int kWThreads = 192;                              // warp 0 producer, warp 1 MMA (+TMEM alloc), warps 2..5 readers + flush
+constexpr int kWReaders = 128;
 #ifndef HN_WPREFETCH
 #define HN_WPREFETCH 0
 #endif
 constexpr int kWPrefetch = HN_WPREFETCH;                    // L2 prefetch distance in 64-sample stages.  0 = off: measured SLOWER with it (2.24 ms at 4 stages, 2.39 at 8,
                                                             // 2.63 at 32, against 2.11 without) - the memory system is already saturated
-constexpr int kWProd = 5;                                   // producer lanes (see the producer role)
+constexpr int kWProd = kWPieces == 2 ? 5 : 9;               // producer lanes (see the producer role): one per copy of a stage at 32-row stages
 
 struct WItem {
     int16_t w_idx;            // destination weight (index into dw[]), -1: none
@@ -50,10 +70,15 @@ struct WItem {
     int16_t x_valid[kWMaxX];  // valid columns (64, or 63 for the PE block)
     int32_t b;                // batch item
     int32_t tile0, tile1;     // tile range [tile0, tile1)
+    int16_t dens;             // 0: none; 1: density-head weight gradient over X blocks dens_x0, dens_x0 + 1; 2: ... and its bias gradient
+    int16_t dens_x0;
+    int32_t dens_blk;         // block of the density head's gradient column in `grads`
 };
 
 struct WShared {
     uint64_t full[kWStages], empty[kWStages], acc_full, acc_empty;
+    float dsr[kWStages][kPieceRows];  // density head: dL/d(pre-ReLU density) of the stage's samples (loss-scaled)
+    int reader_quit;          // set by a reader whose wait failed; read by all readers behind a barrier (uniform exit: no hung bar.sync)
     uint32_t tmem_base;
     volatile int abort;
 };
@@ -78,6 +103,18 @@ struct WArgs {
     int* status;
 };
 
+// `count` arrivals at once on a barrier of this CTA
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+// arrival on the same barrier in CTA `rank` of the cluster, default (CTA-scope release) semantics as in the multicast pipelines of
+// the vendor libraries: the readers' shared-memory loads have returned before the named barrier that precedes this call
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t rank) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(bar, rank)) : "memory");
+}
+
+__device__ __forceinline__ void reader_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWReaders) : "memory"); }
+
 // CL = 1: one CTA per work item.  CL = 3: a cluster of three CTAs works on the three 128-channel chunks of ONE layer over the
 // same samples; every X (layer-input) block is fetched from L2 once per cluster and multicast into all three CTAs' shared
 // memory, which halves the L2->SM traffic that bounds this kernel (~35 B/cycle/SM ingest).
@@ -92,16 +129,20 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
     if (tid == 0) {
-        for (int i = 0; i < kWStages; ++i) { mbar_init(smem_u32(&sh.full[i]), 1); mbar_init(smem_u32(&sh.empty[i]), CL); }
+        // a stage is released by the MMAs of every CTA of the cluster (their commits are multicast) and by every CTA's readers
+        for (int i = 0; i < kWStages; ++i) { mbar_init(smem_u32(&sh.full[i]), 1); mbar_init(smem_u32(&sh.empty[i]), 2 * CL); }
         mbar_init(smem_u32(&sh.acc_full), 1);
         mbar_init(smem_u32(&sh.acc_empty), 128);
         sh.abort = 0;
+        sh.reader_quit = 0;
         mbar_fence_init();
     }
+#if HN_WBIAS == 1
     // "ones" operand: 16 rows x 64 samples of 1.0h (K-major image; every element equal, so swizzling is moot)
     for (int i = tid; i < 2048 / 4; i += kWThreads)
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem + kWOffOnes + i * 4), "r"(0x3C003C00u) : "memory");
     fence_async_smem();
+#endif
     if (warp == 1) tmem_alloc<512>(smem_u32(&sh.tmem_base));
     tc_fence_before_sync();
     __syncthreads();
@@ -123,7 +164,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                 const uint8_t* gsrc = w.g_dfeat ? a.dfeat_image : a.grads;
                 const uint32_t bytes = (2 + w.n_x) * kHalfBytes;
                 for (int tile = w.tile0; tile < w.tile1; ++tile) {
-                    for (int half = 0; half < 2; ++half, ++sc) {
+                    for (int half = 0; half < kWPieces; ++half, ++sc) {
                         const uint32_t stage = sc % kWStages, par = (sc / kWStages) & 1;
                         if (!wwait(&sh.empty[stage], par ^ 1, &sh.abort, a.status, 701)) break;
                         const uint32_t fb = smem_u32(&sh.full[stage]);
@@ -135,8 +176,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                         const uint32_t dst = smem + stage * kWStageBytes;
                         // the same pieces kWPrefetch stages ahead are pulled DRAM -> L2 now: shared memory holds only three stages, far
                         // too few bytes in flight to cover DRAM latency, but L2 has room for dozens
-                        const int ahead = 2 * (tile - w.tile0) + half + kWPrefetch;
-                        const int pf_tile = w.tile0 + (ahead >> 1), pf_half = ahead & 1;
+                        const int ahead = kWPieces * (tile - w.tile0) + half + kWPrefetch;
+                        const int pf_tile = w.tile0 + ahead / kWPieces, pf_half = ahead % kWPieces;
                         const bool pf = kWPrefetch > 0 && pf_tile < w.tile1;
                         int j = 0;
                         for (int k = 0; k < 2; ++k)
@@ -164,19 +205,22 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
         // in descriptor units), and the block loop is resolved per item into at most two MMAs of fixed N.
         if (lane == 0) {
             uint32_t sc = 0, n_item = 0;
+#if HN_WBIAS == 1
             const uint32_t idesc_bias = umma_idesc(128, 16, kF16, kF16, 1, 0);
             const uint32_t ones_lo = desc_lo(smem + kWOffOnes, 16);
+#endif
             for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
                 const WItem w = a.items[it * CL + rank];
                 if (w.tile1 <= w.tile0) continue;
                 bool ok = wwait(&sh.acc_empty, (n_item & 1) ^ 1, &sh.abort, a.status, 710);
                 ++n_item;
+                const bool reading = w.dens || (HN_WBIAS != 1 && w.bias_off >= 0 && a.dbias != nullptr);   // (same predicate in the reader role)
                 const int n1 = w.n_x < 4 ? w.n_x : 4, n2 = w.n_x - n1;              // X blocks of the first / second MMA
                 const uint32_t idesc1 = umma_idesc(128, (uint32_t)(n1 > 0 ? n1 : 1) * 64, kF16, kF16, 1, 1);
                 const uint32_t idesc2 = umma_idesc(128, (uint32_t)(n2 > 0 ? n2 : 1) * 64, kF16, kF16, 1, 1);
                 uint32_t first = 0;                                                   // accumulate flag of the item's first K step
                 for (int tile = w.tile0; tile < w.tile1 && ok; ++tile) {
-                    for (int half = 0; half < 2; ++half, ++sc) {
+                    for (int half = 0; half < kWPieces; ++half, ++sc) {
                         const uint32_t stage = sc % kWStages, par = (sc / kWStages) & 1;
                         ok = wwait(&sh.full[stage], par, &sh.abort, a.status, 711);
                         if (!ok) break;
@@ -186,32 +230,157 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                         const uint32_t g_lo = desc_lo(g_addr, kHalfBytes);
                         const uint32_t x_lo = desc_lo(g_addr + 2 * kHalfBytes, kHalfBytes), x2_lo = desc_lo(g_addr + 6 * kHalfBytes, kHalfBytes);
 #pragma unroll
-                        for (uint32_t ks = 0; ks < 4; ++ks) {
+                        for (uint32_t ks = 0; ks < (uint32_t)kWKSteps; ++ks) {
                             const uint32_t acc = ks == 0 ? first : 1u;
                             if (n1 > 0) umma_f16_lohi(tmem_base, g_lo + ks * 128, x_lo + ks * 128, idesc1, acc);
                             if (n2 > 0) umma_f16_lohi(tmem_base + 256, g_lo + ks * 128, x2_lo + ks * 128, idesc2, acc);
-#if HN_WEXP != 4
-                            umma_f16_lohi(tmem_base + kBiasCol, g_lo + ks * 128, ones_lo + ks * 2, idesc_bias, acc);
+#if HN_WBIAS == 1
+                            if (w.bias_off >= 0) umma_f16_lohi(tmem_base + kBiasCol, g_lo + ks * 128, ones_lo + ks * 2, idesc_bias, acc);
 #endif
                         }
 #endif
                         first = 1;
                         if (CL == 1) umma_commit(smem_u32(&sh.empty[stage]));
                         else umma_commit_multicast(smem_u32(&sh.empty[stage]), kMask);     // a stage is refilled by all peers: all must release it
+                        if (!reading) mbar_arrive_n(smem_u32(&sh.empty[stage]), (uint32_t)CL);   // no reader touches this item's stages: their share of the release
                     }
                 }
                 umma_commit(smem_u32(&sh.acc_full));
             }
         }
     } else {
-        // ======================= flush: TMEM -> atomic adds into dW / dbias =======================
+        // ======================= readers (CUDA-core side sums over the staged operands), then flush =======================
+        // 128 threads.  Thread -> (hb: which 64-column block of the 128-channel chunk, c8: which 16-byte chunk of the 128-byte
+        // row, sg: which 8 of the stage's 64 sample rows); a quarter warp covers the eight chunks of one row, so the 128-bit
+        // shared-memory loads are conflict-free in the swizzled image.
+        const int rt = tid - 64;                                   // 0..127
+        const int rw = rt >> 5;
+        const int hb = rw & 1, c8 = lane & 7, sg = (lane >> 3) + 4 * (rw >> 1);
         const int row = (warp & 3) * 32 + lane;                    // TMEM lane (a warp may only read its own quarter) = dW row in the chunk
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float inv_scale = 1.0f / __ldg(a.grad_scale);
-        uint32_t n_item = 0;
-        for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
+        uint32_t n_item = 0, sc = 0;
+        bool quit = false;
+        for (int it = item0; it < a.n_items && !quit; it += item_stride) {       // (no per-thread abort test here: the exit must be uniform)
             const WItem w = a.items[it * CL + rank];
             if (w.tile1 <= w.tile0) continue;
+            float bsum[8], dsum[8], dsr_acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; dsum[j] = 0.f; }
+            const bool want_bias = (w.bias_off >= 0 && a.dbias != nullptr);
+            const bool read_bias = want_bias && HN_WBIAS != 1;
+            const bool reading = w.dens || read_bias;
+            if (!reading) sc += (uint32_t)kWPieces * (uint32_t)(w.tile1 - w.tile0);    // the MMA thread releases these stages on the readers' behalf
+            for (int tile = w.tile0; tile < w.tile1 && !quit && reading; ++tile) {
+                for (int half = 0; half < kWPieces; ++half, ++sc) {
+                    const uint32_t stage = sc % kWStages, par = (sc / kWStages) & 1;
+                    if (w.dens && rt < kPieceRows) {
+                        // dL/d(pre-ReLU density) of sample rt of this stage: column 0 of the density gradient block (fetched while
+                        // the stage's bulk copies are still in flight)
+                        const int r = half * kPieceRows + rt;
+                        const __half hv = *reinterpret_cast<const __half*>(a.grads + ((size_t)w.dens_blk * a.n_tiles + tile) * kUnitBytes + image_offset((uint32_t)r, 0u));
+                        const float v = __half2float(hv);
+                        sh.dsr[stage][rt] = v;
+                        dsr_acc += v;
+                    }
+                    // ONE thread polls the stage's barrier (with a pause: every mbarrier operation of the CTA goes through one unit, and
+                    // the MMA issuer's own waits must not queue behind 128 pollers - a try_wait per reader thread and stage was measured:
+                    // 4.2 ms instead of 1.85); the others join at the named barrier, which orders their reads behind its observation
+                    if (rt == 0) {
+                        const uint32_t fb = smem_u32(&sh.full[stage]);
+                        bool got = mbar_try_wait(fb, par);
+                        const long long t0 = clock64();
+                        while (!got) {
+                            __nanosleep(32);
+                            got = mbar_try_wait(fb, par);
+                            if (!got && (sh.abort || clock64() - t0 > 2000000000ll)) { sh.abort = 1; atomicCAS(a.status, 0, 730); break; }
+                        }
+                        if (!got) sh.reader_quit = 1;
+                    }
+                    reader_sync();                                 // the stage's dsr values and the quit flag are visible to all readers
+                    quit = sh.reader_quit != 0;                    // (written only before this barrier: every reader sees the same value)
+#if HN_WEXP != 8                                                   // diagnostic build 8: no reader arithmetic
+                    constexpr int RPT = kPieceRows / 8;            // sample rows per reader thread and stage
+                    const uint32_t st_base = smem + stage * kWStageBytes;
+                    auto row_off = [&](int i) -> uint32_t {        // byte offset of this thread's 16-byte chunk of its i-th row (swizzled image)
+                        const uint32_t r = (uint32_t)(sg * RPT + i);
+                        return (r >> 3) * 1024u + (r & 7u) * 128u + (((uint32_t)c8 ^ (r & 7u)) << 4);
+                    };
+                    if (read_bias && !quit) {
+                        const uint32_t gb = st_base + (uint32_t)hb * kHalfBytes;
+#if HN_WBIAS == 2
+                        __half2 h0 = __float2half2_rn(0.f), h1 = h0, h2 = h0, h3 = h0;
+#pragma unroll
+                        for (int i = 0; i < RPT; ++i) {
+                            const uint4 q = ld_shared_v4(gb + row_off(i));
+                            h0 = __hadd2(h0, *reinterpret_cast<const __half2*>(&q.x)); h1 = __hadd2(h1, *reinterpret_cast<const __half2*>(&q.y));
+                            h2 = __hadd2(h2, *reinterpret_cast<const __half2*>(&q.z)); h3 = __hadd2(h3, *reinterpret_cast<const __half2*>(&q.w));
+                        }
+                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+                        bsum[0] += f0.x; bsum[1] += f0.y; bsum[2] += f1.x; bsum[3] += f1.y; bsum[4] += f2.x; bsum[5] += f2.y; bsum[6] += f3.x; bsum[7] += f3.y;
+#else
+#pragma unroll
+                        for (int i = 0; i < RPT; ++i) {
+                            const uint4 q = ld_shared_v4(gb + row_off(i));
+                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+                            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+                            bsum[0] += f0.x; bsum[1] += f0.y; bsum[2] += f1.x; bsum[3] += f1.y; bsum[4] += f2.x; bsum[5] += f2.y; bsum[6] += f3.x; bsum[7] += f3.y;
+                        }
+#endif
+                    }
+                    if (w.dens && !quit) {
+                        const uint32_t xb = st_base + (uint32_t)(2 + w.dens_x0 + hb) * kHalfBytes;
+#pragma unroll
+                        for (int i = 0; i < RPT; ++i) {
+                            const float ds = sh.dsr[stage][sg * RPT + i];
+                            const uint4 q = ld_shared_v4(xb + row_off(i));
+                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+                            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
+                            dsum[0] = fmaf(ds, f0.x, dsum[0]); dsum[1] = fmaf(ds, f0.y, dsum[1]); dsum[2] = fmaf(ds, f1.x, dsum[2]); dsum[3] = fmaf(ds, f1.y, dsum[3]);
+                            dsum[4] = fmaf(ds, f2.x, dsum[4]); dsum[5] = fmaf(ds, f2.y, dsum[5]); dsum[6] = fmaf(ds, f3.x, dsum[6]); dsum[7] = fmaf(ds, f3.y, dsum[7]);
+                        }
+                    }
+#endif
+                    // every reader is done with the stage: one thread releases it in every CTA of the cluster (peers multicast
+                    // layer-input blocks into this CTA's stage, so their producers must see this CTA's readers too)
+                    reader_sync();
+                    if (quit) break;
+                    // Release.  Only the density items read blocks that PEER CTAs multicast into this stage (layer inputs); every
+                    // other item reads its own dZ blocks only, so its CL reader arrivals can all be local - a remote release-arrive
+                    // costs a cluster-scope fence (three of them from one thread per stage took the kernel from 1.85 to 4.1 ms).
+                    if (CL == 1 || !w.dens) {
+                        if (rt == 0) mbar_arrive_n(smem_u32(&sh.empty[stage]), (uint32_t)CL);
+                    } else if (rt < CL) {
+                        mbar_arrive_remote_relaxed(smem_u32(&sh.empty[stage]), (uint32_t)rt);     // one thread per peer, in parallel
+                    }
+                }
+            }
+            // ---- side sums: fold the four sample groups of a warp, then one atomic per column and warp
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bsum[j] += __shfl_xor_sync(0xffffffffu, bsum[j], 8); bsum[j] += __shfl_xor_sync(0xffffffffu, bsum[j], 16);
+                dsum[j] += __shfl_xor_sync(0xffffffffu, dsum[j], 8); dsum[j] += __shfl_xor_sync(0xffffffffu, dsum[j], 16);
+            }
+            if (lane < 8) {
+                const int ch = hb * 64 + c8 * 8;                    // first of this lane's eight channels / layer-input columns
+                if (read_bias) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (ch + j < w.rows) atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + w.bias_off + ch + j, bsum[j] * inv_scale);
+                }
+                if (w.dens && a.dw[W_DENSITY]) {
+                    float* dst = a.dw[W_DENSITY] + w.x_col[w.dens_x0 + hb] + c8 * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) atomicAdd(dst + j, dsum[j] * inv_scale);
+                }
+            }
+            if (w.dens == 2 && rt < 64 && a.dbias) {                 // (threads kPieceRows..63 hold zeros)
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) dsr_acc += __shfl_xor_sync(0xffffffffu, dsr_acc, sft);
+                if (lane == 0) atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + HN_BIAS_OFF_DENSITY, dsr_acc * inv_scale);
+            }
+            if (quit) break;
+            // ---- flush: TMEM -> atomic adds into dW
             wwait(&sh.acc_full, n_item & 1, &sh.abort, a.status, 720);
             ++n_item;
             tc_fence_after_sync();
@@ -231,13 +400,15 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                     }
                 }
             }
+#if HN_WBIAS == 1
             {
                 uint32_t v[32];                                   // bias columns (all 16 equal); x32 load stays inside the 512 columns
                 tmem_ld32(tmem_base + lane_base + kBiasCol, v);
                 tmem_ld_wait();
-                if (row_ok && w.bias_off >= 0 && a.dbias)
+                if (row_ok && want_bias)
                     atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + w.bias_off + row, __uint_as_float(v[0]) * inv_scale);
             }
+#endif
             tc_fence_before_sync();
             mbar_arrive(smem_u32(&sh.acc_empty));
         }
@@ -249,177 +420,20 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
     if (warp == 1) tmem_free<512>(tmem_base);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// CTA-pair variant for the 384 x 384 layers (cta_group::2, M = 256): the pair accumulates the dW rows of chunks 0 and 1 of ONE
-// layer over the same samples.  CTA r loads its own dZ chunk and only HALF of the layer-input columns (X blocks 2r, 2r+1 and
-// 4+r): the tensor core reads the B operand's halves from both SMs, so 40 KiB instead of 64 KiB land in each SM's shared memory
-// per 64-sample stage.  Chunk 2 of those layers has no partner (384 = 256 + 128) and stays on the single-CTA kernel.
-// EXPERIMENT, opt-in with HN_WGRAD_PAIRS=1: correct, but slower than the 3-CTA multicast clusters (see hn_mlp_bwd_weights).
-constexpr int kPairStages = 5;
-constexpr uint32_t kPairStageBytes = 5 * kHalfBytes;          // dZ chunk (2 half-blocks) + 3 X half-blocks = 40 KiB
-constexpr uint32_t kPairOffOnes = kPairStages * kPairStageBytes;
-constexpr uint32_t kPairSmem = kPairOffOnes + 2048 + 1024;
-
-struct WPairShared {
-    uint64_t full[kPairStages], peer_full[kPairStages], empty[kPairStages], acc_full, acc_empty;
-    uint32_t tmem_base;
-    volatile int abort;
-};
-
-__device__ __forceinline__ bool wwait_cluster(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
-    const uint32_t b = smem_u32(bar);
-    if (mbar_try_wait_cluster(b, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(b, parity)) {
-        if (*abort_flag) return false;
-        if (clock64() - t0 > 2000000000ll) { *abort_flag = 1; atomicCAS(status, 0, code); return false; }
-    }
-    return true;
-}
-
-__global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_pair_kernel(const WArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ WPairShared sh;
-    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int item0 = (int)blockIdx.x >> 1, item_stride = (int)gridDim.x >> 1;
-
-    if (tid == 0) {
-        for (int i = 0; i < kPairStages; ++i) { mbar_init(smem_u32(&sh.full[i]), 1); mbar_init(smem_u32(&sh.peer_full[i]), 1); mbar_init(smem_u32(&sh.empty[i]), 1); }
-        mbar_init(smem_u32(&sh.acc_full), 1);
-        mbar_init(smem_u32(&sh.acc_empty), 256);                  // the flush threads of BOTH CTAs release the leader's issuer
-        sh.abort = 0;
-        mbar_fence_init();
-    }
-    for (int i = tid; i < 2048 / 4; i += kWThreads)
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem + kPairOffOnes + i * 4), "r"(0x3C003C00u) : "memory");
-    fence_async_smem();
-    if (warp == 1) tmem_alloc_pair<512>(smem_u32(&sh.tmem_base));
-    tc_fence_before_sync();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = sh.tmem_base;
-
-    if (warp == 0) {
-        // ======================= producer (both CTAs): own dZ chunk + own half of the X columns =======================
-        if (lane == 0) {
-            uint32_t sc = 0;
-            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
-                const WItem w = a.items[it];
-                const int xb[3] = {w.x_blk[2 * rank], w.x_blk[2 * rank + 1], w.x_blk[4 + rank]};
-                for (int tile = w.tile0; tile < w.tile1; ++tile) {
-                    for (int half = 0; half < 2; ++half, ++sc) {
-                        const uint32_t stage = sc % kPairStages, par = (sc / kPairStages) & 1;
-                        if (!wwait_cluster(&sh.empty[stage], par ^ 1, &sh.abort, a.status, 741)) break;
-                        const uint32_t fb = smem_u32(&sh.full[stage]);
-                        mbar_arrive_expect_tx(fb, kPairStageBytes);
-                        const uint32_t dst = smem + stage * kPairStageBytes;
-                        for (int k = 0; k < 2; ++k)
-                            bulk_g2s(dst + k * kHalfBytes, a.grads + ((size_t)(w.g_blk + 2 * rank + k) * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
-                        for (int k = 0; k < 3; ++k)
-                            bulk_g2s(dst + (2 + k) * kHalfBytes, a.act + ((size_t)xb[k] * a.n_tiles + tile) * kUnitBytes + half * kHalfBytes, kHalfBytes, fb);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 1) {
-            // ======================= peer: relay "my stage has landed" to the leader =======================
-            uint32_t sc = 0;
-            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride) {
-                const WItem w = a.items[it];
-                for (int n = 2 * (w.tile1 - w.tile0); n > 0; --n, ++sc) {
-                    const uint32_t stage = sc % kPairStages, par = (sc / kPairStages) & 1;
-                    if (!wwait(&sh.full[stage], par, &sh.abort, a.status, 750)) break;
-                    mbar_arrive_cluster(smem_u32(&sh.peer_full[stage]), 0);
-                }
-            }
-        } else if (lane == 0) {
-            // ======================= leader: MMA issuer =======================
-            uint32_t sc = 0, n_item = 0;
-            const uint32_t idesc1 = umma_idesc(256, 256, kF16, kF16, 1, 1), idesc2 = umma_idesc(256, 128, kF16, kF16, 1, 1);
-            const uint32_t idesc_bias = umma_idesc(256, 16, kF16, kF16, 1, 0);
-            for (int it = item0; it < a.n_items && !sh.abort; it += item_stride, ++n_item) {
-                const WItem w = a.items[it];
-                bool ok = wwait_cluster(&sh.acc_empty, (n_item & 1) ^ 1, &sh.abort, a.status, 742);
-                bool first = true;
-                for (int tile = w.tile0; tile < w.tile1 && ok; ++tile) {
-                    for (int half = 0; half < 2; ++half, ++sc) {
-                        const uint32_t stage = sc % kPairStages, par = (sc / kPairStages) & 1;
-                        ok = wwait(&sh.full[stage], par, &sh.abort, a.status, 743);
-                        if (ok) ok = wwait_cluster(&sh.peer_full[stage], par, &sh.abort, a.status, 744);
-                        if (!ok) break;
-                        tc_fence_after_sync();
-                        const uint32_t g_addr = smem + stage * kPairStageBytes;
-                        const uint32_t x_addr = g_addr + 2 * kHalfBytes;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t ad = umma_desc_mnmajor(g_addr, ks, kHalfBytes);
-                            const bool acc = !(first && ks == 0);
-                            umma_f16_pair(tmem_base, ad, umma_desc_mnmajor(x_addr, ks, kHalfBytes), idesc1, acc);
-                            umma_f16_pair(tmem_base + 256, ad, umma_desc_mnmajor(x_addr + 2 * kHalfBytes, ks, kHalfBytes), idesc2, acc);
-                            umma_f16_pair(tmem_base + kBiasCol, ad, umma_desc_kmajor(smem + kPairOffOnes, ks), idesc_bias, acc);
-                        }
-                        first = false;
-                        umma_commit_pair(smem_u32(&sh.empty[stage]));          // both CTAs' stages are free once these MMAs retire
-                    }
-                }
-                umma_commit_pair(smem_u32(&sh.acc_full));
-            }
-        }
-    } else {
-        // ======================= flush (both CTAs): own 128 rows of the pair's accumulator =======================
-        const int row = (warp & 3) * 32 + lane;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        const float inv_scale = 1.0f / __ldg(a.grad_scale);
-        uint32_t n_item = 0;
-        for (int it = item0; it < a.n_items && !sh.abort; it += item_stride, ++n_item) {
-            const WItem w = a.items[it];
-            wwait_cluster(&sh.acc_full, n_item & 1, &sh.abort, a.status, 745);
-            tc_fence_after_sync();
-            float* dw = (w.w_idx >= 0) ? a.dw[w.w_idx] : nullptr;
-            for (int k = 0; k < 6; ++k) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + k * 64 + h * 32, v);
-                    tmem_ld_wait();
-                    if (dw) {
-                        float* dst = dw + (size_t)(w.row0 + 128 * rank + row) * a.ld[w.w_idx] + w.x_col[k] + h * 32;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]) * inv_scale);
-                    }
-                }
-            }
-            {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_base + kBiasCol, v);
-                tmem_ld_wait();
-                if (w.bias_off >= 0 && a.dbias)
-                    atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + w.bias_off + 128 * rank + row, __uint_as_float(v[0]) * inv_scale);
-            }
-            tc_fence_before_sync();
-            mbar_arrive_cluster(smem_u32(&sh.acc_empty), 0);
-        }
-    }
-
-    tc_fence_before_sync();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 1) tmem_free_pair<512>(tmem_base);
-}
-
 static std::mutex g_w_mu;
 static bool g_w_ready[64] = {};
 
-// host: enumerate work items.  `cluster` = items for the 3-CTA multicast kernel (three consecutive entries = the three
-// 128-channel chunks of one layer over one sample range); `single` = everything else.
-// `side` / n_side: single-CTA items for the SMs the resident 3-CTA clusters leave idle (148 - 3 * 45 = 13 on this part): they run on
-// a second stream while the cluster kernel runs, the rest of the single-CTA work (`single`) follows on all SMs.
-static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters, int n_pairs, int n_side, std::vector<WItem>& cluster,
-                        std::vector<WItem>& single, std::vector<WItem>& pairs, std::vector<WItem>& side) {
+// host: enumerate work items.
+//   cluster : items of the 3-CTA multicast kernel (three consecutive entries = the three 128-channel chunks of one 384-wide
+//             layer over one sample range);
+//   duo     : items of the 2-CTA multicast kernel (two consecutive entries = the two chunks of RGB_layer_1 (128 + 64 rows) or
+//             RGB_layer_2 (128 + 128) over one sample range) - each layer-input block is read from L2 once per pair instead of
+//             once per chunk;
+//   single  : everything else, one CTA per entry (bias-only passes, and all layers when clusters cannot be resident);
+//   side    : single-CTA items for the SMs the resident 3-CTA clusters leave idle (148 - 3 * 45 = 13 on this part): they run on a
+//             second stream while the cluster kernel runs.
+static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters, int n_duos, int n_side, std::vector<WItem>& cluster,
+                        std::vector<WItem>& single, std::vector<WItem>& duo, std::vector<WItem>& side) {
     const int tiles_per_item = (int)(((int64_t)a.n_rays * a.n_samples) / HN_TILE);
     bool want_w = false;
     for (int i = 0; i < 12; ++i) want_w = want_w || (a.dw[i] != nullptr);
@@ -431,24 +445,24 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     layers.push_back({W_R0, HN_HIDDEN, HN_GSLOT_R0, 0, HN_BIAS_OFF_R0, HN_SLOT_H0 + 6 * 7, 6, false, 0});
     layers.push_back({W_R1, HN_RGB1, HN_GSLOT_R1, 0, HN_BIAS_OFF_R1, HN_SLOT_R0, 6, false, 0});
     layers.push_back({W_R2, HN_FEAT, 0, 1, HN_BIAS_OFF_R2, HN_SLOT_X, 3, false, 0});
-    layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});   // density pseudo layer
+    // The density head's weight gradient rides in RGB_layer_0's items (same layer input h7, read by the CUDA-core readers) whenever
+    // that layer's own weight gradient is computed; otherwise it is a one-channel pseudo layer of its own.
+    // Opt-in (HN_WGRAD_DENS_FOLD=1): measured on B200, the readers slow RGB_layer_0's stages by more than the pseudo layer costs (cluster
+    // kernel 1.45 -> 1.79 ms against 0.095 ms for the separate density items), so the default keeps the pseudo layer.
+    static const bool fold_env = [] { const char* e = getenv("HN_WGRAD_DENS_FOLD"); return e && atoi(e) != 0; }();
+    const bool dens_in_r0 = fold_env && want_w && a.dw[W_R0] != nullptr && a.dw[W_DENSITY] != nullptr;
+    if (!dens_in_r0) layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});
     auto active = [&](const LayerW& L) { return want_w || a.want_all_bias || L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1; };
-    // CTA pairs: 384 x 384 layers (six hidden X blocks, no PE block); their chunk 2 goes to the single-CTA list
-    auto paired = [&](const LayerW& L) { return want_w && n_pairs > 0 && L.n_out == HN_HIDDEN && L.n_xblk == 6 && !L.pe && a.dw[L.w_idx] != nullptr; };
-    auto clustered = [&](const LayerW& L) { return !paired(L) && want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
-    // A unit = one layer (cluster list: its three chunks side by side) or one chunk (single list) of one batch item, over all of
+    auto clustered = [&](const LayerW& L) { return want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
+    auto duoed = [&](const LayerW& L) { return want_w && n_duos > 0 && (L.w_idx == W_R1 || L.w_idx == W_R2) && a.dw[L.w_idx] != nullptr; };
+    // A unit = one layer (cluster / duo lists: its chunks side by side) or one chunk (single list) of one batch item, over all of
     // the item's tiles, with a cost per tile ~ MMA cycles / operand bytes of a stage.  The units of a list are laid end to end and
-    // cut into one equal-cost share per worker (a 3-CTA cluster or a CTA): a worker gets one or two sample ranges, every worker
-    // finishes at the same time, and each accumulator is flushed (atomics) only once or twice.  [Equal sample splits per layer
-    // left 108 equal items for 45 resident clusters: a makespan of 3 items against a mean of 2.4.]
-    // Measured (no-MMA / no-load diagnostic builds, ncu): a stage takes ~2400 cycles almost regardless of how many operand
-    // blocks it carries - the kernel is bound by DRAM latency against the bytes three stages keep in flight, not by tensor or
-    // byte throughput - so a tile costs about the same whatever the layer width; the block count only adds a small slope.
+    // cut into one equal-cost share per worker (a cluster or a CTA): a worker gets one or two sample ranges, every worker
+    // finishes at the same time, and each accumulator is flushed (atomics) only once or twice.
     static const double slope = [] { const char* e = getenv("HN_WGRAD_SLOPE"); return e ? atof(e) : 40.0; }();   // tuning knob (cycles per operand block)
     auto stage_cost = [](int n_x) { return 1000.0 + slope * n_x; };
     struct Unit { std::vector<WItem> tmpl; int b; double cost; int t0, t1; };      // tiles [t0, t1) of batch item b
-    std::vector<Unit> units_c, units_s;
-    int layers_pair = 0;
+    std::vector<Unit> units_c, units_d, units_s;
     auto make_item = [&](const LayerW& L, int j, int b) {
         WItem w{};
         w.w_idx = (int16_t)((want_w && a.dw[L.w_idx]) ? L.w_idx : -1);
@@ -464,20 +478,24 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
             if (L.pe) { w.x_blk[n] = HN_SLOT_PE; w.x_col[n] = 0; w.x_valid[n] = HN_PE; ++n; }
         }
         w.n_x = (int16_t)n;
+        if (dens_in_r0 && L.w_idx == W_R0) {                        // chunk j covers h7 columns [128 j, 128 j + 128)
+            w.dens = (int16_t)(j == 0 ? 2 : 1);
+            w.dens_x0 = (int16_t)(2 * j);
+            w.dens_blk = HN_GSLOT_DENS;
+        }
         return w;
     };
     for (const LayerW& L : layers) {
         if (!active(L)) continue;
-        const bool cl = clustered(L), pr = paired(L);
-        if (pr) ++layers_pair;
+        const bool cl = clustered(L), du = !cl && duoed(L);
         for (int b = 0; b < a.B; ++b) {
-            if (cl) {
+            if (cl || du) {
                 Unit u; u.b = b; u.t0 = 0; u.t1 = tiles_per_item;
-                for (int j = 0; j < 3; ++j) u.tmpl.push_back(make_item(L, j, b));
+                for (int j = 0; j < (cl ? 3 : 2); ++j) u.tmpl.push_back(make_item(L, j, b));
                 u.cost = stage_cost(u.tmpl[0].n_x);
-                units_c.push_back(u);
+                (cl ? units_c : units_d).push_back(u);
             } else {
-                for (int j = pr ? 2 : 0; j * 128 < L.n_out; ++j) {
+                for (int j = 0; j * 128 < L.n_out; ++j) {
                     Unit u; u.b = b; u.t0 = 0; u.t1 = tiles_per_item;
                     u.tmpl.push_back(make_item(L, j, b));
                     u.cost = stage_cost(u.tmpl[0].n_x);
@@ -533,44 +551,32 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
                     out.push_back(j * group + r < lists[w].size() ? lists[w][j * group + r] : WItem{});
     };
     partition(units_c, n_clusters, 3, cluster);
-    if (n_side > 0 && !units_c.empty() && !units_s.empty()) {
-        // share of the single-CTA work that n_side SMs finish in about the time the cluster kernel takes (cost ~ stages)
-        double cost_c = 0, cost_s = 0;
+    if (n_side > 0 && !units_c.empty() && !units_d.empty()) {
+        // share of the two-chunk layers that n_side SMs finish, as single-CTA items, in about the time the cluster kernel takes
+        double cost_c = 0, cost_d = 0;
         for (const Unit& u : units_c) cost_c += u.cost * 3 * (u.t1 - u.t0);
-        for (const Unit& u : units_s) cost_s += u.cost * (u.t1 - u.t0);
+        for (const Unit& u : units_d) cost_d += u.cost * 2 * (u.t1 - u.t0);
         static const double tune = [] { const char* e = getenv("HN_WGRAD_SIDE"); return e ? atof(e) : 0.85; }();
-        double f = tune * (cost_c / (3.0 * n_clusters)) * n_side / cost_s;          // (time of the cluster phase) x n_side / (single work)
+        double f = tune * (cost_c / (3.0 * n_clusters)) * n_side / cost_d;          // (time of the cluster phase) x n_side / (duo work)
         f = f > 0.9 ? 0.9 : f;
         std::vector<Unit> first, rest;
-        for (const Unit& u : units_s) {
+        for (const Unit& u : units_d) {
             const int cut = u.t0 + (int)((u.t1 - u.t0) * f);
-            if (cut > u.t0) { Unit p = u; p.t1 = cut; first.push_back(p); }
+            if (cut > u.t0)
+                for (size_t j = 0; j < u.tmpl.size(); ++j) { Unit p; p.b = u.b; p.cost = u.cost; p.t0 = u.t0; p.t1 = cut; p.tmpl.push_back(u.tmpl[j]); first.push_back(p); }
             if (cut < u.t1) { Unit p = u; p.t0 = cut; rest.push_back(p); }
         }
         partition(first, n_side, 1, side);
-        partition(rest, n_sm, 1, single);
+        partition(rest, n_duos, 2, duo);
     } else {
-        partition(units_s, n_sm, 1, single);
+        partition(units_d, n_duos, 2, duo);
     }
-    // opt-in CTA-pair items (uniform sample splits)
-    if (layers_pair > 0) {
-        int sp = (2 * n_pairs + layers_pair * a.B - 1) / (layers_pair * a.B);
-        sp = sp < 1 ? 1 : (sp > tiles_per_item ? tiles_per_item : sp);
-        for (const LayerW& L : layers) {
-            if (!active(L) || !paired(L)) continue;
-            for (int b = 0; b < a.B; ++b)
-                for (int q = 0; q < sp; ++q) {
-                    WItem w = make_item(L, 0, b);
-                    w.tile0 = b * tiles_per_item + (int)((int64_t)tiles_per_item * q / sp);
-                    w.tile1 = b * tiles_per_item + (int)((int64_t)tiles_per_item * (q + 1) / sp);
-                    if (w.tile1 > w.tile0) pairs.push_back(w);
-                }
-        }
-    }
+    partition(units_s, n_sm, 1, single);
 }
 
-static int launch_wgrad(const WArgs& k, int cl, int grid, cudaStream_t st) {
-    if (cl == 1) {
+template <int CL>
+static int launch_wgrad(const WArgs& k, int grid, cudaStream_t st) {
+    if (CL == 1) {
         mlp_wgrad_kernel<1><<<grid, kWThreads, kWgradSmem, st>>>(k);
         return check_launch("hn_mlp_bwd_weights");
     }
@@ -578,15 +584,28 @@ static int launch_wgrad(const WArgs& k, int cl, int grid, cudaStream_t st) {
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kWThreads); cfg.dynamicSmemBytes = kWgradSmem; cfg.stream = st;
     cudaLaunchAttribute attr{};
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 3; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_wgrad_kernel<3>, k);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_wgrad_kernel<CL>, k);
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-    return check_launch("hn_mlp_bwd_weights (3-CTA clusters)");
+    return check_launch(CL == 3 ? "hn_mlp_bwd_weights (3-CTA clusters)" : "hn_mlp_bwd_weights (2-CTA clusters)");
+}
+
+template <int CL>
+static int resident_clusters(int n_sm) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL * (n_sm / CL)); cfg.blockDim = dim3(kWThreads); cfg.dynamicSmemBytes = kWgradSmem;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, mlp_wgrad_kernel<CL>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    return n;
 }
 
 static int g_w_clusters[64] = {};
-static int g_w_pairs[64] = {};
+static int g_w_duos[64] = {};
 static cudaStream_t g_w_side[64] = {};
 static cudaEvent_t g_w_fork[64] = {}, g_w_join[64] = {};
 
@@ -601,37 +620,20 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
         return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: items workspace missing or too small (hn_wgrad_workspace_bytes)");
     int dev = 0;
     cudaGetDevice(&dev);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     {
         std::lock_guard<std::mutex> lk(g_w_mu);
         if (dev < 64 && !g_w_ready[dev]) {
             cudaError_t e = cudaFuncSetAttribute(mlp_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
             if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-            // how many 3-CTA clusters can be resident at once (GPC sizes strand a few SMs)
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(3 * 49); cfg.blockDim = dim3(kWThreads); cfg.dynamicSmemBytes = kWgradSmem;
-            cudaLaunchAttribute attr{};
-            attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = 3; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-            cfg.attrs = &attr; cfg.numAttrs = 1;
-            int n = 0;
+            // how many clusters can be resident at once (GPC sizes strand a few SMs); HN_WGRAD_CLUSTERS=0 / HN_WGRAD_DUOS=0: single-CTA items only
             const char* env = getenv("HN_WGRAD_CLUSTERS");
-            if (env && atoi(env) == 0) n = 0;
-            else if (cudaOccupancyMaxActiveClusters(&n, mlp_wgrad_kernel<3>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
-            g_w_clusters[dev] = n;
-            // resident CTA pairs of the pair kernel.  Opt-in (HN_WGRAD_PAIRS=1): validated by the same parity tests, but measured
-            // SLOWER on B200 (2.90 vs 2.21 ms per Reso64 batch-2 pass) - what bounds this kernel is L2 -> SM read traffic, which the
-            // 3-CTA multicast clusters already cut to the compulsory 32 KiB per chunk and stage; a pair reads 40 KiB and strands chunk 2.
-            int np = 0;
-            const char* envp = getenv("HN_WGRAD_PAIRS");
-            if (envp && atoi(envp) != 0) {
-                e = cudaFuncSetAttribute(mlp_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
-                if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-                cfg.gridDim = dim3(2 * 74); cfg.dynamicSmemBytes = kPairSmem;
-                attr.val.clusterDim.x = 2;
-                if (cudaOccupancyMaxActiveClusters(&np, mlp_wgrad_pair_kernel, &cfg) != cudaSuccess) { np = 0; cudaGetLastError(); }
-            }
-            g_w_pairs[dev] = np;
+            g_w_clusters[dev] = (env && atoi(env) == 0) ? 0 : resident_clusters<3>(n_sm);
+            const char* envd = getenv("HN_WGRAD_DUOS");
+            g_w_duos[dev] = (envd && atoi(envd) == 0) ? 0 : resident_clusters<2>(n_sm);
             // a second stream (+ two events) per device: the single-CTA items that fill the SMs the clusters leave idle run on it,
             // forked from and joined back into the caller's stream (HN_WGRAD_SIDE=0 disables it)
             const char* envs = getenv("HN_WGRAD_SIDE");
@@ -643,22 +645,20 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
             g_w_ready[dev] = true;
         }
     }
-    int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_clusters = dev < 64 ? g_w_clusters[dev] : 0;
-    const int n_pairs = dev < 64 ? g_w_pairs[dev] : 0;
-    std::vector<WItem> cluster, single, pairs, side;
+    const int n_duos = dev < 64 ? g_w_duos[dev] : 0;
+    std::vector<WItem> cluster, single, duo, side;
     cudaStream_t side_stream = dev < 64 ? g_w_side[dev] : nullptr;
     const int n_idle = n_sm - 3 * n_clusters;
-    const int n_side = (side_stream && n_pairs == 0 && n_clusters > 0 && n_idle >= 4) ? n_idle : 0;
-    build_items(*a, n_sm, n_clusters, n_pairs, n_side, cluster, single, pairs, side);
-    if (cluster.empty() && single.empty() && pairs.empty() && side.empty()) return HN_OK;
-    if ((cluster.size() + single.size() + pairs.size() + side.size()) * sizeof(WItem) > a->items_workspace_bytes)
+    const int n_side = (side_stream && n_clusters > 0 && n_duos > 0 && n_idle >= 4) ? n_idle : 0;
+    build_items(*a, n_sm, n_clusters, n_duos, n_side, cluster, single, duo, side);
+    if (cluster.empty() && single.empty() && duo.empty() && side.empty()) return HN_OK;
+    if ((cluster.size() + single.size() + duo.size() + side.size()) * sizeof(WItem) > a->items_workspace_bytes)
         return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: items workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<WItem> all(cluster);
     all.insert(all.end(), single.begin(), single.end());
-    all.insert(all.end(), pairs.begin(), pairs.end());
+    all.insert(all.end(), duo.begin(), duo.end());
     all.insert(all.end(), side.begin(), side.end());
     // the item table is tiny (<100 KiB); pageable -> device copy is stream-ordered and returns after staging
     cudaError_t e = cudaMemcpyAsync(a->items_workspace, all.data(), all.size() * sizeof(WItem), cudaMemcpyHostToDevice, st);
@@ -670,48 +670,39 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     k.dbias = a->dbias;
     k.n_tiles = (int)(total_samples(a->B, a->n_rays, a->n_samples) / HN_TILE);
     k.status = a->status;
-    if (!pairs.empty()) {
-        k.items = (const WItem*)a->items_workspace + cluster.size() + single.size(); k.n_items = (int)pairs.size();
-        const int np = k.n_items < n_pairs ? k.n_items : n_pairs;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * np); cfg.blockDim = dim3(kWThreads); cfg.dynamicSmemBytes = kPairSmem; cfg.stream = st;
-        cudaLaunchAttribute attr{};
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        cudaError_t pe = cudaLaunchKernelEx(&cfg, mlp_wgrad_pair_kernel, k);
-        if (pe != cudaSuccess) return set_error((int)pe, cudaGetErrorString(pe));
-        if (int rc = check_launch("hn_mlp_bwd_weights (CTA pairs)")) return rc;
-    }
+    const WItem* base = (const WItem*)a->items_workspace;
     const bool forked = !side.empty() && !cluster.empty();
     // the side stream and its two events are per device, shared by all callers: the fork / launch / join sequence is serialised
     std::unique_lock<std::mutex> side_lock(g_w_mu, std::defer_lock);
     if (forked) side_lock.lock();
     if (forked && cudaEventRecord(g_w_fork[dev], st) != cudaSuccess) return set_error(HN_E_PROTOCOL, "hn_mlp_bwd_weights: event record failed");
     if (!cluster.empty()) {
-        k.items = (const WItem*)a->items_workspace; k.n_items = (int)cluster.size() / 3;
-        const int nc = n_clusters;                                  // the balanced schedule has one column per resident cluster
-        if (int rc = launch_wgrad(k, 3, 3 * nc, st)) return rc;
+        k.items = base; k.n_items = (int)cluster.size() / 3;
+        if (int rc = launch_wgrad<3>(k, 3 * n_clusters, st)) return rc;      // the balanced schedule has one column per resident cluster
     }
     if (forked) {
         // the idle SMs' share, concurrently with the clusters (launched after them: it can only take what they leave free)
         cudaStreamWaitEvent(side_stream, g_w_fork[dev], 0);
         WArgs ks = k;
-        ks.items = (const WItem*)a->items_workspace + cluster.size() + single.size() + pairs.size(); ks.n_items = (int)side.size();
-        if (int rc = launch_wgrad(ks, 1, n_side, side_stream)) return rc;
+        ks.items = base + cluster.size() + single.size() + duo.size(); ks.n_items = (int)side.size();
+        if (int rc = launch_wgrad<1>(ks, n_side, side_stream)) return rc;
         cudaEventRecord(g_w_join[dev], side_stream);
         cudaStreamWaitEvent(st, g_w_join[dev], 0);
     }
+    if (forked) side_lock.unlock();
+    if (!duo.empty()) {
+        k.items = base + cluster.size() + single.size(); k.n_items = (int)duo.size() / 2;
+        if (int rc = launch_wgrad<2>(k, 2 * n_duos, st)) return rc;
+    }
     if (!single.empty()) {
-        k.items = (const WItem*)a->items_workspace + cluster.size(); k.n_items = (int)single.size();
-        const int grid = n_sm;
-        if (int rc = launch_wgrad(k, 1, grid, st)) return rc;
+        k.items = base + cluster.size(); k.n_items = (int)single.size();
+        if (int rc = launch_wgrad<1>(k, n_sm, st)) return rc;
     }
     return HN_OK;
 }
 
 extern "C" size_t hn_wgrad_workspace_bytes(int B) {
-    // upper bound: 35 (layer, chunk) pairs x B x splits, splits chosen so that items <= 2*SMs + pairs*B
-    // upper bound: per list (#workers + #units) pieces, padded to whole rounds: clusters 3 * 3 * (49 + 9 B), single 3 * (160 + 9 B), pairs
+    // upper bound: per list (#workers + #units) pieces, padded to whole rounds: clusters 3 * 3 * (49 + 9 B), duos 2 * 2 * (74 + 2 B),
+    // single 3 * (160 + 12 B), side (13 + 4 B)
     return (size_t)(200 * (size_t)(B > 0 ? B : 1) + 2000) * sizeof(hn::WItem);
 }
