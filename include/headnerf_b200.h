@@ -212,9 +212,15 @@ typedef struct {
     int* status;
     int want_all_bias;        /* with every dw NULL: 0 = bias gradients of the latent-folded layers only (FeaExt_module_0,
                                * _5, RGB_layer_1: what the code gradients need), 1 = of all 12 layers (bias-only fine-tuning) */
+    void* det_workspace;      /* NULL: sample-range partial sums meet in dw / dbias through atomic adds (summation order, and the
+                               * last bits, vary from run to run).  Non-NULL (hn_wgrad_det_workspace_bytes(B) bytes): every work
+                               * item writes a private slice and a second kernel adds the slices in a fixed order - run-to-run
+                               * bit-identical gradients (what the reference asks of cuDNN with cudnn.deterministic, train.py:26-29) */
+    size_t det_workspace_bytes;
 } hn_mlp_bwd_weights_t;
 
 size_t hn_wgrad_workspace_bytes(int B);
+size_t hn_wgrad_det_workspace_bytes(int B);
 int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

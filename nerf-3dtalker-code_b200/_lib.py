@@ -54,7 +54,8 @@ class MlpBwdWeights(C.Structure):
     _fields_ = [("B", C.c_int), ("n_rays", C.c_int), ("n_samples", C.c_int),
                 ("act", _p), ("grads", _p), ("dfeat_image", _p), ("grad_scale", _p),
                 ("dw", _p * 12), ("ld", C.c_int * 12), ("l5_hidden_col", C.c_int), ("dbias", _p),
-                ("items_workspace", _p), ("items_workspace_bytes", C.c_size_t), ("status", _p), ("want_all_bias", C.c_int)]
+                ("items_workspace", _p), ("items_workspace_bytes", C.c_size_t), ("status", _p), ("want_all_bias", C.c_int),
+                ("det_workspace", _p), ("det_workspace_bytes", C.c_size_t)]
 
 
 class MlpFwdPrecise(C.Structure):
@@ -103,7 +104,7 @@ class Adam(C.Structure):
 
 EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pack_weights", "hn_sample_rays",
            "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
-           "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes",
+           "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes", "hn_wgrad_det_workspace_bytes",
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
            "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
            "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd",
@@ -134,6 +135,8 @@ def load():
         getattr(lib, name).argtypes = [C.c_int64]
     lib.hn_wgrad_workspace_bytes.restype = C.c_size_t
     lib.hn_wgrad_workspace_bytes.argtypes = [C.c_int]
+    lib.hn_wgrad_det_workspace_bytes.restype = C.c_size_t
+    lib.hn_wgrad_det_workspace_bytes.argtypes = [C.c_int]
     lib.hn_pack_weights.argtypes = [C.POINTER(Weights), _p, _p]
     lib.hn_precise_packed_bytes.restype = C.c_size_t
     lib.hn_precise_workspace_floats.restype = C.c_size_t

@@ -14,6 +14,7 @@
 // RGB_layer_0's own weight gradient is not requested.]
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <vector>
 #include "hn_api.h"
@@ -73,6 +74,7 @@ struct WItem {
     int16_t dens;             // 0: none; 1: density-head weight gradient over X blocks dens_x0, dens_x0 + 1; 2: ... and its bias gradient
     int16_t dens_x0;
     int32_t dens_blk;         // block of the density head's gradient column in `grads`
+    int32_t slot;             // deterministic mode: index of this item's private partial-sum slice
 };
 
 struct WShared {
@@ -101,7 +103,14 @@ struct WArgs {
     float* dbias;
     const WItem* items; int n_items; int n_tiles;
     int* status;
+    float* partials;          // deterministic mode: [slots][kDetSlotFloats] private partial sums (no atomics), else NULL
 };
+
+// deterministic mode: every work item flushes its accumulator (128 rows x up to 448 columns), its bias column sums (two reader
+// warps per 64-column block write separately) and, for the density fold, its two partial rows into a private slice; a second
+// kernel adds the slices of every destination in item order.  Same arithmetic, fixed summation order: run-to-run bit-identical.
+constexpr int kDetAccFloats = 128 * 448;
+constexpr int kDetSlotFloats = kDetAccFloats + 128 /*bias from the MMA path*/ + 2 * 128 /*bias, reader halves*/ + 2 * 128 /*density, reader halves*/ + 2 /*density bias*/ + 6;
 
 // `count` arrivals at once on a barrier of this CTA
 __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
@@ -361,7 +370,15 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                 bsum[j] += __shfl_xor_sync(0xffffffffu, bsum[j], 8); bsum[j] += __shfl_xor_sync(0xffffffffu, bsum[j], 16);
                 dsum[j] += __shfl_xor_sync(0xffffffffu, dsum[j], 8); dsum[j] += __shfl_xor_sync(0xffffffffu, dsum[j], 16);
             }
-            if (lane < 8) {
+            float* const slot = a.partials ? a.partials + (size_t)w.slot * kDetSlotFloats : nullptr;
+            if (slot && lane < 8) {
+                const int ch = hb * 64 + c8 * 8, sgh = rw >> 1;     // the two sample-group halves of a block write separate rows
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (read_bias) slot[kDetAccFloats + 128 + sgh * 128 + ch + j] = bsum[j];
+                    if (w.dens) slot[kDetAccFloats + 384 + sgh * 128 + ch + j] = dsum[j];
+                }
+            } else if (lane < 8) {
                 const int ch = hb * 64 + c8 * 8;                    // first of this lane's eight channels / layer-input columns
                 if (read_bias) {
 #pragma unroll
@@ -377,7 +394,10 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
             if (w.dens == 2 && rt < 64 && a.dbias) {                 // (threads kPieceRows..63 hold zeros)
 #pragma unroll
                 for (int sft = 16; sft >= 1; sft >>= 1) dsr_acc += __shfl_xor_sync(0xffffffffu, dsr_acc, sft);
-                if (lane == 0) atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + HN_BIAS_OFF_DENSITY, dsr_acc * inv_scale);
+                if (lane == 0) {
+                    if (slot) slot[kDetAccFloats + 640 + rw] = dsr_acc;
+                    else atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + HN_BIAS_OFF_DENSITY, dsr_acc * inv_scale);
+                }
             }
             if (quit) break;
             // ---- flush: TMEM -> atomic adds into dW
@@ -391,7 +411,12 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                     uint32_t v[32];
                     tmem_ld32(tmem_base + lane_base + k * 64 + h * 32, v);
                     tmem_ld_wait();
-                    if (row_ok && w.w_idx >= 0 && a.dw[w.w_idx]) {
+                    if (slot) {                                    // private slice, plain 128-bit stores
+                        float4* dst = reinterpret_cast<float4*>(slot + (size_t)row * 448 + k * 64 + h * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                    } else if (row_ok && w.w_idx >= 0 && a.dw[w.w_idx]) {
                         float* dst = a.dw[w.w_idx] + (size_t)(w.row0 + row) * a.ld[w.w_idx] + w.x_col[k] + h * 32;
                         const int nvalid = w.x_valid[k] - h * 32;
 #pragma unroll
@@ -405,7 +430,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                 uint32_t v[32];                                   // bias columns (all 16 equal); x32 load stays inside the 512 columns
                 tmem_ld32(tmem_base + lane_base + kBiasCol, v);
                 tmem_ld_wait();
-                if (row_ok && want_bias)
+                if (slot) slot[kDetAccFloats + row] = __uint_as_float(v[0]);
+                else if (row_ok && want_bias)
                     atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + w.bias_off + row, __uint_as_float(v[0]) * inv_scale);
             }
 #endif
@@ -418,6 +444,40 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
     __syncthreads();
     if (CL > 1) cluster_sync_all();                              // peers may still multicast into / signal this CTA
     if (warp == 1) tmem_free<512>(tmem_base);
+}
+
+// ---- deterministic mode, second pass: one CTA per (destination chunk of dW | bias row of one item), fixed item order
+struct WDst {
+    int32_t kind;             // 0: dW chunk (w_idx, row0, rows, columns from x_col / x_valid); 1: bias rows of item b
+    int32_t w_idx, row0, rows, n_x, b, bias_off;
+    int16_t x_col[kWMaxX], x_valid[kWMaxX];
+    int32_t first, count;     // range in the slot list
+};
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WArgs a, const WDst* dsts, const int* slot_list, const int bias_mode) {
+    const WDst d = dsts[blockIdx.x];
+    const float inv_scale = 1.0f / __ldg(a.grad_scale);
+    const int* sl = slot_list + d.first;
+    if (d.kind == 0) {
+        float* dw = a.dw[d.w_idx];
+        const int ld = a.ld[d.w_idx];
+        for (int e = threadIdx.x; e < d.rows * d.n_x * 64; e += blockDim.x) {
+            const int r = e / (d.n_x * 64), c = e % (d.n_x * 64), k = c >> 6, cc = c & 63;
+            if (cc >= d.x_valid[k]) continue;
+            float s = 0.f;
+            for (int i = 0; i < d.count; ++i) s += a.partials[(size_t)sl[i] * kDetSlotFloats + (size_t)r * 448 + c];
+            dw[(size_t)(d.row0 + r) * ld + d.x_col[k] + cc] += s * inv_scale;
+        }
+    } else if (d.kind == 1) {
+        for (int r = threadIdx.x; r < d.rows; r += blockDim.x) {
+            float s = 0.f;
+            for (int i = 0; i < d.count; ++i) {
+                const float* p = a.partials + (size_t)sl[i] * kDetSlotFloats + kDetAccFloats;
+                s += bias_mode == 1 ? p[r] : (p[128 + r] + p[256 + r]);
+            }
+            a.dbias[(size_t)d.b * HN_BIAS_STRIDE + d.bias_off + r] += s * inv_scale;
+        }
+    }
 }
 
 static std::mutex g_w_mu;
@@ -450,7 +510,7 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     // Opt-in (HN_WGRAD_DENS_FOLD=1): measured on B200, the readers slow RGB_layer_0's stages by more than the pseudo layer costs (cluster
     // kernel 1.45 -> 1.79 ms against 0.095 ms for the separate density items), so the default keeps the pseudo layer.
     static const bool fold_env = [] { const char* e = getenv("HN_WGRAD_DENS_FOLD"); return e && atoi(e) != 0; }();
-    const bool dens_in_r0 = fold_env && want_w && a.dw[W_R0] != nullptr && a.dw[W_DENSITY] != nullptr;
+    const bool dens_in_r0 = fold_env && !a.det_workspace && want_w && a.dw[W_R0] != nullptr && a.dw[W_DENSITY] != nullptr;   // (the fold has no deterministic reduction)
     if (!dens_in_r0) layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});
     auto active = [&](const LayerW& L) { return want_w || a.want_all_bias || L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1; };
     auto clustered = [&](const LayerW& L) { return want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
@@ -574,6 +634,8 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     partition(units_s, n_sm, 1, single);
 }
 
+static inline bool k_has_dw(const hn_mlp_bwd_weights_t& a, int w_idx) { return w_idx >= 0 && a.dw[w_idx] != nullptr; }
+
 template <int CL>
 static int launch_wgrad(const WArgs& k, int grid, cudaStream_t st) {
     if (CL == 1) {
@@ -660,6 +722,45 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     all.insert(all.end(), single.begin(), single.end());
     all.insert(all.end(), duo.begin(), duo.end());
     all.insert(all.end(), side.begin(), side.end());
+    // ---- deterministic mode: a private slice per work item, and the list of slices per destination in item order
+    const bool det = a->det_workspace != nullptr;
+    std::vector<WDst> dsts;
+    std::vector<int> slot_list;
+    if (det) {
+        int n_slots = 0;
+        for (WItem& w : all) if (w.tile1 > w.tile0) w.slot = n_slots++;
+        const size_t need = (size_t)n_slots * kDetSlotFloats * sizeof(float) + (all.size() + 64) * (sizeof(WDst) + sizeof(int));
+        if (need > a->det_workspace_bytes) return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: deterministic workspace too small (hn_wgrad_det_workspace_bytes)");
+        // destinations in order of first appearance; their slices in item order (two passes: count, then fill)
+        std::map<std::pair<int, int>, int> by_w, by_b;
+        std::vector<std::vector<int>> lists;
+        for (const WItem& w : all) {
+            if (w.tile1 <= w.tile0) continue;
+            if (k_has_dw(*a, w.w_idx)) {
+                auto it = by_w.find({w.w_idx, w.row0});
+                if (it == by_w.end()) {
+                    WDst d{}; d.kind = 0; d.w_idx = w.w_idx; d.row0 = w.row0; d.rows = w.rows; d.n_x = w.n_x;
+                    for (int q = 0; q < w.n_x; ++q) { d.x_col[q] = w.x_col[q]; d.x_valid[q] = w.x_valid[q]; }
+                    it = by_w.emplace(std::make_pair((int)w.w_idx, (int)w.row0), (int)dsts.size()).first;
+                    dsts.push_back(d); lists.emplace_back();
+                }
+                lists[it->second].push_back(w.slot);
+            }
+            if (w.bias_off >= 0 && a->dbias) {
+                auto it = by_b.find({w.b, w.bias_off});
+                if (it == by_b.end()) {
+                    WDst d{}; d.kind = 1; d.b = w.b; d.bias_off = w.bias_off; d.rows = w.rows;
+                    it = by_b.emplace(std::make_pair((int)w.b, (int)w.bias_off), (int)dsts.size()).first;
+                    dsts.push_back(d); lists.emplace_back();
+                }
+                lists[it->second].push_back(w.slot);
+            }
+        }
+        for (size_t i = 0; i < dsts.size(); ++i) {
+            dsts[i].first = (int)slot_list.size(); dsts[i].count = (int)lists[i].size();
+            slot_list.insert(slot_list.end(), lists[i].begin(), lists[i].end());
+        }
+    }
     // the item table is tiny (<100 KiB); pageable -> device copy is stream-ordered and returns after staging
     cudaError_t e = cudaMemcpyAsync(a->items_workspace, all.data(), all.size() * sizeof(WItem), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
@@ -670,6 +771,19 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     k.dbias = a->dbias;
     k.n_tiles = (int)(total_samples(a->B, a->n_rays, a->n_samples) / HN_TILE);
     k.status = a->status;
+    const WDst* d_dsts = nullptr;
+    const int* d_slots = nullptr;
+    if (det) {
+        // layout of the deterministic workspace: [destinations][slot list][slices]
+        uint8_t* wsb = (uint8_t*)a->det_workspace;
+        const size_t off_slots = (dsts.size() * sizeof(WDst) + 255) & ~(size_t)255;
+        const size_t off_part = (off_slots + slot_list.size() * sizeof(int) + 255) & ~(size_t)255;
+        e = cudaMemcpyAsync(wsb, dsts.data(), dsts.size() * sizeof(WDst), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(wsb + off_slots, slot_list.data(), slot_list.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+        d_dsts = (const WDst*)wsb; d_slots = (const int*)(wsb + off_slots);
+        k.partials = (float*)(wsb + off_part);
+    }
     const WItem* base = (const WItem*)a->items_workspace;
     const bool forked = !side.empty() && !cluster.empty();
     // the side stream and its two events are per device, shared by all callers: the fork / launch / join sequence is serialised
@@ -698,7 +812,17 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
         k.items = base + cluster.size(); k.n_items = (int)single.size();
         if (int rc = launch_wgrad<1>(k, n_sm, st)) return rc;
     }
+    if (det && !dsts.empty()) {
+        wgrad_reduce_kernel<<<(unsigned)dsts.size(), 256, 0, st>>>(k, d_dsts, d_slots, HN_WBIAS);
+        if (int rc = check_launch("hn_mlp_bwd_weights (deterministic reduction)")) return rc;
+    }
     return HN_OK;
+}
+
+extern "C" size_t hn_wgrad_det_workspace_bytes(int B) {
+    // one slice per work item (same bound as the item table) + the destination / slot tables
+    const size_t items = 200 * (size_t)(B > 0 ? B : 1) + 2000;
+    return items * (hn::kDetSlotFloats * sizeof(float) + sizeof(hn::WDst) + sizeof(int)) + 4096;
 }
 
 extern "C" size_t hn_wgrad_workspace_bytes(int B) {

@@ -95,6 +95,12 @@ class HeadNeRFNet(nn.Module):
         self.calib_rays = 512
         self._calib = None                       # (weights key, calls since, decision "fast" | "high", measured error)
         self._fuse_grads = False
+        # Weight gradients meet through atomic adds by default (summation order, hence the last bits, vary from run to run).
+        # deterministic = True: every work item writes a private slice and a second kernel adds them in a fixed order (bit-identical
+        # runs, one extra ~20 us kernel and a few hundred MB of workspace); None (default) follows PyTorch's own switches - the
+        # reference trains with cudnn.deterministic = True (train.py:26-29).
+        self.deterministic = None
+        self._kernel_cache = {}
         # every derived cache (packed operand images, cached bg_img, blur taps, the precision decision) is dropped whenever the
         # parameters may have been replaced behind autograd's version counters: load_state_dict, .to()/.cuda()/.float(), and -
         # because the reference's own loader writes through `model.state_dict()[k].data.copy_(...)` (talker_trainer.py:557-567),
@@ -229,7 +235,8 @@ class HeadNeRFNet(nn.Module):
                 "l5_hidden_col": L.PE + self.shape_dims, "precision": "high" if high else "fast", "grad_into": None if high else grad_into,
                 "grad_target": float(getattr(self, "grad_target", 1024.0 if high else 64.0)),
                 # frozen weights with trainable biases: the weight pass must still visit the layers whose bias gradients no latent code needs
-                "all_bias": any(m.bias.requires_grad for i, m in enumerate(self.fg_CD_predictor.layers()) if i not in (0, 5, 10))}
+                "all_bias": any(m.bias.requires_grad for i, m in enumerate(self.fg_CD_predictor.layers()) if i not in (0, 5, 10)),
+                "deterministic": self._deterministic(), "cache": self._kernel_cache}
         if high:
             ws, meta["packed_hl"] = self._packed_weights_precise()
         else:
@@ -242,6 +249,11 @@ class HeadNeRFNet(nn.Module):
         if pad:
             Fm, bg = Fm[:, :n_r], bg[:, :n_r]
         return Fm, bg
+
+    def _deterministic(self):
+        if self.deterministic is not None:
+            return bool(self.deterministic)
+        return bool(torch.backends.cudnn.deterministic or torch.are_deterministic_algorithms_enabled())
 
     def _calibrate(self, mode, batch_xy, audiostyle, shape_code, appea_code, batch_Rmats, batch_Tvecs, batch_inv_inmats, t_rand):
         """precision="auto": which kernel family keeps THIS checkpoint's feature map inside the parity gate?  Measured, not

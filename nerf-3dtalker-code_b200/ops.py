@@ -362,6 +362,19 @@ class FoldBiasFunction(torch.autograd.Function):
         return tuple(res)
 
 
+def _det_workspace(meta, B, dev):
+    """Deterministic weight gradients (meta["deterministic"]): the private-slice workspace of hn_mlp_bwd_weights, kept on the module
+    (meta["cache"]) between steps - a few hundred MB that need no zero-fill."""
+    if not meta.get("deterministic"):
+        return None
+    cache = meta.setdefault("cache", {})
+    n = L.load().hn_wgrad_det_workspace_bytes(B)
+    ws = cache.get("det_ws")
+    if ws is None or ws.numel() < n or ws.device != dev:
+        ws = cache["det_ws"] = torch.empty(n, dtype=torch.uint8, device=dev)
+    return ws
+
+
 class RenderFunction(torch.autograd.Function):
     """inputs : xy [B,2,N_r], R [B,3,3], T [B,3,1], K^-1 [B,3,3], t_rand or None, bias_eff [B,3920],
                 12 weights (header order; [8] is density_module.weight), then non-tensor meta
@@ -474,6 +487,8 @@ class RenderFunction(torch.autograd.Function):
             w.l5_hidden_col = meta["l5_hidden_col"]
             w.dbias, w.status = _ptr(dbias), _ptr(status)
             w.want_all_bias = 1 if (need_bias and meta.get("all_bias", True)) else 0
+            det_ws = _det_workspace(meta, B, dev)
+            w.det_workspace, w.det_workspace_bytes = _ptr(det_ws), (det_ws.numel() if det_ws is not None else 0)
             # with weight gradients the library launches two kernels: 3-CTA clusters for the 384-wide layers, then the rest
             _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=3 if need_w else 1)
         if _DEBUG_SYNC:
@@ -620,6 +635,8 @@ class RenderFunctionPrecise(torch.autograd.Function):
                 w.ld[i] = wt.numel() // wt.shape[0]
             w.l5_hidden_col = meta["l5_hidden_col"]
             w.dbias, w.status = _ptr(dbias), _ptr(status)
+            det_ws = _det_workspace(meta, B, dev)
+            w.det_workspace, w.det_workspace_bytes = _ptr(det_ws), (det_ws.numel() if det_ws is not None else 0)
             _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=3)
         if _DEBUG_SYNC:
             check_status(status, "hn_mlp_bwd_precise")

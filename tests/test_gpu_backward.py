@@ -189,3 +189,44 @@ def test_camera_chain_kernel_matches_autograd(hn):
     assert gT.shape == (3, 3, 1)
     for got, ref in ((gR, rR), (gT.reshape(3, 3), rT.reshape(3, 3)), (gK, rK)):
         assert (got - ref).abs().max() <= 2e-4 * ref.abs().max(), float((got - ref).abs().max() / ref.abs().max())
+
+
+def test_deterministic_weight_gradients_are_bit_identical(hn):
+    """deterministic=True (or torch.backends.cudnn.deterministic, as the reference's train.py:26-29 sets it): the weight-gradient
+    pass reduces private per-item slices in a fixed order instead of atomics - two runs give the same bits, and the values agree
+    with the atomic path to fp32 summation noise."""
+    g = load_golden("fs16_test_trained")
+    opt = g["opt"]
+    net = hn.HeadNeRFNet(hn.BaseOptions({"featmap_size": opt.featmap_size, "featmap_nc": 256, "pred_img_size": opt.pred_img_size}), False, False)
+    net.load_state_dict(O.formula_state_dict(opt, g["variant"]), strict=True)
+    net = net.to(DEV).eval()
+    net.precision = "fast"
+    x = {k: v.to(DEV) for k, v in g["inp"].items()}
+    gen = torch.Generator().manual_seed(3)
+    gF = (torch.randn(g["B"], opt.featmap_size ** 2, 256, generator=gen) * 1e-2).to(DEV)
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        codes = {k: x[k].clone().requires_grad_(True) for k in ("shape_code", "appea_code", "audiostyle")}
+        Fm, bg = net.render_rays("test", x["batch_xy"], codes["audiostyle"], codes["shape_code"], codes["appea_code"],
+                                 x["batch_Rmats"], x["batch_Tvecs"], x["batch_inv_inmats"])
+        torch.autograd.backward([Fm, bg], [gF, gF[..., 0].contiguous()])
+        net.check_faults()
+        return ([p.grad.clone() for p in net.fg_CD_predictor.parameters()], [codes[k].grad.clone() for k in codes])
+
+    assert net._deterministic() is False
+    ref_w, ref_c = run()
+    net.deterministic = True
+    a_w, a_c = run()
+    b_w, b_c = run()
+    for p, q in zip(a_w + a_c, b_w + b_c):
+        assert torch.equal(p, q), "deterministic mode is not run-to-run bit-identical"
+    for p, r in zip(a_w + a_c, ref_w + ref_c):
+        assert float(r.abs().max()) > 0 and (p - r).abs().max() <= 1e-4 * r.abs().max() + 1e-12
+    net.deterministic = None
+    prev = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        assert net._deterministic() is True                       # follows PyTorch's own switch by default
+    finally:
+        torch.backends.cudnn.deterministic = prev
