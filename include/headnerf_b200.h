@@ -413,6 +413,29 @@ typedef struct {
 
 int hn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const hn_adam_t* h, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Hierarchical resampling: NetWorks/utils.py:164-265 FineSample.forward - per ray, the pdf of
+ * the interior coarse compositing weights, n_fine + 1 inverse-CDF depths (uniform = NULL: linspace(0,1), the reference's
+ * test mode; else the caller's uniforms [n_rays_total, n_fine + 1], its rand() of train mode), merged and sorted with the
+ * coarse depths; outputs n_coarse + n_fine samples per ray, sample-major: zvals, z_dists (x ray_l) and points
+ * o + d * l * z (out_pts may be NULL).  ray_o / ray_d are channel-major [B,3,n_rays] like the reference's tensors.        */
+typedef struct {
+    int64_t n_rays_total;     /* B * n_rays                                                                        */
+    int n_rays;               /* rays per item                                                                     */
+    int n_coarse, n_fine;     /* num_sample_coarse (64), num_sample_fine (128)                                     */
+    const float* weights;     /* [n_rays_total, n_coarse] compositing weights (hn_composite_fwd)                   */
+    const float* zvals;       /* [n_rays_total, n_coarse] coarse depths                                            */
+    const float* uniform;     /* [n_rays_total, n_fine + 1] or NULL                                                */
+    const float* ray_o;       /* [B,3,n_rays]                                                                      */
+    const float* ray_d;       /* [B,3,n_rays]                                                                      */
+    const float* ray_l;       /* [n_rays_total]                                                                    */
+    float* out_zvals;         /* [n_rays_total, n_coarse + n_fine]                                                 */
+    float* out_zdists;        /* [n_rays_total, n_coarse + n_fine]                                                 */
+    float* out_pts;           /* [n_rays_total, n_coarse + n_fine, 3] or NULL                                      */
+} hn_fine_sample_t;
+
+int hn_fine_sample(const hn_fine_sample_t* a, void* stream);
+
 /* Bytes of the saved-for-backward buffers for M samples. */
 size_t hn_act_bytes(int64_t M);
 size_t hn_grads_bytes(int64_t M);

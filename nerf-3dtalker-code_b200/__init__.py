@@ -7,9 +7,11 @@ from .headnerf_net import HeadNeRFNet, MLPforNeRF
 from . import ops
 from . import dist
 from . import train
+from . import sampling
+from .sampling import FineSample
 from .train import HeadNeRFLossUtils, FusedAdam, Audio2style, save_checkpoint, load_checkpoint
 from . import _lib
 from .build import build as build_library
 
 __all__ = ["BaseOptions", "NeuralRenderer", "PixelShuffleUpsample", "Blur", "HeadNeRFNet", "MLPforNeRF",
-           "ops", "build_library", "train", "HeadNeRFLossUtils", "FusedAdam", "Audio2style", "save_checkpoint", "load_checkpoint"]
+           "ops", "build_library", "train", "HeadNeRFLossUtils", "FusedAdam", "Audio2style", "save_checkpoint", "load_checkpoint", "FineSample", "sampling"]

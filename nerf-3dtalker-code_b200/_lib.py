@@ -97,6 +97,11 @@ class PhotoLoss(C.Structure):
                 ("mask", _p), ("partials", _p), ("ticket", _p), ("out", _p)]
 
 
+class FineSample(C.Structure):
+    _fields_ = [("n_rays_total", C.c_int64), ("n_rays", C.c_int), ("n_coarse", C.c_int), ("n_fine", C.c_int), ("weights", _p), ("zvals", _p),
+                ("uniform", _p), ("ray_o", _p), ("ray_d", _p), ("ray_l", _p), ("out_zvals", _p), ("out_zdists", _p), ("out_pts", _p)]
+
+
 class Adam(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
                 ("grad_scale", C.c_float), ("step", C.c_int64)]
@@ -108,7 +113,7 @@ EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pac
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
            "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
            "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd",
-           "hn_photo_loss_workspace_bytes", "hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step"]
+           "hn_photo_loss_workspace_bytes", "hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step", "hn_fine_sample"]
 
 _lib = None
 
@@ -161,7 +166,8 @@ def load():
     lib.hn_photo_loss_fwd.argtypes = [C.POINTER(PhotoLoss), _p]
     lib.hn_photo_loss_bwd.argtypes = [C.POINTER(PhotoLoss), _p, _p, _p, _p]
     lib.hn_adam_step.argtypes = [_p, _p, _p, _p, C.c_int64, C.POINTER(Adam), _p]
-    for name in ("hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step"):
+    lib.hn_fine_sample.argtypes = [C.POINTER(FineSample), _p]
+    for name in ("hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step", "hn_fine_sample"):
         getattr(lib, name).restype = C.c_int
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
     lib.hn_mlp_fwd.argtypes = [C.POINTER(MlpFwd), _p]

@@ -187,3 +187,28 @@ def test_audio2style_matches_reference(hn):
     assert y_ref.shape == (5, 64)
     assert torch.equal(y_ref, y_ours)
     assert (y_ref - y_orc).abs().max() <= 2e-6 * (1 + y_ref.abs().max())      # nn.LSTM fuses the gate GEMMs differently: fp32 rounding only
+
+
+@pytest.mark.parametrize("disturb", [False, True])
+def test_fine_sample_bit_equal(disturb):
+    """oracle.fine_sample == the real NetWorks.utils.FineSample on the real GenSamplePoints / CalcRayColor outputs."""
+    ref_import.load()
+    from NetWorks.utils import FineSample, GenSamplePoints, CalcRayColor
+    opt_ref, _ = ref_import.build(8, 32)
+    opt = _opts(8, 32)
+    inp = O.synthetic_inputs(opt, 2, seed=3)
+    gen = GenSamplePoints(opt_ref)
+    coarse = gen(inp["batch_xy"], inp["batch_Rmats"], inp["batch_Tvecs"], inp["batch_inv_inmats"], False)
+    g = torch.Generator().manual_seed(1)
+    dens = torch.relu(torch.randn(2, 1, 64, 64, generator=g) * 6)
+    feat = torch.randn(2, 4, 64, 64, generator=g)
+    _, _, _, w = CalcRayColor()(None, feat, dens, coarse["z_dists"], coarse["zvals"])
+    fs = FineSample(opt_ref)
+    torch.manual_seed(5)
+    r = fs(w, coarse, disturb)
+    torch.manual_seed(5)
+    o = O.fine_sample(w, coarse, opt_ref.num_sample_fine, disturb)
+    assert set(r.keys()) == set(o.keys()) == {"pts", "dirs", "zvals", "z_dists"}
+    for k in r:
+        assert r[k].shape == o[k].shape and torch.equal(r[k], o[k]), k
+    assert r["zvals"].shape == (2, 1, 64, 192)
