@@ -27,11 +27,6 @@ int check_geometry(int B, int n_rays, int n_samples, const char* who) {
     return HN_OK;
 }
 
-bool use_cta_pairs(int n_tiles) {
-    static const int env = [] { const char* e = getenv("HN_CTA_PAIRS"); return e ? atoi(e) : 0; }();
-    return env != 0 && n_tiles >= 2 && (n_tiles % 2) == 0;
-}
-
 // One thread per sample; NetWorks/utils.py:147-161,64-89.
 __global__ void sample_rays_kernel(hn_camera_t cam, float* pts, float* zvals, float* z_dists, float* ray_d, float* ray_l) {
     const int64_t M = (int64_t)cam.B * cam.n_rays * cam.n_samples;

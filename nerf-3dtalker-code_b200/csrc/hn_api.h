@@ -8,7 +8,4 @@ int set_error(int code, const char* msg);     // records a thread-local message,
 int check_launch(const char* what);           // cudaGetLastError() -> 0 or positive cudaError_t
 inline int64_t total_samples(int B, int n_rays, int n_samples) { return (int64_t)B * n_rays * n_samples; }
 int check_geometry(int B, int n_rays, int n_samples, const char* who);
-// CTA-pair (cta_group::2) kernels: correct but currently slower than the single-CTA kernels (remote barrier arrivals on the
-// epilogue critical path), so they are opt-in: HN_CTA_PAIRS=1; they need an even tile count
-bool use_cta_pairs(int n_tiles);
 }  // namespace hn

@@ -31,9 +31,8 @@ constexpr uint32_t kBwdSmem = 6 * kUnitBytes + kBStages * kBStageBytes + 1024;
 constexpr uint32_t kBTmemCols = 512;
 
 struct BwdShared {
-    uint64_t w_full[6], w_empty[6], w_peer[6];
-    uint64_t a_ready[3], in_ready, in_peer, z_free, acc_full[4], acc_empty[4];
-    uint64_t a_ready_p[3], acc_empty_p[4];                  // pair mode, leader only: one arrival each, forwarded by the peer CTA
+    uint64_t w_full[3], w_empty[3];
+    uint64_t a_ready[3], in_ready, z_free, acc_full[4], acc_empty[4];
     float dp_part[2][128][3];
     uint32_t tmem_base;
     volatile int abort;
@@ -64,8 +63,6 @@ __device__ __forceinline__ void pe_backward_half(const uint32_t (&g)[32], const 
     }
 }
 
-// PAIR = true: CTA pair with cta_group::2 MMAs (see hn_mlp_fwd.cu); work item w -> tile 2w + rank.
-template <bool PAIR>
 __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_bwd_data_t a, const int n_tiles, const int with_pe) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ BwdShared sh;
@@ -75,30 +72,27 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
     const bool saving = (a.grads != nullptr);
     // weight ring geometry: single CTA 3 x 32 KiB (two 64-wide K blocks of 128 rows); pair mode 6 x 16 KiB (this CTA's
     // half of the rows of both K blocks) - same bytes in flight per CTA, i.e. twice the prefetch depth per weight byte needed
-    constexpr int STAGES = PAIR ? 6 : 3;
-    constexpr uint32_t STAGE_BYTES = PAIR ? kUnitBytes : 2 * kUnitBytes;
-    constexpr uint32_t KB_STRIDE = PAIR ? kUnitBytes / 2 : kUnitBytes;
-    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
-    const int work0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int work_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int n_work = PAIR ? n_tiles / 2 : n_tiles;
+    constexpr int STAGES = 3;
+    constexpr uint32_t STAGE_BYTES = 2 * kUnitBytes;
+    constexpr uint32_t KB_STRIDE = kUnitBytes;
+    const int work0 = (int)blockIdx.x;
+    const int work_stride = (int)gridDim.x;
+    const int n_work = n_tiles;
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&sh.w_full[i]), 1); mbar_init(smem_u32(&sh.w_empty[i]), 1); mbar_init(smem_u32(&sh.w_peer[i]), 1);
+            mbar_init(smem_u32(&sh.w_full[i]), 1); mbar_init(smem_u32(&sh.w_empty[i]), 1);
         }
-        for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&sh.a_ready[i]), kEpiWarps); mbar_init(smem_u32(&sh.a_ready_p[i]), 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&sh.a_ready[i]), kEpiWarps); }
         mbar_init(smem_u32(&sh.in_ready), 1);
-        mbar_init(smem_u32(&sh.in_peer), 1);
         mbar_init(smem_u32(&sh.z_free), kEpiWarps);
-        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.acc_empty[i]), kEpiWarps); mbar_init(smem_u32(&sh.acc_empty_p[i]), 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sh.acc_full[i]), 1); mbar_init(smem_u32(&sh.acc_empty[i]), kEpiWarps); }
         sh.abort = 0;
         mbar_fence_init();
     }
-    if (warp == 2) { if (PAIR) tmem_alloc_pair<kBTmemCols>(smem_u32(&sh.tmem_base)); else tmem_alloc<kBTmemCols>(smem_u32(&sh.tmem_base)); }
+    if (warp == 2) tmem_alloc<kBTmemCols>(smem_u32(&sh.tmem_base));
     tc_fence_before_sync();
     __syncthreads();
-    if (PAIR) cluster_sync_all();
     tc_fence_after_sync();
     const uint32_t tmem_base = sh.tmem_base;
     const int n_ops = tb.n_ops, n_epis = tb.n_epis;
@@ -110,7 +104,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
             const uint8_t* wt = (const uint8_t*)a.packed + (size_t)kFwdUnits * kUnitBytes;
             const uint8_t* din = (const uint8_t*)a.dfeat_image;
             for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
-                const int tile = PAIR ? 2 * w + (int)rank : w;
+                const int tile = w;
                 if (!wait_or_abort(&sh.z_free, par_free ^ 1, &sh.abort, a.status, 401)) break;
                 par_free ^= 1;
                 mbar_arrive_expect_tx(smem_u32(&sh.in_ready), 4 * kUnitBytes);
@@ -120,40 +114,25 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
                     const uint32_t stage = uc % STAGES, par = (uc / STAGES) & 1;
                     if (!wait_or_abort(&sh.w_empty[stage], par ^ 1, &sh.abort, a.status, 402)) break;
                     const MmaOp op = tb.mma[u];
-                    const uint32_t bytes = (uint32_t)op.n8 * 8 * 128 / (PAIR ? 2 : 1);      // pair mode: this CTA's half of the B operand
+                    const uint32_t bytes = (uint32_t)op.n8 * 8 * 128;
                     const uint32_t fb = smem_u32(&sh.w_full[stage]);
                     mbar_arrive_expect_tx(fb, bytes * op.nkb);
                     for (int k = 0; k < op.nkb; ++k)
                         bulk_g2s(smem + kBOffW + stage * STAGE_BYTES + k * KB_STRIDE,
-                                 wt + (size_t)(op.unit + k) * kUnitBytes + (PAIR ? rank * bytes : 0), bytes, fb);
+                                 wt + (size_t)(op.unit + k) * kUnitBytes, bytes, fb);
                 }
             }
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (PAIR && rank == 1) {
-            // peer CTA: relay "my dL/dfeat image / my half of the weights has landed" to the leader
-            if (lane == 0) {
-                uint32_t uc = 0, par_in = 0;
-                for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
-                    if (!wait_or_abort(&sh.in_ready, par_in, &sh.abort, a.status, 530)) break;
-                    par_in ^= 1;
-                    mbar_arrive_cluster(smem_u32(&sh.in_peer), 0);
-                    for (int u = 0; u < n_ops; ++u, ++uc) {
-                        const uint32_t stage = uc % STAGES, par = (uc / STAGES) & 1;
-                        if (!wait_or_abort(&sh.w_full[stage], par, &sh.abort, a.status, 531)) break;
-                        mbar_arrive_cluster(smem_u32(&sh.w_peer[stage]), 0);
-                    }
-                }
-            }
-        } else {
+        {
             // the whole warp walks the schedule (uniform control flow keeps descriptors in uniform registers); one
             // elected lane issues the MMAs and commits
             uint32_t uc = 0, par_ready = 0, par_in = 0, par_empty = 0;
             // The issuer shares its scheduler with four epilogue warps and gets a fraction of the issue slots, so what it
             // executes per MMA bounds the tensor pipe: dependencies are polled without clock reads, the NEXT unit's weight
             // barrier is queried before its answer is needed, and one elected-lane block issues the MMAs and the commits.
-            bool pre = !PAIR && mbar_try_wait(smem_u32(&sh.w_full[0]), 0);
+            bool pre = mbar_try_wait(smem_u32(&sh.w_full[0]), 0);
             MmaOp op = tb.mma[0];
             for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
                 for (int u = 0; u < n_ops; ++u, ++uc) {
@@ -161,27 +140,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
                     bool ok = true;
                     if (op.wait_src == 5) {
                         ok = wait_spin(&sh.in_ready, par_in, &sh.abort, a.status, 501);
-                        if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.in_peer, par_in, &sh.abort, a.status, 509);
                         par_in ^= 1;
                     } else if (op.wait_src) {
                         const int c = op.wait_src - 1;
                         ok = wait_spin(&sh.a_ready[c], (par_ready >> c) & 1, &sh.abort, a.status, 502 + c);
-                        if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.a_ready_p[c], (par_ready >> c) & 1, &sh.abort, a.status, 242 + c);
                         par_ready ^= 1u << c;
                     }
                     if (ok && op.wait_empty) {
                         ok = wait_spin(&sh.acc_empty[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 510 + op.q);
-                        if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.acc_empty_p[op.q], ((par_empty >> op.q) & 1) ^ 1, &sh.abort, a.status, 246 + op.q);
                         par_empty ^= 1u << op.q;
                     }
                     const uint32_t stage = uc % STAGES, par = (uc / STAGES) & 1;
                     if (ok && !pre) ok = wait_spin(&sh.w_full[stage], par, &sh.abort, a.status, 520);
-                    if (PAIR && ok) ok = wait_or_abort_x<true>(&sh.w_peer[stage], par, &sh.abort, a.status, 521);
                     if (!ok) break;
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem + kBOffZ + op.a_blk * kUnitBytes;
                     const uint32_t b_addr = smem + kBOffW + stage * STAGE_BYTES;
-                    const uint32_t idesc = umma_idesc(PAIR ? 256 : 128, (uint32_t)op.n8 * 8, kF16, kF16, 0, 0);
+                    const uint32_t idesc = umma_idesc(128, (uint32_t)op.n8 * 8, kF16, kF16, 0, 0);
                     const uint32_t d_addr = tmem_base + (uint32_t)op.tmem_col8 * 8;
                     const uint32_t a_lo = desc_lo(a_addr, 16), b_lo = desc_lo(b_addr, 16);
                     const uint32_t first = op.first, nkb = op.nkb;
@@ -190,43 +165,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
                         for (uint32_t k = 0; k < nkb; ++k) {
 #pragma unroll
                             for (uint32_t ks = 0; ks < 4; ++ks)
-                                umma_lohi_x<PAIR>(d_addr, a_lo + k * (kUnitBytes >> 4) + ks * 2, b_lo + k * (KB_STRIDE >> 4) + ks * 2, idesc,
+                                umma_f16_lohi(d_addr, a_lo + k * (kUnitBytes >> 4) + ks * 2, b_lo + k * (KB_STRIDE >> 4) + ks * 2, idesc,
                                                   (first && k == 0 && ks == 0) ? 0u : 1u);
                         }
-                        umma_commit_x<PAIR>(empty_bar);
-                        if (op.commit) umma_commit_x<PAIR>(full_bar);
+                        umma_commit(empty_bar);
+                        if (op.commit) umma_commit(full_bar);
                     }
                     __syncwarp();
                     // ask for the next unit's weights now; the answer is consumed at the top of the next iteration
-                    pre = !PAIR && mbar_try_wait(smem_u32(&sh.w_full[(uc + 1) % STAGES]), ((uc + 1) / STAGES) & 1);
+                    pre = mbar_try_wait(smem_u32(&sh.w_full[(uc + 1) % STAGES]), ((uc + 1) / STAGES) & 1);
                     op = nxt;
                 }
-            }
-        }
-    } else if (warp == 3) {
-        // ======================= pair mode, peer CTA: barrier forwarder =======================
-        // The peer's epilogue warps arrive on their OWN CTA's barriers (cheap); this thread relays every completed phase
-        // to the leader with a single remote arrive, keeping cluster-scope release traffic off the epilogue's critical path.
-        if (PAIR && rank == 1 && lane == 0) {
-            const int my_tiles = (n_work - work0 + work_stride - 1) / work_stride;
-            uint64_t* local[8] = {&sh.a_ready[0], &sh.a_ready[1], &sh.a_ready[2], &sh.acc_empty[0], &sh.acc_empty[1], &sh.acc_empty[2], &sh.acc_empty[3], &sh.a_ready[0]};
-            uint64_t* remote[8] = {&sh.a_ready_p[0], &sh.a_ready_p[1], &sh.a_ready_p[2], &sh.acc_empty_p[0], &sh.acc_empty_p[1], &sh.acc_empty_p[2], &sh.acc_empty_p[3], &sh.a_ready_p[0]};
-            int left[8];
-            for (int i = 0; i < 3; ++i) left[i] = tb.n_ready[i] * my_tiles;
-            for (int i = 0; i < 4; ++i) left[3 + i] = tb.n_empty[i] * my_tiles;
-            left[7] = 0;
-            uint32_t par = 0;
-            int total = 0;
-            for (int i = 0; i < 8; ++i) total += left[i];
-            const long long t0 = clock64();
-            while (total > 0 && !sh.abort) {
-                for (int i = 0; i < 8; ++i) {
-                    if (left[i] > 0 && mbar_try_wait(smem_u32(local[i]), (par >> i) & 1)) {
-                        mbar_arrive_cluster(smem_u32(remote[i]), 0);
-                        par ^= 1u << i; --left[i]; --total;
-                    }
-                }
-                if (clock64() - t0 > 20000000000ll) { sh.abort = 1; atomicCAS(a.status, 0, 260); }
             }
         }
     } else if (warp >= kCtrlWarps) {
@@ -242,7 +191,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
         const float scale = __ldg(a.grad_scale);
         const float inv_scale = 1.0f / scale;
         for (int w = work0; w < n_work && !sh.abort; w += work_stride) {
-            const int tile = PAIR ? 2 * w + (int)rank : w;
+            const int tile = w;
             const size_t m = (size_t)tile * HN_TILE + row;
             const float dsr = (__ldg(a.sigma + m) > 0.f) ? __ldg(a.dsigma + m) * scale : 0.f;   // d/d(pre-ReLU density), scaled
             const uint32_t* mask_row = a.masks + m * HN_MASK_WORDS;
@@ -350,8 +299,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) mlp_bwd_kernel(const hn_mlp_
 
     tc_fence_before_sync();
     __syncthreads();
-    if (PAIR) cluster_sync_all();
-    if (warp == 2) { if (PAIR) tmem_free_pair<kBTmemCols>(tmem_base); else tmem_free<kBTmemCols>(tmem_base); }
+    if (warp == 2) tmem_free<kBTmemCols>(tmem_base);
 }
 
 static std::mutex g_bwd_mu;
@@ -371,10 +319,9 @@ extern "C" int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream) {
     if (with_pe && (!a->g_ray_v || !a->g_ray_l))
         return set_error(HN_E_BADARG, "hn_mlp_bwd_data: g_ray_o, g_ray_v and g_ray_l must be given together");
     const int64_t M_all = total_samples(a->cam.B, a->cam.n_rays, a->cam.n_samples);
-    // the training step (no camera gradients) runs on the tensor-memory chain; dL/dPE needs this file's kernel (it keeps a
-    // dedicated accumulator for it).  HN_BWD_SMEM=1 forces the shared-memory-operand kernel (A/B comparisons).
-    static const bool force_smem = [] { const char* e = getenv("HN_BWD_SMEM"); return e && atoi(e) != 0; }();
-    if (!with_pe && !force_smem && !use_cta_pairs((int)(M_all / HN_TILE))) return launch_bwd_data_tmem(a, stream);
+    // the training step (no camera gradients) runs on the tensor-memory chain (hn_mlp_fwd.cu); dL/dPE needs this file's kernel,
+    // which keeps a dedicated accumulator for it
+    if (!with_pe) return launch_bwd_data_tmem(a, stream);
     int dev = 0;
     cudaGetDevice(&dev);
     {
@@ -383,8 +330,7 @@ extern "C" int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream) {
             const HostSchedules& hs = host_schedules();
             cudaError_t e = cudaMemcpyToSymbol(c_bwd, &hs.bwd_nope, sizeof(BwdTables), 0);
             if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_bwd, &hs.bwd, sizeof(BwdTables), sizeof(BwdTables));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
             if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
             g_bwd_ready[dev] = true;
         }
@@ -393,19 +339,7 @@ extern "C" int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int64_t M = total_samples(a->cam.B, a->cam.n_rays, a->cam.n_samples);
     const int n_tiles = (int)(M / HN_TILE);
-    if (use_cta_pairs(n_tiles)) {
-        const int n_pairs = (n_tiles / 2) < (n_sm / 2) ? (n_tiles / 2) : (n_sm / 2);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = kBwdSmem; cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr{};
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_bwd_kernel<true>, *a, n_tiles, with_pe ? 1 : 0);
-        if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-        return check_launch("hn_mlp_bwd_data (cta pairs)");
-    }
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    mlp_bwd_kernel<false><<<grid, kFusedThreads, kBwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, with_pe ? 1 : 0);
+    mlp_bwd_kernel<<<grid, kFusedThreads, kBwdSmem, (cudaStream_t)stream>>>(*a, n_tiles, with_pe ? 1 : 0);
     return check_launch("hn_mlp_bwd_data");
 }

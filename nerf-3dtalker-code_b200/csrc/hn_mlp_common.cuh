@@ -31,41 +31,6 @@ __device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, vo
     return true;
 }
 
-// same, for barriers that also receive arrivals from the peer CTA of a pair (cluster-scope acquire)
-template <bool PAIR>
-__device__ __forceinline__ bool wait_or_abort_x(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int* status, int code) {
-    if (!PAIR) return wait_or_abort(bar, parity, abort_flag, status, code);
-    const uint32_t b = smem_u32(bar);
-    if (mbar_try_wait_cluster(b, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(b, parity)) {
-        if (*abort_flag) return false;
-        if (clock64() - t0 > 2000000000ll) {
-            *abort_flag = 1;
-            atomicCAS(status, 0, code);
-            return false;
-        }
-    }
-    return true;
-}
-
-// one arrival per warp on a barrier that lives in the LEADER CTA (rank 0) of the pair; in single-CTA mode a local arrive
-template <bool PAIR>
-__device__ __forceinline__ void warp_arrive_leader(uint32_t bar, int lane) {
-    __syncwarp();
-    if (lane == 0) { if (PAIR) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar); }
-}
-
-template <bool PAIR> __device__ __forceinline__ void umma_x(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, bool acc) {
-    if (PAIR) umma_f16_pair(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
-}
-template <bool PAIR> __device__ __forceinline__ void umma_lohi_x(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-    if (PAIR) umma_f16_pair_lohi(d, a_lo, b_lo, idesc, acc); else umma_f16_lohi(d, a_lo, b_lo, idesc, acc);
-}
-template <bool PAIR> __device__ __forceinline__ void umma_commit_x(uint32_t bar) {
-    if (PAIR) umma_commit_pair(bar); else umma_commit(bar);
-}
-
 // Optional pipeline cycle counters (build with -DHN_PIPE_COUNTERS, read with tools/pipeline_counters.py): the
 // forward kernel's CTA 0 writes, as 64-bit cycle counts, status[2..17] (MMA issuer: total, waits by barrier class,
 // issue, commit) and status[18..29] (epilogue warp 0: total, wait, TMEM load, math+store, sync, next-tile PE).
