@@ -39,7 +39,10 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# algorithmic cost per ray·sample (SURVEY.md §8d / DESIGN.md §4): latent columns folded into biases, padding not counted
+# algorithmic cost per ray·sample (SURVEY.md §8d / DESIGN.md §4): latent columns folded into biases, padding not counted.  The
+# kernels EXECUTE less: RGB_layer_0 (no activation) is multiplied into RGB_layer_1 once per weight version (SURVEY.md appendix A4,
+# "optional algebraic fusion"), which removes 384 x 384 MACs per ray·sample from each pass; both figures are reported.
+MAC_R0 = 384 * 384
 MAC_FWD = 1_351_296
 FLOP_FWD = 2 * MAC_FWD
 FLOP_DGRAD = 2 * (MAC_FWD - 2 * 63 * 384)        # no gradient w.r.t. the positional encoding in the training step
@@ -316,6 +319,8 @@ def run_config2(args):
         if name in flops:
             k["tflops_algorithmic"] = round(flops[name] / (d["ms_avg"] * 1e-3) / 1e12, 1)
             k["frac_of_tensor_peak"] = round(k["tflops_algorithmic"] / peaks["tflops"], 4)
+            k["tflops_executed"] = round((flops[name] - 2 * MAC_R0 * M) / (d["ms_avg"] * 1e-3) / 1e12, 1)
+            k["executed_frac_of_tensor_peak"] = round(k["tflops_executed"] / peaks["tflops"], 4)
         if name in traffic:
             k["dram_bytes_per_launch_ncu"] = traffic[name]
         kernels[name] = k
@@ -341,6 +346,10 @@ def run_config2(args):
                 "peak_source": peaks["src"], "algorithmic_flop_per_launch": flops[dom],
                 "algorithmic_flop_per_ray_sample": {"hn_mlp_fwd": FLOP_FWD, "hn_mlp_bwd_data": FLOP_DGRAD, "hn_mlp_bwd_weights": FLOP_WGRAD}[dom],
                 "all_mlp_kernels_frac": {n: kernels[n]["frac_of_tensor_peak"] for n in flops if n in kernels},
+                "executed": {"note": "RGB_layer_0 multiplied into RGB_layer_1 (SURVEY.md appendix A4): 147 456 MAC per ray*sample fewer per pass than the "
+                                     "section 8d figure `frac` is quoted on; the same kernels against the MACs they actually issue:",
+                             "mac_per_ray_sample_fwd": MAC_FWD - MAC_R0, "frac": kernels[dom]["executed_frac_of_tensor_peak"],
+                             "all_mlp_kernels_frac": {n: kernels[n]["executed_frac_of_tensor_peak"] for n in flops if n in kernels}},
                 "step_tflops_algorithmic": round(step_tflops, 1), "step_frac_of_tensor_peak": round(step_tflops / peaks["tflops"], 4),
                 "hbm_view": ({"operand_gbs": kernels[dom].get("gbs_operands"), "operand_frac_of_hbm_peak": kernels[dom].get("operand_frac_of_hbm_peak"),
                               "peak_gbs": peaks["hbm_gbs"]} if dom == "hn_mlp_bwd_weights" else None),

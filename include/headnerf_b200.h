@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 2
+#define HN_ABI_VERSION 3
 
 /* error codes (negative = argument / configuration errors) */
 #define HN_OK 0
@@ -212,6 +212,10 @@ typedef struct {
     int* status;
     int want_all_bias;        /* with every dw NULL: 0 = bias gradients of the latent-folded layers only (FeaExt_module_0,
                                * _5, RGB_layer_1: what the code gradients need), 1 = of all 12 layers (bias-only fine-tuning) */
+    int r0_fused;             /* 1: `act` / `grads` come from the fast chains (no RGB_layer_0: RGB_layer_1's layer input is
+                               * FeaExt_module_7's output and its weight gradient is dL/dW_f -> `dwf`; dw[9] is not written,
+                               * dw[10] only marks that the gradient is wanted); 0: from hn_mlp_bwd_data_precise (12 layers)     */
+    float* dwf;               /* r0_fused: [192, 384] zero-initialised, accumulated; NULL = RGB_layer_1 / _0 gradients not wanted */
     void* det_workspace;      /* NULL: sample-range partial sums meet in dw / dbias through atomic adds (summation order, and the
                                * last bits, vary from run to run).  Non-NULL (hn_wgrad_det_workspace_bytes(B) bytes): every work
                                * item writes a private slice and a second kernel adds the slices in a fixed order - run-to-run
@@ -238,6 +242,10 @@ typedef struct {
     const float* shape_code;          /* [B, shape_dims]                                                    */
     const float* audio;               /* [B, 64]                                                            */
     const float* appea;               /* [B, appea_dims]                                                    */
+    int r0_fused;                     /* 1 (the fast kernels): RGB_layer_1's row also carries W_R1[:, :384] b_R0 - those chains
+                                       * skip RGB_layer_0, which has no activation and is multiplied into RGB_layer_1 by
+                                       * hn_pack_weights; 0 (hn_mlp_fwd_precise, which runs the twelve layers one by one)       */
+    const float* wr0; int ldr0;       /* RGB_layer_0.weight [384, 384]: read by hn_render_bwd only (may be NULL elsewhere)       */
 } hn_fold_t;
 
 typedef struct {
@@ -247,6 +255,22 @@ typedef struct {
 } hn_fold_grads_t;
 
 int hn_fold_bias(const hn_fold_t* a, float* bias_eff /*[B, HN_BIAS_STRIDE]*/, void* stream);
+
+/* Backward of the RGB_layer_0 fold (NetWorks/models.py:79-80 has no activation between RGB_layer_0 and RGB_layer_1, so the fast
+ * kernels run them as one matrix W_f = W_R1[:, :384] W_R0): hn_mlp_bwd_weights (r0_fused = 1) delivers dL/dW_f [192,384] and the
+ * bias-row gradient; this turns them into dL/dW_R1[:, :384] (+=), dL/dW_R0 (+=) and - written into RGB_layer_0's entries of item
+ * 0's bias-row gradient, where hn_fold_bias_bwd finds it - dL/db_R0.  Call between hn_mlp_bwd_weights and hn_fold_bias_bwd.   */
+typedef struct {
+    int B;
+    const float* wr0; int ldr0;       /* RGB_layer_0.weight [384, 384]                                       */
+    const float* wr1; int ldr1;       /* RGB_layer_1.weight [192, 384 + appea_dims]                          */
+    const float* b_r0;                /* RGB_layer_0.bias [384]                                              */
+    const float* dwf;                 /* [192, 384] from hn_mlp_bwd_weights                                  */
+    float* dbias_eff;                 /* [B, HN_BIAS_STRIDE] in / out                                        */
+    float* dwr0;                      /* += [384, ldr0], or NULL                                             */
+    float* dwr1;                      /* += hidden columns of [192, ldr1], or NULL                           */
+} hn_unfuse_t;
+int hn_unfuse_r0r1(const hn_unfuse_t* a, void* stream);
 int hn_fold_bias_bwd(const hn_fold_t* a, const float* dbias_eff /*[B, HN_BIAS_STRIDE]*/, const hn_fold_grads_t* g, void* stream);
 
 /* Power-of-two loss scale of the half-precision backward chain: *scale_out = 2^floor(log2(target / max|g|)),
@@ -369,6 +393,7 @@ typedef struct {
     void* items_workspace; size_t items_workspace_bytes;   /* hn_wgrad_workspace_bytes(B)                          */
     float* g_ray_o; float* g_ray_v; float* g_ray_l;        /* zeroed workspaces, camera gradients only             */
     float* dw[12]; int ld[12]; int l5_hidden_col;          /* zeroed weight-gradient outputs (NULL entries skipped) */
+    float* dwf;                                            /* zeroed [192,384] workspace (dw[9] / dw[10] / fold_grads.dbias[9]) */
     hn_fold_grads_t fold_grads;                            /* code gradients (=), folded columns / biases (+=)      */
     float* dR; float* dT; float* dKinv;                    /* zeroed [B,3,3] / [B,3] / [B,3,3], or NULL             */
     int* status;

@@ -55,7 +55,7 @@ class MlpBwdWeights(C.Structure):
                 ("act", _p), ("grads", _p), ("dfeat_image", _p), ("grad_scale", _p),
                 ("dw", _p * 12), ("ld", C.c_int * 12), ("l5_hidden_col", C.c_int), ("dbias", _p),
                 ("items_workspace", _p), ("items_workspace_bytes", C.c_size_t), ("status", _p), ("want_all_bias", C.c_int),
-                ("det_workspace", _p), ("det_workspace_bytes", C.c_size_t)]
+                ("r0_fused", C.c_int), ("dwf", _p), ("det_workspace", _p), ("det_workspace_bytes", C.c_size_t)]
 
 
 class MlpFwdPrecise(C.Structure):
@@ -71,7 +71,13 @@ class MlpBwdDataPrecise(C.Structure):
 
 class Fold(C.Structure):
     _fields_ = [("B", C.c_int), ("shape_dims", C.c_int), ("appea_dims", C.c_int), ("w0", _p), ("ld0", C.c_int), ("w5", _p), ("ld5", C.c_int),
-                ("wr1", _p), ("ldr1", C.c_int), ("bias", _p * 12), ("shape_code", _p), ("audio", _p), ("appea", _p)]
+                ("wr1", _p), ("ldr1", C.c_int), ("bias", _p * 12), ("shape_code", _p), ("audio", _p), ("appea", _p),
+                ("r0_fused", C.c_int), ("wr0", _p), ("ldr0", C.c_int)]
+
+
+class Unfuse(C.Structure):
+    _fields_ = [("B", C.c_int), ("wr0", _p), ("ldr0", C.c_int), ("wr1", _p), ("ldr1", C.c_int), ("b_r0", _p), ("dwf", _p),
+                ("dbias_eff", _p), ("dwr0", _p), ("dwr1", _p)]
 
 
 class FoldGrads(C.Structure):
@@ -88,7 +94,7 @@ class RenderBwd(C.Structure):
                 ("act", _p), ("masks", _p), ("gF", _p), ("g_bg", _p), ("grad_target", C.c_float), ("dfeat_image", _p), ("dsigma", _p),
                 ("ddelta", _p), ("grads", _p), ("scale", _p), ("scale_scratch8", _p), ("dbias_eff", _p), ("items_workspace", _p),
                 ("items_workspace_bytes", C.c_size_t), ("g_ray_o", _p), ("g_ray_v", _p), ("g_ray_l", _p), ("dw", _p * 12),
-                ("ld", C.c_int * 12), ("l5_hidden_col", C.c_int), ("fold_grads", FoldGrads), ("dR", _p), ("dT", _p), ("dKinv", _p),
+                ("ld", C.c_int * 12), ("l5_hidden_col", C.c_int), ("dwf", _p), ("fold_grads", FoldGrads), ("dR", _p), ("dT", _p), ("dKinv", _p),
                 ("status", _p)]
 
 
@@ -113,7 +119,7 @@ EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pac
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
            "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
            "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd",
-           "hn_photo_loss_workspace_bytes", "hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step", "hn_fine_sample"]
+           "hn_photo_loss_workspace_bytes", "hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step", "hn_fine_sample", "hn_unfuse_r0r1"]
 
 _lib = None
 
@@ -167,6 +173,8 @@ def load():
     lib.hn_photo_loss_bwd.argtypes = [C.POINTER(PhotoLoss), _p, _p, _p, _p]
     lib.hn_adam_step.argtypes = [_p, _p, _p, _p, C.c_int64, C.POINTER(Adam), _p]
     lib.hn_fine_sample.argtypes = [C.POINTER(FineSample), _p]
+    lib.hn_unfuse_r0r1.argtypes = [C.POINTER(Unfuse), _p]
+    lib.hn_unfuse_r0r1.restype = C.c_int
     for name in ("hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step", "hn_fine_sample"):
         getattr(lib, name).restype = C.c_int
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
@@ -180,7 +188,7 @@ def load():
                  "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
                  "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd"):
         getattr(lib, name).restype = C.c_int
-    if lib.hn_abi_version() != 2:
+    if lib.hn_abi_version() != 3:
         raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")
     _lib = lib
     return lib

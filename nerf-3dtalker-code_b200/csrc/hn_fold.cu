@@ -14,6 +14,7 @@ namespace hn {
 
 struct FoldK {
     int B, S, A;
+    int r0_fused;             // 1: RGB_layer_1's row also carries W_R1[:, :384] b_R0 (the fast chains skip RGB_layer_0, hn_mlp_sched.h)
     const float* w0; int ld0; const float* w5; int ld5; const float* wr1; int ldr1;
     const float* bias[12];
     const float* shape; const float* audio; const float* appea;
@@ -53,6 +54,10 @@ __global__ void __launch_bounds__(256) fold_fwd_kernel(FoldK k, float* bias_eff)
     } else if (l == W_R1) {
         const float* w = k.wr1 + (size_t)r * k.ldr1 + HN_HIDDEN;
         for (int c = lane; c < k.A; c += 32) acc = fmaf(__ldg(w + c), __ldg(k.appea + (size_t)b * k.A + c), acc);
+        if (k.r0_fused) {
+            const float* wh = k.wr1 + (size_t)r * k.ldr1;
+            for (int c = lane; c < HN_HIDDEN; c += 32) acc = fmaf(__ldg(wh + c), __ldg(k.bias[W_R0] + c), acc);
+        }
     }
     acc = warp_sum(acc);
     if (lane == 0) bias_eff[wid] = (l >= 0) ? __ldg(k.bias[l] + r) + acc : 0.f;
@@ -162,7 +167,7 @@ static int fill(const hn_fold_t* a, FoldK* k, const char* who) {
     if (a->B <= 0 || a->shape_dims <= 0 || a->appea_dims <= 0 || a->ld0 < HN_PE + a->shape_dims + 64 || a->ld5 < HN_PE + a->shape_dims ||
         a->ldr1 < HN_HIDDEN + a->appea_dims)
         return set_error(HN_E_BADARG, who);
-    k->B = a->B; k->S = a->shape_dims; k->A = a->appea_dims;
+    k->B = a->B; k->S = a->shape_dims; k->A = a->appea_dims; k->r0_fused = a->r0_fused;
     k->w0 = a->w0; k->ld0 = a->ld0; k->w5 = a->w5; k->ld5 = a->ld5; k->wr1 = a->wr1; k->ldr1 = a->ldr1;
     for (int i = 0; i < 12; ++i) k->bias[i] = a->bias[i];
     k->shape = a->shape_code; k->audio = a->audio; k->appea = a->appea;
@@ -199,6 +204,66 @@ extern "C" int hn_fold_bias_bwd(const hn_fold_t* a, const float* dbias_eff, cons
         fold_bwd_params_kernel<<<(n + 255) / 256, 256, 0, st>>>(k, dbias_eff, o);
     }
     return check_launch("hn_fold_bias_bwd");
+}
+
+namespace hn {
+// Backward of the RGB_layer_0 fold (hn_mlp_sched.h): with W_f = W_R1a W_R0 and RGB_layer_1's bias row b_R1 + W_R1a b_R0 + ...,
+//   dW_R1a = dW_f W_R0^T + g b_R0^T,   dW_R0 = W_R1a^T dW_f,   db_R0 = W_R1a^T g      (g = sum over items of dL/d(bias row of RGB_layer_1))
+// db_R0 is delivered through RGB_layer_0's (otherwise unused) entries of item 0's bias-row gradient, from where hn_fold_bias_bwd
+// picks it up like every other bias gradient.  dW_R1a contracts over the CONTIGUOUS index of both operands: one warp per element,
+// lanes along k (coalesced rows, shuffle reduction); dW_R0 and db_R0: one thread per element, consecutive threads on consecutive k.
+__global__ void __launch_bounds__(256) unfuse_r1_kernel(const hn_unfuse_t a) {
+    const int wid = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (wid >= HN_RGB1 * HN_HIDDEN) return;
+    const int n = wid / HN_HIDDEN, c = wid % HN_HIDDEN;
+    float acc = 0.f;
+    for (int k = lane; k < HN_HIDDEN; k += 32) acc = fmaf(__ldg(a.dwf + (size_t)n * HN_HIDDEN + k), __ldg(a.wr0 + (size_t)c * a.ldr0 + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        float g = 0.f;
+        for (int b = 0; b < a.B; ++b) g += a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R1 + n];
+        a.dwr1[(size_t)n * a.ldr1 + c] += fmaf(g, __ldg(a.b_r0 + c), acc);
+    }
+}
+
+__global__ void __launch_bounds__(256) unfuse_r0_kernel(const hn_unfuse_t a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= HN_HIDDEN * HN_HIDDEN) return;
+    const int c = t / HN_HIDDEN, k = t % HN_HIDDEN;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int n = 0; n < HN_RGB1; ++n) acc = fmaf(__ldg(a.wr1 + (size_t)n * a.ldr1 + c), __ldg(a.dwf + (size_t)n * HN_HIDDEN + k), acc);
+    a.dwr0[(size_t)c * a.ldr0 + k] += acc;
+}
+
+// db_R0 = W_R1a^T g: one block; g (192 sums over the items) goes through shared memory first - 384 threads each re-deriving it with
+// dependent global loads took 0.1 ms
+__global__ void __launch_bounds__(HN_HIDDEN) unfuse_b0_kernel(const hn_unfuse_t a) {
+    __shared__ float g[HN_RGB1];
+    const int t = threadIdx.x;
+    if (t < HN_RGB1) {
+        float s = 0.f;
+        for (int b = 0; b < a.B; ++b) s += a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R1 + t];
+        g[t] = s;
+    }
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll 16                                                   // one block: keep 16 independent loads in flight
+    for (int n = 0; n < HN_RGB1; ++n) acc = fmaf(__ldg(a.wr1 + (size_t)n * a.ldr1 + t), g[n], acc);
+    a.dbias_eff[HN_BIAS_OFF_R0 + t] = acc;
+    for (int b = 1; b < a.B; ++b) a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R0 + t] = 0.f;
+}
+}  // namespace hn
+
+extern "C" int hn_unfuse_r0r1(const hn_unfuse_t* a, void* stream) {
+    using namespace hn;
+    if (!a || !a->wr0 || !a->wr1 || !a->b_r0 || !a->dwf || !a->dbias_eff || a->B <= 0 || a->ldr0 < HN_HIDDEN || a->ldr1 < HN_HIDDEN)
+        return set_error(HN_E_BADARG, "hn_unfuse_r0r1: null pointer or inconsistent dimensions");
+    // (the R0 kernel writes RGB_layer_0's bias-row entries, which the R1 kernel does not read: any order)
+    if (a->dwr1) unfuse_r1_kernel<<<(HN_RGB1 * HN_HIDDEN * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
+    if (a->dwr0) unfuse_r0_kernel<<<(HN_HIDDEN * HN_HIDDEN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
+    unfuse_b0_kernel<<<1, HN_HIDDEN, 0, (cudaStream_t)stream>>>(*a);
+    return check_launch("hn_unfuse_r0r1");
 }
 
 extern "C" int hn_loss_scale(const float* g, int64_t n, float target, float* scale_out, void* scratch8, void* stream) {

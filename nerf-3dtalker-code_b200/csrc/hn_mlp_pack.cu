@@ -42,13 +42,26 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a, uint8_t* packed) 
     }
 }
 
+// W_f = W_R1[:, :384] W_R0  (192 x 384, fp32): RGB_layer_0 has no activation, so the two layers are one linear map per sample
+// (hn_mlp_sched.h).  One thread per element, 384-long dot product; runs once per weight version.
+__global__ void __launch_bounds__(256) fuse_r0r1_kernel(const float* wr1, int ldr1, const float* wr0, int ldr0, float* wf) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= HN_RGB1 * HN_HIDDEN) return;
+    const int n = t / HN_HIDDEN, k = t % HN_HIDDEN;
+    float acc = 0.f;
+    for (int c = 0; c < HN_HIDDEN; ++c) acc = fmaf(__ldg(wr1 + (size_t)n * ldr1 + c), __ldg(wr0 + (size_t)c * ldr0 + k), acc);
+    wf[t] = acc;
+}
+
 static std::mutex g_mu;
 static bool g_uploaded[64] = {};
 
 }  // namespace hn
 
+static size_t packed_units_bytes() { return (size_t)(hn::kFwdUnits + hn::host_schedules().n_bwd_pack_units + hn::kBwdTUnits) * hn::kUnitBytes; }
+
 extern "C" size_t hn_packed_weights_bytes(void) {
-    return (size_t)(hn::kFwdUnits + hn::host_schedules().n_bwd_pack_units + hn::kBwdTUnits) * hn::kUnitBytes;
+    return packed_units_bytes() + (size_t)HN_RGB1 * HN_HIDDEN * sizeof(float);      // + the fp32 scratch of the fused RGB_layer_1 x RGB_layer_0 matrix
 }
 
 extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream) {
@@ -57,7 +70,7 @@ extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream
     for (int i = 0; i < 12; ++i)
         if (!w->w[i] || w->ld[i] <= 0) return set_error(HN_E_BADARG, "hn_pack_weights: null weight pointer or bad leading dimension");
     if (w->ld[W_L0] < HN_PE + 1 || w->l5_hidden_col < HN_PE || w->l5_hidden_col + HN_HIDDEN > w->ld[W_L5] ||
-        w->ld[W_R1] < HN_HIDDEN || w->ld[W_R2] != HN_RGB1)
+        w->ld[W_R1] < HN_HIDDEN || w->ld[W_R0] < HN_HIDDEN || w->ld[W_R2] != HN_RGB1)
         return set_error(HN_E_UNSUPPORTED, "hn_pack_weights: layer shapes do not match fg_CD_predictor (hidden 384, feat 256)");
     const HostSchedules& hs = host_schedules();
     int dev = 0;
@@ -74,8 +87,12 @@ extern "C" int hn_pack_weights(const hn_weights_t* w, void* packed, void* stream
             g_uploaded[dev] = true;
         }
     }
+    float* wf = reinterpret_cast<float*>((uint8_t*)packed + packed_units_bytes());
+    fuse_r0r1_kernel<<<(HN_RGB1 * HN_HIDDEN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w->w[W_R1], w->ld[W_R1], w->w[W_R0], w->ld[W_R0], wf);
+    if (int rc = check_launch("hn_pack_weights (RGB_layer_0 fold)")) return rc;
     PackArgs a;
     for (int i = 0; i < 12; ++i) { a.w[i] = w->w[i]; a.ld[i] = w->ld[i]; }
+    a.w[W_R1] = wf; a.ld[W_R1] = HN_HIDDEN;                           // every RGB_layer_1 unit is cut from the fused matrix
     a.l5_hidden_col = w->l5_hidden_col;
     a.n_units = kFwdUnits + hs.n_bwd_pack_units + kBwdTUnits;
     pack_kernel<<<a.n_units, 256, 0, (cudaStream_t)stream>>>(a, (uint8_t*)packed);

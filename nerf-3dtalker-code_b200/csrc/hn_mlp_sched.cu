@@ -282,7 +282,7 @@ void build_fwd(HostSchedules* hs) {
     std::vector<FwdLayer> layers;
     for (int l = 0; l < 8; ++l)
         layers.push_back({l, (l == 0 || l == 5) ? 1 : 0, l == 0 ? 0 : 6, {128, 128, 128}, 3, EPI_HIDDEN, l * HN_HIDDEN, HN_SLOT_H0 + 6 * l, 12 * l, l == 5, l == 7 ? 1 : 0, true});
-    layers.push_back({W_R0, 0, 6, {128, 128, 128}, 3, EPI_LINEAR, HN_BIAS_OFF_R0, HN_SLOT_R0, -1, false, 0, true});
+    // (RGB_layer_0 is folded into RGB_layer_1's weights and bias: see hn_mlp_sched.h)
     layers.push_back({W_R1, 0, 6, {128, 64, 0}, 2, EPI_HIDDEN, HN_BIAS_OFF_R1, HN_SLOT_X, 96, false, 0, true});
     layers.push_back({W_R2, 0, 3, {128, 128, 0}, 2, EPI_FEAT, HN_BIAS_OFF_R2, -1, -1, false, 0, false});
     build_tmem_chain(layers, false, &hs->fwd, hs->fwd_pack, kFwdUnits, kFwdEpis);
@@ -296,10 +296,9 @@ void build_bwdt(HostSchedules* hs) {
     std::vector<FwdLayer> layers;
     FwdLayer r2{W_R2, 4, 0, {128, 64, 0}, 2, EPI_GRAD_MASK, 0, HN_GSLOT_R1, 96, false, 0, true}; r2.transposed = true;
     layers.push_back(r2);
-    FwdLayer r1{W_R1, 0, 3, {128, 128, 128}, 3, EPI_GRAD_LINEAR, 0, HN_GSLOT_R0, -1, false, 0, true}; r1.transposed = true;
+    // (W_R1[:, :384] W_R0)^T: straight to dL/d(FeaExt_module_7 pre-activation), which also receives the density head's rank-1 term
+    FwdLayer r1{W_R1, 0, 3, {128, 128, 128}, 3, EPI_GRAD_DENSITY, 0, HN_GSLOT_Z0 + 6 * 7, 12 * 7, false, 0, true}; r1.transposed = true;
     layers.push_back(r1);
-    FwdLayer r0{W_R0, 0, 6, {128, 128, 128}, 3, EPI_GRAD_DENSITY, 0, HN_GSLOT_Z0 + 6 * 7, 12 * 7, false, 0, true}; r0.transposed = true;
-    layers.push_back(r0);
     for (int l = 7; l >= 1; --l) {
         // FeaExt_module_1^T closes the chain: its output (dZ of FeaExt_module_0) is only saved, no GEMM reads it
         FwdLayer s{l, 0, 6, {128, 128, 128}, 3, EPI_GRAD_MASK, 0, HN_GSLOT_Z0 + 6 * (l - 1), 12 * (l - 1), l == 5, 0, l > 1}; s.transposed = true;
@@ -340,10 +339,8 @@ HostSchedules* build() {
         Builder b; b.n_acc = 3; b.backward = true;
         ChainStep r2{}; r2.w_idx = W_R2; r2.n_kb = 4; r2.n_out = HN_RGB1; r2.kind = EPI_GRAD_MASK; r2.save_blk = HN_GSLOT_R1;
         r2.mask_word = 96; b.step(r2, true);
-        ChainStep r1{}; r1.w_idx = W_R1; r1.n_kb = 3; r1.n_out = HN_HIDDEN; r1.kind = EPI_GRAD_LINEAR; r1.save_blk = HN_GSLOT_R0;
-        r1.mask_word = -1; b.step(r1, false);
-        ChainStep r0{}; r0.w_idx = W_R0; r0.n_kb = 6; r0.n_out = HN_HIDDEN; r0.kind = EPI_GRAD_DENSITY;
-        r0.save_blk = HN_GSLOT_Z0 + 6 * 7; r0.mask_word = 12 * 7; b.step(r0, false);
+        ChainStep r1{}; r1.w_idx = W_R1; r1.n_kb = 3; r1.n_out = HN_HIDDEN; r1.kind = EPI_GRAD_DENSITY;       // fused (W_R1 W_R0)^T
+        r1.save_blk = HN_GSLOT_Z0 + 6 * 7; r1.mask_word = 12 * 7; b.step(r1, false);
         for (int l = 7; l >= 1; --l) {
             ChainStep s{};
             s.w_idx = l; s.n_kb = 6; s.n_out = HN_HIDDEN; s.kind = EPI_GRAD_MASK;

@@ -7,6 +7,13 @@
 //   EpiOp  : for every accumulator chunk, in completion order: bias, activation, destination
 // The weight producer, the MMA issuer and the epilogue warps all walk the same tables, so the three
 // roles cannot drift apart.  fg_CD_predictor layer list: NetWorks/models.py:29-59, forward :62-87.
+//
+// RGB_layer_0 has no activation (models.py:79-80: x = RGB_layer_0(x); x = relu(RGB_layer_1(cat[x, appea]))), so it never
+// runs as a layer here: hn_pack_weights multiplies it into RGB_layer_1's hidden block once per weight version
+// (W_f = W_R1[:, :384] W_R0, 192 x 384; hn_fold_bias adds W_R1[:, :384] b_R0 to RGB_layer_1's effective bias), the chains go
+// FeaExt_module_7 -> RGB_layer_1 directly ("optional algebraic fusion": -147 456 MAC per ray*sample
+// in each of the three passes, 12 fewer saved operand blocks per tile), and hn_unfuse_r0r1 maps dL/dW_f back to the two
+// weight gradients (two 192 x 384 x 384 products per step).
 #pragma once
 #include <stdint.h>
 
@@ -67,9 +74,9 @@ struct EpiOp {
     uint16_t mask_word;            // word offset in the per-sample mask row, 0xFFFF = none
 };
 
-constexpr int kFwdUnits = 170;     // 168 weight units + 2 empty ones that keep every ring stage a PAIR of units
+constexpr int kFwdUnits = 152;     // 150 weight units + 2 empty ones that keep every ring stage a PAIR of units
 constexpr int kFwdStages = kFwdUnits / 2;
-constexpr int kFwdEpis = 31;
+constexpr int kFwdEpis = 28;
 constexpr int kBwdUnitsMax = 176;
 constexpr int kBwdEpisMax = 36;
 
@@ -125,9 +132,9 @@ struct FwdTables { StageOp stage[kFwdStages]; EpiOp2 epi[kFwdEpis]; int n_stages
 // ---- data-gradient chain without dL/dPE (the training step), same machinery as the forward chain: gradients live in tensor
 // memory as the A operand, W^T units stream through the ring.  The first GEMM (RGB_layer_2^T) reads the four dL/dfeat
 // K blocks from a two-block shared-memory ring (a_src = kSrcSmem | k, slot k & 1, every block awaited: wait_src 4).
-constexpr int kBwdTUnits = 162;    // 2 * 81 stages (fits the forward tables' arrays: 81 <= 85 stages, 29 <= 31 chunks)
+constexpr int kBwdTUnits = 144;    // 2 * 72 stages (fits the forward tables' arrays: 72 <= 76 stages, 26 <= 28 chunks)
 constexpr int kBwdTStages = kBwdTUnits / 2;
-constexpr int kBwdTEpis = 29;
+constexpr int kBwdTEpis = 26;
 
 struct BwdTables { MmaOp mma[kBwdUnitsMax]; EpiOp epi[kBwdEpisMax]; int n_ops; int n_epis; int n_ready[3]; int n_empty[4]; };
 

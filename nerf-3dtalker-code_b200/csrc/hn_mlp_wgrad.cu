@@ -100,6 +100,7 @@ struct WArgs {
     const uint8_t* act; const uint8_t* grads; const uint8_t* dfeat_image;
     const float* grad_scale;
     float* dw[12]; int ld[12];
+    float* dwf;               // fused RGB_layer_1 x RGB_layer_0 gradient [192, 384] (r0_fused), replaces dw[W_R1] as the destination
     float* dbias;
     const WItem* items; int n_items; int n_tiles;
     int* status;
@@ -417,7 +418,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                         for (int i = 0; i < 8; ++i)
                             dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
                     } else if (row_ok && w.w_idx >= 0 && a.dw[w.w_idx]) {
-                        float* dst = a.dw[w.w_idx] + (size_t)(w.row0 + row) * a.ld[w.w_idx] + w.x_col[k] + h * 32;
+                        const bool to_f = (w.w_idx == W_R1 && a.dwf != nullptr);
+                        float* dst = (to_f ? a.dwf : a.dw[w.w_idx]) + (size_t)(w.row0 + row) * (to_f ? HN_HIDDEN : a.ld[w.w_idx]) + w.x_col[k] + h * 32;
                         const int nvalid = w.x_valid[k] - h * 32;
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -459,8 +461,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WArgs a, const 
     const float inv_scale = 1.0f / __ldg(a.grad_scale);
     const int* sl = slot_list + d.first;
     if (d.kind == 0) {
-        float* dw = a.dw[d.w_idx];
-        const int ld = a.ld[d.w_idx];
+        const bool to_f = (d.w_idx == W_R1 && a.dwf != nullptr);
+        float* dw = to_f ? a.dwf : a.dw[d.w_idx];
+        const int ld = to_f ? HN_HIDDEN : a.ld[d.w_idx];
         for (int e = threadIdx.x; e < d.rows * d.n_x * 64; e += blockDim.x) {
             const int r = e / (d.n_x * 64), c = e % (d.n_x * 64), k = c >> 6, cc = c & 63;
             if (cc >= d.x_valid[k]) continue;
@@ -502,15 +505,17 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     for (int l = 0; l < 8; ++l)
         layers.push_back({l, HN_HIDDEN, HN_GSLOT_Z0 + 6 * l, 0, l * HN_HIDDEN, l == 0 ? -1 : HN_SLOT_H0 + 6 * (l - 1), l == 0 ? 0 : 6,
                           l == 0 || l == 5, l == 5 ? a.l5_hidden_col : 0});
-    layers.push_back({W_R0, HN_HIDDEN, HN_GSLOT_R0, 0, HN_BIAS_OFF_R0, HN_SLOT_H0 + 6 * 7, 6, false, 0});
-    layers.push_back({W_R1, HN_RGB1, HN_GSLOT_R1, 0, HN_BIAS_OFF_R1, HN_SLOT_R0, 6, false, 0});
+    // r0_fused (the fast chains): RGB_layer_0 is not a layer (hn_mlp_sched.h) - RGB_layer_1's layer input is FeaExt_module_7's output
+    const bool fused = a.r0_fused != 0;
+    if (!fused) layers.push_back({W_R0, HN_HIDDEN, HN_GSLOT_R0, 0, HN_BIAS_OFF_R0, HN_SLOT_H0 + 6 * 7, 6, false, 0});
+    layers.push_back({W_R1, HN_RGB1, HN_GSLOT_R1, 0, HN_BIAS_OFF_R1, fused ? HN_SLOT_H0 + 6 * 7 : HN_SLOT_R0, 6, false, 0});
     layers.push_back({W_R2, HN_FEAT, 0, 1, HN_BIAS_OFF_R2, HN_SLOT_X, 3, false, 0});
     // The density head's weight gradient rides in RGB_layer_0's items (same layer input h7, read by the CUDA-core readers) whenever
     // that layer's own weight gradient is computed; otherwise it is a one-channel pseudo layer of its own.
     // Opt-in (HN_WGRAD_DENS_FOLD=1): measured on B200, the readers slow RGB_layer_0's stages by more than the pseudo layer costs (cluster
     // kernel 1.45 -> 1.79 ms against 0.095 ms for the separate density items), so the default keeps the pseudo layer.
     static const bool fold_env = [] { const char* e = getenv("HN_WGRAD_DENS_FOLD"); return e && atoi(e) != 0; }();
-    const bool dens_in_r0 = fold_env && !a.det_workspace && want_w && a.dw[W_R0] != nullptr && a.dw[W_DENSITY] != nullptr;   // (the fold has no deterministic reduction)
+    const bool dens_in_r0 = fold_env && !fused && !a.det_workspace && want_w && a.dw[W_R0] != nullptr && a.dw[W_DENSITY] != nullptr;   // (the fold has no deterministic reduction)
     if (!dens_in_r0) layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});
     auto active = [&](const LayerW& L) { return want_w || a.want_all_bias || L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1; };
     auto clustered = [&](const LayerW& L) { return want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
@@ -678,6 +683,8 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     if (!a || !a->act || !a->grads || !a->dfeat_image || !a->grad_scale || !a->status)
         return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: null pointer");
     if (int rc = check_geometry(a->B, a->n_rays, a->n_samples, "hn_mlp_bwd_weights")) return rc;
+    if (a->r0_fused && a->dw[W_R1] && !a->dwf)
+        return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: r0_fused needs the dwf buffer for RGB_layer_1's (fused) weight gradient");
     if (!a->items_workspace || a->items_workspace_bytes < hn_wgrad_workspace_bytes(a->B))
         return set_error(HN_E_BADARG, "hn_mlp_bwd_weights: items workspace missing or too small (hn_wgrad_workspace_bytes)");
     int dev = 0;
@@ -768,6 +775,7 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
     k.act = (const uint8_t*)a->act; k.grads = (const uint8_t*)a->grads; k.dfeat_image = (const uint8_t*)a->dfeat_image;
     k.grad_scale = a->grad_scale;
     for (int i = 0; i < 12; ++i) { k.dw[i] = a->dw[i]; k.ld[i] = a->ld[i]; }
+    k.dwf = a->r0_fused ? a->dwf : nullptr;
     k.dbias = a->dbias;
     k.n_tiles = (int)(total_samples(a->B, a->n_rays, a->n_samples) / HN_TILE);
     k.status = a->status;

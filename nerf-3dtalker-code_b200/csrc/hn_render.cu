@@ -12,7 +12,9 @@ extern "C" int hn_render_fwd(const hn_render_fwd_t* a, void* stream) {
     if (!a || !a->bias_eff || !a->feat || !a->sigma || !a->delta || !a->F || !a->bg_alpha || !a->status)
         return set_error(HN_E_BADARG, "hn_render_fwd: null pointer");
     if (a->fold.B != a->cam.B) return set_error(HN_E_BADARG, "hn_render_fwd: fold.B != cam.B");
-    if (int rc = hn_fold_bias(&a->fold, a->bias_eff, stream)) return rc;
+    hn_fold_t fold = a->fold;
+    fold.r0_fused = 1;                                              // the fused chains skip RGB_layer_0 (hn_mlp_sched.h)
+    if (int rc = hn_fold_bias(&fold, a->bias_eff, stream)) return rc;
     hn_mlp_fwd_t m{};
     m.cam = a->cam; m.bias = a->bias_eff; m.w_density = a->w_density; m.packed = a->packed;
     m.feat = a->feat; m.sigma = a->sigma; m.delta = a->delta; m.zvals = nullptr;
@@ -61,13 +63,29 @@ extern "C" int hn_render_bwd(const hn_render_bwd_t* a, void* stream) {
         w.B = a->cam.B; w.n_rays = a->cam.n_rays; w.n_samples = a->cam.n_samples;
         w.act = a->act; w.grads = a->grads; w.dfeat_image = a->dfeat_image; w.grad_scale = a->scale;
         for (int i = 0; i < 12; ++i) { w.dw[i] = a->dw[i]; w.ld[i] = a->ld[i]; }
+        // RGB_layer_0 is folded into RGB_layer_1: their weight gradients come from dL/dW_f (hn_unfuse_r0r1 below)
+        const bool want_r = a->dw[9] || a->dw[10];
+        if (want_r && (!a->dwf || !a->fold.wr0))
+            return set_error(HN_E_BADARG, "hn_render_bwd: RGB_layer_0 / _1 weight gradients need the dwf workspace and fold.wr0");
+        w.r0_fused = 1; w.dwf = want_r ? a->dwf : nullptr;
+        w.dw[9] = nullptr; w.dw[10] = want_r ? a->dwf : nullptr;     // (non-NULL marks "wanted"; the kernel writes to dwf)
         w.l5_hidden_col = a->l5_hidden_col; w.dbias = a->dbias_eff;
         w.items_workspace = a->items_workspace; w.items_workspace_bytes = a->items_workspace_bytes; w.status = a->status;
         for (int i = 0; i < 12; ++i)
             if (i != 0 && i != 5 && i != 10 && a->fold_grads.dbias[i]) w.want_all_bias = 1;   // beyond the latent-folded layers (FeaExt_module_0, _5, RGB_layer_1)
         if (int rc = hn_mlp_bwd_weights(&w, stream)) return rc;
-        if (need_fold)
-            if (int rc = hn_fold_bias_bwd(&a->fold, a->dbias_eff, &a->fold_grads, stream)) return rc;
+        if (want_r || a->fold_grads.dbias[9]) {
+            hn_unfuse_t u{};
+            u.B = a->cam.B; u.wr0 = a->fold.wr0; u.ldr0 = a->fold.ldr0; u.wr1 = a->fold.wr1; u.ldr1 = a->fold.ldr1; u.b_r0 = a->fold.bias[9];
+            u.dwf = a->dwf; u.dbias_eff = a->dbias_eff; u.dwr0 = a->dw[9]; u.dwr1 = a->dw[10];
+            if (!u.wr0 || !u.dwf) return set_error(HN_E_BADARG, "hn_render_bwd: RGB_layer_0's bias gradient needs fold.wr0 and the dwf workspace");
+            if (int rc = hn_unfuse_r0r1(&u, stream)) return rc;
+        }
+        if (need_fold) {
+            hn_fold_t fold = a->fold;
+            fold.r0_fused = 1;
+            if (int rc = hn_fold_bias_bwd(&fold, a->dbias_eff, &a->fold_grads, stream)) return rc;
+        }
     }
     if (need_cam)
         if (int rc = hn_camera_bwd(&a->cam, a->g_ray_o, a->g_ray_v, a->g_ray_l, a->dR, a->dT, a->dKinv, stream)) return rc;

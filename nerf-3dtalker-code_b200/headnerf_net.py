@@ -163,11 +163,12 @@ class HeadNeRFNet(nn.Module):
         return {"w": [m.weight.grad if m.weight.requires_grad else None for m in lay],
                 "b": [m.bias.grad if m.bias.requires_grad else None for m in lay]}
 
-    def _fold_biases_cuda(self, shape_code, appea_code, audiostyle, grad_into):
-        """Effective bias row per batch item through the library (hn_fold_bias): [B, HN_BIAS_STRIDE]."""
+    def _fold_biases_cuda(self, shape_code, appea_code, audiostyle, grad_into, r0_fused=False):
+        """Effective bias row per batch item through the library (hn_fold_bias): [B, HN_BIAS_STRIDE].  r0_fused (the fast kernels, which
+        run RGB_layer_0 multiplied into RGB_layer_1): RGB_layer_1's row also carries W_R1[:, :384] b_R0."""
         lay = self.fg_CD_predictor.layers()
         return ops.FoldBiasFunction.apply(shape_code, audiostyle, appea_code, lay[0].weight, lay[5].weight, lay[10].weight,
-                                          *[m.bias for m in lay], {"grad_into": grad_into})
+                                          *[m.bias for m in lay], {"grad_into": grad_into, "r0_fused": r0_fused})
 
     def _fold_biases(self, shape_code, appea_code, audiostyle):
         """Effective bias row per batch item: [B, HN_BIAS_STRIDE].  Plain-PyTorch statement of the folding
@@ -230,13 +231,15 @@ class HeadNeRFNet(nn.Module):
         if self.precision == "auto" and not high:
             high = self._calibrate(mode, batch_xy, audiostyle, shape_code, appea_code, batch_Rmats, batch_Tvecs, batch_inv_inmats, t_rand) == "high"
         grad_into = self._grad_into()
-        bias = self._fold_biases_cuda(shape_code.float(), appea_code.float(), audiostyle.float(), grad_into)
+        bias = self._fold_biases_cuda(shape_code.float(), appea_code.float(), audiostyle.float(), grad_into, r0_fused=not high)
         meta = {"n_samples": ns, "world_z1": self.opt.world_z1, "world_z2": self.opt.world_z2,
                 "l5_hidden_col": L.PE + self.shape_dims, "precision": "high" if high else "fast", "grad_into": None if high else grad_into,
                 "grad_target": float(getattr(self, "grad_target", 1024.0 if high else 64.0)),
                 # frozen weights with trainable biases: the weight pass must still visit the layers whose bias gradients no latent code needs
                 "all_bias": any(m.bias.requires_grad for i, m in enumerate(self.fg_CD_predictor.layers()) if i not in (0, 5, 10)),
-                "deterministic": self._deterministic(), "cache": self._kernel_cache}
+                "deterministic": self._deterministic(), "cache": self._kernel_cache,
+                "r0_fused": not high, "b_r0": self.fg_CD_predictor.RGB_layer_0.bias.detach(),
+                "need_b_r0": self.fg_CD_predictor.RGB_layer_0.bias.requires_grad}
         if high:
             ws, meta["packed_hl"] = self._packed_weights_precise()
         else:

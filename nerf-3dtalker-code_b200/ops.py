@@ -304,8 +304,11 @@ class FoldBiasFunction(torch.autograd.Function):
     buffers, "b": 12 bias-gradient buffers} to accumulate into directly instead of returning parameter gradients."""
 
     @staticmethod
-    def _args(shape, audio, appea, w0, w5, wr1, biases):
+    def _args(shape, audio, appea, w0, w5, wr1, biases, r0_fused=False, wr0=None):
         a = L.Fold()
+        a.r0_fused = 1 if r0_fused else 0                           # the fast chains skip RGB_layer_0 (csrc/hn_mlp_sched.h)
+        if wr0 is not None:
+            a.wr0, a.ldr0 = wr0.data_ptr(), wr0.numel() // wr0.shape[0]
         a.B, a.shape_dims, a.appea_dims = shape.shape[0], shape.shape[1], appea.shape[1]
         a.w0, a.ld0 = w0.data_ptr(), w0.numel() // w0.shape[0]
         a.w5, a.ld5 = w5.data_ptr(), w5.numel() // w5.shape[0]
@@ -325,7 +328,7 @@ class FoldBiasFunction(torch.autograd.Function):
         w0, w5, wr1 = (_dev_f32(w.detach(), "folded weight") for w in (w0, w5, wr1))
         bs = [_dev_f32(b.detach(), "bias") for b in biases]
         out = torch.empty(shape.shape[0], L.BIAS_STRIDE, device=shape.device)
-        a = FoldBiasFunction._args(shape, audio, appea, w0, w5, wr1, bs)
+        a = FoldBiasFunction._args(shape, audio, appea, w0, w5, wr1, bs, meta.get("r0_fused", False))
         _call("hn_fold_bias", lib.hn_fold_bias, C.byref(a), _ptr(out), _stream())
         ctx.save_for_backward(shape, audio, appea, w0, w5, wr1, *bs)
         ctx.meta = meta
@@ -339,7 +342,7 @@ class FoldBiasFunction(torch.autograd.Function):
         need = ctx.needs_input_grad
         into = ctx.meta.get("grad_into")
         g = g.contiguous().float()
-        a = FoldBiasFunction._args(shape, audio, appea, w0, w5, wr1, bs)
+        a = FoldBiasFunction._args(shape, audio, appea, w0, w5, wr1, bs, ctx.meta.get("r0_fused", False))
         out = L.FoldGrads()
         res = [None] * 19
         for i, (name, t) in enumerate((("dshape", shape), ("daudio", audio), ("dappea", appea))):
@@ -443,8 +446,12 @@ class RenderFunction(torch.autograd.Function):
         into = meta.get("grad_into")
         into_w = into["w"] if into else None
         dst_w = [_grad_dst(into_w, i, weights[i]) if (need_w and need[6 + i]) else None for i in range(12)]
+        # RGB_layer_0 is folded into RGB_layer_1 (csrc/hn_mlp_sched.h): the weight pass delivers dL/dW_f, hn_unfuse_r0r1 the two gradients
+        need_r = need_w and (need[6 + 9] or need[6 + 10])
+        run_unfuse = need_r or (need_bias and meta.get("need_b_r0", False))
         sizes = {"status": 64, "g_o": B * n_rays * 3 if need_cam else 0, "g_v": B * n_rays * 3 if need_cam else 0,
-                 "g_l": B * n_rays if need_cam else 0, "dbias": B * L.BIAS_STRIDE if save_grads else 0}
+                 "g_l": B * n_rays if need_cam else 0, "dbias": B * L.BIAS_STRIDE if save_grads else 0,
+                 "dwf": L.RGB1 * L.HIDDEN if run_unfuse else 0}
         for i in range(12):
             sizes[f"w{i}"] = weights[i].numel() if (need_w and need[6 + i] and dst_w[i] is None) else 0
         zbuf = torch.zeros(sum(sizes.values()), device=dev)
@@ -484,6 +491,12 @@ class RenderFunction(torch.autograd.Function):
                 else:
                     w.dw[i] = None
                 w.ld[i] = wt.numel() // wt.shape[0]
+            dst_r0 = (dst_w[9] if dst_w[9] is not None else dws[9]) if (need_w and need[6 + 9]) else None
+            dst_r1 = (dst_w[10] if dst_w[10] is not None else dws[10]) if (need_w and need[6 + 10]) else None
+            w.r0_fused = 1
+            w.dw[9] = None
+            w.dw[10] = views["dwf"].data_ptr() if need_r else None   # (non-NULL = "RGB_layer_1's fused gradient is wanted": it goes to dwf)
+            w.dwf = _ptr(views["dwf"]) if need_r else None
             w.l5_hidden_col = meta["l5_hidden_col"]
             w.dbias, w.status = _ptr(dbias), _ptr(status)
             w.want_all_bias = 1 if (need_bias and meta.get("all_bias", True)) else 0
@@ -491,6 +504,14 @@ class RenderFunction(torch.autograd.Function):
             w.det_workspace, w.det_workspace_bytes = _ptr(det_ws), (det_ws.numel() if det_ws is not None else 0)
             # with weight gradients the library launches two kernels: 3-CTA clusters for the 384-wide layers, then the rest
             _call("hn_mlp_bwd_weights", lib.hn_mlp_bwd_weights, C.byref(w), _stream(), kernels=3 if need_w else 1)
+            if run_unfuse:
+                u = L.Unfuse()
+                u.B = B
+                u.wr0, u.ldr0 = _ptr(weights[9]), weights[9].numel() // weights[9].shape[0]
+                u.wr1, u.ldr1 = _ptr(weights[10]), weights[10].numel() // weights[10].shape[0]
+                u.b_r0, u.dwf, u.dbias_eff = _ptr(meta["b_r0"]), _ptr(views["dwf"]), _ptr(dbias)
+                u.dwr0, u.dwr1 = _ptr(dst_r0), _ptr(dst_r1)
+                _call("hn_unfuse_r0r1", lib.hn_unfuse_r0r1, C.byref(u), _stream())
         if _DEBUG_SYNC:
             check_status(status, "hn_mlp_bwd")
         FAULTS.watch(status, "hn_mlp_bwd_data / hn_mlp_bwd_weights")

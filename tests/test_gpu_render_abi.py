@@ -48,7 +48,7 @@ def test_one_call_render_matches_module(hn):
     packed = ops.pack_weights(ws, L.PE + net.shape_dims)
     T3 = x["batch_Tvecs"].reshape(B, 3).contiguous()
     cam = ops._camera(x["batch_xy"], x["batch_Rmats"], T3, x["batch_inv_inmats"], None, ns, net.opt.world_z1, net.opt.world_z2)
-    fold = ops.FoldBiasFunction._args(x["shape_code"], x["audiostyle"], x["appea_code"], ws[0], ws[5], ws[10], bs)
+    fold = ops.FoldBiasFunction._args(x["shape_code"], x["audiostyle"], x["appea_code"], ws[0], ws[5], ws[10], bs, wr0=ws[9])
     f32 = lambda *s: torch.empty(*s, device=DEV)
     z32 = lambda *s: torch.zeros(*s, device=DEV)
     u8 = lambda n: torch.empty(n, dtype=torch.uint8, device=DEV)
@@ -84,6 +84,8 @@ def test_one_call_render_matches_module(hn):
         b.ld[i] = ws[i].numel() // ws[i].shape[0]
         b.fold_grads.dbias[i] = dbs[i].data_ptr()
     b.l5_hidden_col = L.PE + net.shape_dims
+    dwf = z32(L.RGB1, L.HIDDEN)                                      # dL/d(W_R1[:, :384] W_R0): RGB_layer_0 is folded into RGB_layer_1
+    b.dwf = _p(dwf)
     dshape, daudio, dappea = torch.empty_like(x["shape_code"]), torch.empty_like(x["audiostyle"]), torch.empty_like(x["appea_code"])
     b.fold_grads.dshape, b.fold_grads.daudio, b.fold_grads.dappea = dshape.data_ptr(), daudio.data_ptr(), dappea.data_ptr()
     b.fold_grads.dw0, b.fold_grads.dw5, b.fold_grads.dwr1 = dws[0].data_ptr(), dws[5].data_ptr(), dws[10].data_ptr()

@@ -126,7 +126,7 @@ def _replay_fwd(stages, epi, n_tiles, late, tile_flip=1):
 @pytest.mark.parametrize("late", [False, True])
 def test_forward_tmem_schedule(dump, late):
     stages, epi = dump("fwd")
-    assert len(stages) == 85 and len(epi) == 31
+    assert len(stages) == 76 and len(epi) == 28          # 10 GEMMs: RGB_layer_0 is folded into RGB_layer_1 (csrc/hn_mlp_sched.h)
     for c in range(3):
         arrivals = sum(1 for e in epi if e["ready"] == c)
         waits = sum(1 for m in stages if m["wait_src"] == 1 + c)
@@ -136,14 +136,17 @@ def test_forward_tmem_schedule(dump, late):
     for i, e in enumerate(epi):
         if e["wait_next"]:
             assert i + 1 < len(epi) and not epi[i + 1]["wait_next"] and epi[i + 1]["ready"] == 1 and e["ready"] == 0
-    _replay_fwd(stages, epi, 4, late)
+    assert dump.tile_flip == 0                      # even number of layers: the TMEM halves must NOT swap between tiles
+    _replay_fwd(stages, epi, 4, late, tile_flip=0)
+    with pytest.raises(AssertionError):             # ... and the replay does catch the cross-tile clobber if they did
+        _replay_fwd(stages, epi, 4, True, tile_flip=1)
 
 
 @pytest.mark.parametrize("late", [False, True])
 def test_data_gradient_tmem_schedule(dump, late):
     """The data-gradient chain without dL/dPE runs on the same tensor-memory machinery as the forward chain."""
     stages, epi = dump("bwdt")
-    assert len(stages) == 81 and len(epi) == 29
+    assert len(stages) == 72 and len(epi) == 26
     for c in range(3):
         assert sum(1 for e in epi if e["ready"] == c) == sum(1 for m in stages if m["wait_src"] == 1 + c), f"a_ready[{c}]"
     assert sum(m["commit"] for m in stages) == len(epi)
@@ -153,10 +156,10 @@ def test_data_gradient_tmem_schedule(dump, late):
     for i, e in enumerate(epi):
         if e["wait_next"]:
             assert i + 1 < len(epi) and not epi[i + 1]["wait_next"] and epi[i + 1]["ready"] == 1 and e["ready"] == 0
-    assert dump.tile_flip == 0                      # even number of layers: the halves must NOT swap between tiles
-    _replay_fwd(stages, epi, 4, late, tile_flip=0)
-    with pytest.raises(AssertionError):             # ... and the replay does catch the cross-tile clobber if they did
-        _replay_fwd(stages, epi, 4, True, tile_flip=1)
+    assert dump.tile_flip == 1                      # nine layers: odd tiles swap the TMEM halves
+    _replay_fwd(stages, epi, 4, late, tile_flip=1)
+    with pytest.raises(AssertionError):             # ... and the replay does catch the cross-tile clobber if they did not
+        _replay_fwd(stages, epi, 4, True, tile_flip=0)
 
 
 @pytest.mark.parametrize("which", ["bwd"])

@@ -68,10 +68,10 @@ with open(os.path.join(prof, f"{tag}_ncu_full_summary.md"), "w") as f:
                 traffic[api] = {"dram_gbytes_per_launch": round(tr, 4),
                                 "tensor_pipe_pct": round(float(vals["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]), 2),
                                 "dram_pct": round(float(vals["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]), 2)}
-prev = os.path.join(prof, "r01_traffic.json")
+prev = os.path.join(prof, "r01h_traffic.json")
 if os.path.isfile(prev):                                                           # kernels outside this capture window keep their last figure
     for k, v in json.load(open(prev))["kernels"].items():
-        traffic.setdefault(k, dict(v, note="from profiles/r01_traffic.json (kernel unchanged, not in this capture)"))
+        traffic.setdefault(k, dict(v, note="from profiles/r01h_traffic.json (kernel not in this capture)"))
 with open(os.path.join(prof, f"{tag}_traffic.json"), "w") as f:
     json.dump({"source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, Reso64 batch 2)", "kernels": traffic}, f, indent=1)
 print(json.dumps(traffic, indent=1))
