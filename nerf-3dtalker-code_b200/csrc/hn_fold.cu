@@ -218,12 +218,10 @@ __global__ void __launch_bounds__(256) unfuse_r1_kernel(const hn_unfuse_t a) {
     const int n = wid / HN_HIDDEN, c = wid % HN_HIDDEN;
     float acc = 0.f;
     for (int k = lane; k < HN_HIDDEN; k += 32) acc = fmaf(__ldg(a.dwf + (size_t)n * HN_HIDDEN + k), __ldg(a.wr0 + (size_t)c * a.ldr0 + k), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-        float g = 0.f;
-        for (int b = 0; b < a.B; ++b) g += a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R1 + n];
-        a.dwr1[(size_t)n * a.ldr1 + c] += fmaf(g, __ldg(a.b_r0 + c), acc);
-    }
+    float g = 0.f;                                                  // the items' bias-row gradients: lanes in parallel, folded with acc
+    for (int b = lane; b < a.B; b += 32) g += a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R1 + n];
+    acc = warp_sum(fmaf(g, __ldg(a.b_r0 + c), acc));
+    if (lane == 0) a.dwr1[(size_t)n * a.ldr1 + c] += acc;
 }
 
 __global__ void __launch_bounds__(256) unfuse_r0_kernel(const hn_unfuse_t a) {

@@ -75,6 +75,7 @@ struct WItem {
     int16_t dens_x0;
     int32_t dens_blk;         // block of the density head's gradient column in `grads`
     int32_t slot;             // deterministic mode: index of this item's private partial-sum slice
+    int32_t dens_row1;        // 1 + accumulator row that holds the density head's weight / bias gradient, 0 = none (see build_items)
 };
 
 struct WShared {
@@ -417,6 +418,10 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                    } else if (w.dens_row1 && row == w.dens_row1 - 1) {
+                        float* dst = a.dw[W_DENSITY] + w.x_col[k] + h * 32;     // the free density row (build_items): dW_density = sum dsigma x h7
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]) * inv_scale);
                     } else if (row_ok && w.w_idx >= 0 && a.dw[w.w_idx]) {
                         const bool to_f = (w.w_idx == W_R1 && a.dwf != nullptr);
                         float* dst = (to_f ? a.dwf : a.dw[w.w_idx]) + (size_t)(w.row0 + row) * (to_f ? HN_HIDDEN : a.ld[w.w_idx]) + w.x_col[k] + h * 32;
@@ -433,6 +438,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WArgs a) 
                 tmem_ld32(tmem_base + lane_base + kBiasCol, v);
                 tmem_ld_wait();
                 if (slot) slot[kDetAccFloats + row] = __uint_as_float(v[0]);
+                else if (w.dens_row1 && row == w.dens_row1 - 1 && a.dbias)
+                    atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + HN_BIAS_OFF_DENSITY, __uint_as_float(v[0]) * inv_scale);
                 else if (row_ok && want_bias)
                     atomicAdd(a.dbias + (size_t)w.b * HN_BIAS_STRIDE + w.bias_off + row, __uint_as_float(v[0]) * inv_scale);
             }
@@ -454,6 +461,7 @@ struct WDst {
     int32_t w_idx, row0, rows, n_x, b, bias_off;
     int16_t x_col[kWMaxX], x_valid[kWMaxX];
     int32_t first, count;     // range in the slot list
+    int32_t src_row;          // first accumulator row of the slices that feeds this destination (64 for the free density row)
 };
 
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WArgs a, const WDst* dsts, const int* slot_list, const int bias_mode) {
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WArgs a, const 
             const int r = e / (d.n_x * 64), c = e % (d.n_x * 64), k = c >> 6, cc = c & 63;
             if (cc >= d.x_valid[k]) continue;
             float s = 0.f;
-            for (int i = 0; i < d.count; ++i) s += a.partials[(size_t)sl[i] * kDetSlotFloats + (size_t)r * 448 + c];
+            for (int i = 0; i < d.count; ++i) s += a.partials[(size_t)sl[i] * kDetSlotFloats + (size_t)(d.src_row + r) * 448 + c];
             dw[(size_t)(d.row0 + r) * ld + d.x_col[k] + cc] += s * inv_scale;
         }
     } else if (d.kind == 1) {
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WArgs a, const 
             float s = 0.f;
             for (int i = 0; i < d.count; ++i) {
                 const float* p = a.partials + (size_t)sl[i] * kDetSlotFloats + kDetAccFloats;
-                s += bias_mode == 1 ? p[r] : (p[128 + r] + p[256 + r]);
+                s += bias_mode == 1 ? p[d.src_row + r] : (p[128 + d.src_row + r] + p[256 + d.src_row + r]);
             }
             a.dbias[(size_t)d.b * HN_BIAS_STRIDE + d.bias_off + r] += s * inv_scale;
         }
@@ -516,7 +524,14 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
     // kernel 1.45 -> 1.79 ms against 0.095 ms for the separate density items), so the default keeps the pseudo layer.
     static const bool fold_env = [] { const char* e = getenv("HN_WGRAD_DENS_FOLD"); return e && atoi(e) != 0; }();
     const bool dens_in_r0 = fold_env && !fused && !a.det_workspace && want_w && a.dw[W_R0] != nullptr && a.dw[W_DENSITY] != nullptr;   // (the fold has no deterministic reduction)
-    if (!dens_in_r0) layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});
+    // With RGB_layer_0 folded away, RGB_layer_1's layer input IS h7, and the second gradient block of its 64-row second chunk is
+    // the density head's gradient block (slot HN_GSLOT_R1 + 3 = HN_GSLOT_DENS, column 0 = dL/d(pre-ReLU density)): row 64 of that
+    // chunk's accumulator already holds sum_m dsigma_m h7_m - the density head's weight gradient - and its bias column the bias
+    // gradient.  The flush writes that row out and the one-channel pseudo layer (6 blocks of h7 re-read, an M = 128 MMA for one
+    // row) is not needed.
+    const bool dens_free = fused && want_w && a.dwf != nullptr && a.dw[W_R1] != nullptr && a.dw[W_DENSITY] != nullptr;
+    static_assert(HN_GSLOT_R1 + 3 == HN_GSLOT_DENS, "the density gradient block must follow RGB_layer_1's three blocks");
+    if (!dens_in_r0 && !dens_free) layers.push_back({W_DENSITY, 1, HN_GSLOT_DENS, 0, HN_BIAS_OFF_DENSITY, HN_SLOT_H0 + 6 * 7, 6, false, 0});
     auto active = [&](const LayerW& L) { return want_w || a.want_all_bias || L.w_idx == W_L0 || L.w_idx == W_L5 || L.w_idx == W_R1; };
     auto clustered = [&](const LayerW& L) { return want_w && n_clusters > 0 && L.n_out == HN_HIDDEN && a.dw[L.w_idx] != nullptr; };
     auto duoed = [&](const LayerW& L) { return want_w && n_duos > 0 && (L.w_idx == W_R1 || L.w_idx == W_R2) && a.dw[L.w_idx] != nullptr; };
@@ -543,6 +558,7 @@ static void build_items(const hn_mlp_bwd_weights_t& a, int n_sm, int n_clusters,
             if (L.pe) { w.x_blk[n] = HN_SLOT_PE; w.x_col[n] = 0; w.x_valid[n] = HN_PE; ++n; }
         }
         w.n_x = (int16_t)n;
+        if (dens_free && L.w_idx == W_R1 && j == 1) w.dens_row1 = 64 + 1;
         if (dens_in_r0 && L.w_idx == W_R0) {                        // chunk j covers h7 columns [128 j, 128 j + 128)
             w.dens = (int16_t)(j == 0 ? 2 : 1);
             w.dens_x0 = (int16_t)(2 * j);
@@ -752,6 +768,25 @@ extern "C" int hn_mlp_bwd_weights(const hn_mlp_bwd_weights_t* a, void* stream) {
                     dsts.push_back(d); lists.emplace_back();
                 }
                 lists[it->second].push_back(w.slot);
+            }
+            if (w.dens_row1) {                                           // the free density row of RGB_layer_1's second chunk
+                auto it = by_w.find({(int)W_DENSITY, 0});
+                if (it == by_w.end()) {
+                    WDst d{}; d.kind = 0; d.w_idx = W_DENSITY; d.row0 = 0; d.rows = 1; d.n_x = w.n_x; d.src_row = w.dens_row1 - 1;
+                    for (int q = 0; q < w.n_x; ++q) { d.x_col[q] = w.x_col[q]; d.x_valid[q] = w.x_valid[q]; }
+                    it = by_w.emplace(std::make_pair((int)W_DENSITY, 0), (int)dsts.size()).first;
+                    dsts.push_back(d); lists.emplace_back();
+                }
+                lists[it->second].push_back(w.slot);
+                if (a->dbias) {
+                    auto ib = by_b.find({w.b, (int)HN_BIAS_OFF_DENSITY});
+                    if (ib == by_b.end()) {
+                        WDst d{}; d.kind = 1; d.b = w.b; d.bias_off = HN_BIAS_OFF_DENSITY; d.rows = 1; d.src_row = w.dens_row1 - 1;
+                        ib = by_b.emplace(std::make_pair((int)w.b, (int)HN_BIAS_OFF_DENSITY), (int)dsts.size()).first;
+                        dsts.push_back(d); lists.emplace_back();
+                    }
+                    lists[ib->second].push_back(w.slot);
+                }
             }
             if (w.bias_off >= 0 && a->dbias) {
                 auto it = by_b.find({w.b, w.bias_off});
