@@ -192,6 +192,8 @@ typedef struct {
     int* status;
 } hn_mlp_bwd_data_t;
 
+/* (SURVEY.md section 8b lists a separate hn_sample_pe_bwd: it is folded in here - with g_ray_* given this kernel also runs the
+ * positional-encoding backward and the per-ray sampling reductions, and hn_camera_bwd finishes the chain to R / T / K^-1.)      */
 int hn_mlp_bwd_data(const hn_mlp_bwd_data_t* a, void* stream);
 
 /* MLP backward, weight path: contraction over all samples of (pre-activation gradient)^T x (layer input).

@@ -119,11 +119,25 @@ def test_consumer_graph_capture_matches_eager(hn):
         return out["coarse_dict"]["merge_img"].detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
 
     img0, g0 = step()
+    keys0 = list(net.state_dict().keys())
     net.capture_consumer_graph(2)
     for _ in range(2):                                            # replay twice: static buffers must be refreshed every time
         img1, g1 = step()
+    # while captured: the module tree and the checkpoint layout are untouched, and every call the graphs were NOT captured for
+    # (no autograd, other batch sizes, the background map alone) runs the eager module with the right shapes
+    assert list(net.state_dict().keys()) == keys0 and not any("_consumer_graph" in k for k in keys0)
+    call = lambda xs: net("test", xs["batch_xy"], None, xs["audiostyle"], None, xs["shape_code"], xs["appea_code"], xs["batch_Rmats"], xs["batch_Tvecs"], xs["batch_inv_inmats"])
+    with torch.no_grad():                                         # validation without .eval(): training flag still matches the capture
+        out = call(x)
+    assert out["coarse_dict"]["merge_img"].shape == (2, 3, 64, 64) and out["coarse_dict"]["bg_img"].shape == (1, 3, 64, 64)
+    assert (out["coarse_dict"]["merge_img"] - img0).abs().max() <= 1e-5
+    x3 = {k: v.to(DEV) for k, v in O.synthetic_inputs(opt, 3, seed=3).items()}
+    assert call(x3)["coarse_dict"]["merge_img"].shape == (3, 3, 64, 64)       # another batch size, autograd on: eager, no size mismatch
     net.release_consumer_graph()
-    assert (img0 - img1).abs().max() <= 1e-5
-    assert set(g0) == set(g1)
+    assert "forward" not in net.neural_render.__dict__           # the dispatcher is gone: plain eager launches again
+    img2, g2 = step()
+    assert (img0 - img1).abs().max() <= 1e-5 and (img0 - img2).abs().max() <= 1e-5
+    assert set(g0) == set(g1) == set(g2)
     for k in g0:
         assert (g0[k] - g1[k]).abs().max() <= 2e-3 * (g0[k].abs().max() + 1e-12), k
+        assert (g0[k] - g2[k]).abs().max() <= 2e-3 * (g0[k].abs().max() + 1e-12), k

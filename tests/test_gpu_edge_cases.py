@@ -93,6 +93,33 @@ def test_gaze_columns(hn):
     assert worst[0] >= 0.999, worst
 
 
+def test_bias_only_fine_tuning_gets_every_bias_gradient(hn):
+    """All twelve weights frozen, biases trainable: the weight pass must still visit the layers whose bias gradients no latent code
+    needs (hn_mlp_bwd_weights_t.want_all_bias) - round 1 returned silent zeros for nine of the twelve bias vectors."""
+    opt, sd, net = _net(hn, 8, 64, variant="init")               # (random-init weights: the single-pass kernels' own territory)
+    for n, p in net.fg_CD_predictor.named_parameters():
+        p.requires_grad_(n.endswith(".bias"))
+    inp = O.synthetic_inputs(opt, 2, seed=31)
+    sdo = {k: v.clone().requires_grad_(k.startswith("fg_CD_predictor") and k.endswith(".bias")) for k, v in sd.items()}
+    r = O.render_features(sdo, opt, "test", inp["batch_xy"], inp["audiostyle"], inp["shape_code"], inp["appea_code"],
+                          inp["batch_Rmats"], inp["batch_Tvecs"], inp["batch_inv_inmats"])
+    gen = torch.Generator().manual_seed(3)
+    gF, gb = torch.randn(r["F"].shape, generator=gen), torch.randn(r["bg_alpha"].shape, generator=gen)
+    torch.autograd.backward([r["F"], r["bg_alpha"]], [gF, gb])
+    xc = {k: v.to(DEV) for k, v in inp.items()}
+    Fm, bg = net.render_rays("test", xc["batch_xy"], xc["audiostyle"], xc["shape_code"], xc["appea_code"],
+                             xc["batch_Rmats"], xc["batch_Tvecs"], xc["batch_inv_inmats"])
+    torch.autograd.backward([Fm, bg], [gF.permute(0, 2, 1).contiguous().to(DEV), gb[:, 0].contiguous().to(DEV)])
+    net.check_faults()
+    for n, p in net.fg_CD_predictor.named_parameters():
+        if n.endswith(".bias"):
+            ref = sdo["fg_CD_predictor." + n].grad
+            assert p.grad is not None and float(ref.abs().max()) > 0, n
+            assert cosine(p.grad, ref) >= 0.999, (n, cosine(p.grad, ref))
+        else:
+            assert p.grad is None, n
+
+
 def test_error_behaviour(hn):
     with pytest.raises(hn._lib.HeadNeRFLibraryError):           # 48 samples per ray: outside what the kernels are specialised for
         opt, sd, net = _net(hn, 8, 48)
