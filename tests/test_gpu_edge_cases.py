@@ -96,7 +96,8 @@ def test_gaze_columns(hn):
 def test_bias_only_fine_tuning_gets_every_bias_gradient(hn):
     """All twelve weights frozen, biases trainable: the weight pass must still visit the layers whose bias gradients no latent code
     needs (hn_mlp_bwd_weights_t.want_all_bias) - round 1 returned silent zeros for nine of the twelve bias vectors."""
-    opt, sd, net = _net(hn, 8, 64, variant="init")               # (random-init weights: the single-pass kernels' own territory)
+    opt, sd, net = _net(hn, 16, 64, variant="init")              # random-init weights: the single-pass kernels' own territory; 256 rays
+                                                                  # per item (with 64 the deepest layer's gradient sits at 0.9990)
     for n, p in net.fg_CD_predictor.named_parameters():
         p.requires_grad_(n.endswith(".bias"))
     inp = O.synthetic_inputs(opt, 2, seed=31)
