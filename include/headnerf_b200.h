@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HN_ABI_VERSION 3
+#define HN_ABI_VERSION 4
 
 /* error codes (negative = argument / configuration errors) */
 #define HN_OK 0
@@ -462,6 +462,51 @@ typedef struct {
 } hn_fine_sample_t;
 
 int hn_fine_sample(const hn_fine_sample_t* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The consumer: NeuralRenderer.forward (NetWorks/neural_renderer.py:72-91) with its
+ * PixelShuffleUpsample blocks (NetWorks/PixelShuffleUpsample.py:36-45), forward and backward, one call per direction.
+ * Every 1x1 convolution, LeakyReLU(0.2), RGB head + skip sum and the final sigmoid run in one grouped tensor-core GEMM
+ * kernel (tcgen05 kind::tf32 - the precision cuDNN's default gives the reference on this GPU - fp32 accumulation) over the
+ * NCHW planes; the tails are hn_upsample_tail_* / hn_rgb_upsample_*.  Weights are the state-dict tensors as they are:
+ * Conv2d weight [out, in, 1, 1] = row-major [out, in].  channels(i) = max(feat_nc >> i, min_feat), resolution(i) =
+ * featmap_size << i, out_dim = 3.  Supported: 1..4 blocks, channels a multiple of 4 and <= 256 after the first block.   */
+#define HN_NR_MAX_BLOCKS 4
+typedef struct {
+    int B, n_blocks, feat_nc, min_feat, featmap_size, final_actvn;
+    const float* x;                                   /* [B, feat_nc, fs, fs]                                       */
+    const float* w1[HN_NR_MAX_BLOCKS];                /* feat_upsample_list.i.layer_1.weight [2C, C]                */
+    const float* b1[HN_NR_MAX_BLOCKS];
+    const float* w2[HN_NR_MAX_BLOCKS];                /* feat_upsample_list.i.layer_2.weight [4C, 2C]               */
+    const float* b2[HN_NR_MAX_BLOCKS];
+    const float* wf[HN_NR_MAX_BLOCKS];                /* feat_layers.i.weight [C', C]                               */
+    const float* bf[HN_NR_MAX_BLOCKS];
+    const float* wrgb[HN_NR_MAX_BLOCKS + 1];          /* feat_2_rgb_list.j.weight [3, channels(j)]                  */
+    const float* brgb[HN_NR_MAX_BLOCKS + 1];
+    float tail_taps[HN_NR_MAX_BLOCKS][3];             /* feat_upsample_list.i.blur_layer.f, HOST values             */
+    float rgb_taps[3];                                /* rgb_upsample.1.f, HOST values                              */
+    float* saved;                                     /* hn_nr_saved_floats() floats: activations kept for backward */
+    float* img;                                       /* [B, 3, fs << n_blocks, fs << n_blocks] out                 */
+    int* status;                                      /* zeroed device int[64]                                      */
+} hn_nr_fwd_t;
+
+typedef struct {
+    hn_nr_fwd_t f;                                    /* the forward call's arguments (saved / img as it left them) */
+    const float* g_img;                               /* dL/dimg [B, 3, S, S]                                       */
+    float* scratch;                                   /* hn_nr_scratch_floats() floats                              */
+    float* g_x;                                       /* dL/dx [B, feat_nc, fs, fs] out (overwritten), or NULL      */
+    /* weight / bias gradients, ACCUMULATED (+=, atomics; caller zero-initialises or passes .grad); NULL weight = skip  */
+    float* dw1[HN_NR_MAX_BLOCKS]; float* db1[HN_NR_MAX_BLOCKS];
+    float* dw2[HN_NR_MAX_BLOCKS]; float* db2[HN_NR_MAX_BLOCKS];
+    float* dwf[HN_NR_MAX_BLOCKS]; float* dbf[HN_NR_MAX_BLOCKS];
+    float* dwrgb[HN_NR_MAX_BLOCKS + 1]; float* dbrgb[HN_NR_MAX_BLOCKS + 1];
+} hn_nr_bwd_t;
+
+long long hn_nr_saved_floats(int B, int n_blocks, int feat_nc, int min_feat, int featmap_size);     /* -1: unsupported geometry */
+long long hn_nr_scratch_floats(int B, int n_blocks, int feat_nc, int min_feat, int featmap_size);
+int hn_nr_launches(int n_blocks, int backward);                                                     /* kernels per call         */
+int hn_nr_fwd(const hn_nr_fwd_t* a, void* stream);
+int hn_nr_bwd(const hn_nr_bwd_t* b, void* stream);
 
 /* Bytes of the saved-for-backward buffers for M samples. */
 size_t hn_act_bytes(int64_t M);

@@ -113,13 +113,32 @@ class Adam(C.Structure):
                 ("grad_scale", C.c_float), ("step", C.c_int64)]
 
 
+NR_MAX_BLOCKS = 4
+
+
+class NrFwd(C.Structure):
+    _fields_ = [("B", C.c_int), ("n_blocks", C.c_int), ("feat_nc", C.c_int), ("min_feat", C.c_int), ("featmap_size", C.c_int),
+                ("final_actvn", C.c_int), ("x", _p),
+                ("w1", _p * NR_MAX_BLOCKS), ("b1", _p * NR_MAX_BLOCKS), ("w2", _p * NR_MAX_BLOCKS), ("b2", _p * NR_MAX_BLOCKS),
+                ("wf", _p * NR_MAX_BLOCKS), ("bf", _p * NR_MAX_BLOCKS), ("wrgb", _p * (NR_MAX_BLOCKS + 1)), ("brgb", _p * (NR_MAX_BLOCKS + 1)),
+                ("tail_taps", (C.c_float * 3) * NR_MAX_BLOCKS), ("rgb_taps", C.c_float * 3),
+                ("saved", _p), ("img", _p), ("status", _p)]
+
+
+class NrBwd(C.Structure):
+    _fields_ = [("f", NrFwd), ("g_img", _p), ("scratch", _p), ("g_x", _p),
+                ("dw1", _p * NR_MAX_BLOCKS), ("db1", _p * NR_MAX_BLOCKS), ("dw2", _p * NR_MAX_BLOCKS), ("db2", _p * NR_MAX_BLOCKS),
+                ("dwf", _p * NR_MAX_BLOCKS), ("dbf", _p * NR_MAX_BLOCKS), ("dwrgb", _p * (NR_MAX_BLOCKS + 1)), ("dbrgb", _p * (NR_MAX_BLOCKS + 1))]
+
+
 EXPORTS = ["hn_abi_version", "hn_last_error", "hn_packed_weights_bytes", "hn_pack_weights", "hn_sample_rays",
            "hn_mlp_fwd", "hn_composite_fwd", "hn_composite_bwd", "hn_mlp_bwd_data", "hn_mlp_bwd_weights",
            "hn_act_bytes", "hn_grads_bytes", "hn_mask_bytes", "hn_dfeat_image_bytes", "hn_wgrad_workspace_bytes", "hn_wgrad_det_workspace_bytes",
            "hn_precise_packed_bytes", "hn_precise_workspace_floats", "hn_pack_weights_precise", "hn_mlp_fwd_precise",
            "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
            "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd",
-           "hn_photo_loss_workspace_bytes", "hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step", "hn_fine_sample", "hn_unfuse_r0r1"]
+           "hn_photo_loss_workspace_bytes", "hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step", "hn_fine_sample", "hn_unfuse_r0r1",
+           "hn_nr_saved_floats", "hn_nr_scratch_floats", "hn_nr_launches", "hn_nr_fwd", "hn_nr_bwd"]
 
 _lib = None
 
@@ -175,6 +194,14 @@ def load():
     lib.hn_fine_sample.argtypes = [C.POINTER(FineSample), _p]
     lib.hn_unfuse_r0r1.argtypes = [C.POINTER(Unfuse), _p]
     lib.hn_unfuse_r0r1.restype = C.c_int
+    for name in ("hn_nr_saved_floats", "hn_nr_scratch_floats"):
+        getattr(lib, name).restype = C.c_longlong
+        getattr(lib, name).argtypes = [C.c_int] * 5
+    lib.hn_nr_launches.argtypes = [C.c_int, C.c_int]
+    lib.hn_nr_launches.restype = C.c_int
+    lib.hn_nr_fwd.argtypes = [C.POINTER(NrFwd), _p]
+    lib.hn_nr_bwd.argtypes = [C.POINTER(NrBwd), _p]
+    lib.hn_nr_fwd.restype = lib.hn_nr_bwd.restype = C.c_int
     for name in ("hn_photo_loss_fwd", "hn_photo_loss_bwd", "hn_adam_step", "hn_fine_sample"):
         getattr(lib, name).restype = C.c_int
     lib.hn_sample_rays.argtypes = [C.POINTER(Camera), _p, _p, _p, _p, _p, _p]
@@ -188,7 +215,7 @@ def load():
                  "hn_mlp_bwd_data_precise", "hn_fold_bias", "hn_fold_bias_bwd", "hn_loss_scale", "hn_camera_bwd",
                  "hn_upsample_tail_fwd", "hn_upsample_tail_bwd", "hn_rgb_upsample_fwd", "hn_rgb_upsample_bwd", "hn_merge_fwd", "hn_merge_bwd", "hn_render_fwd", "hn_render_bwd"):
         getattr(lib, name).restype = C.c_int
-    if lib.hn_abi_version() != 3:
+    if lib.hn_abi_version() != 4:
         raise HeadNeRFLibraryError("ABI version mismatch between _lib.py and libheadnerf_b200.so")
     _lib = lib
     return lib

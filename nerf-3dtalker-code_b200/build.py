@@ -9,7 +9,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libheadnerf_b200.so")
 SOURCES = ["hn_api.cu", "hn_composite.cu", "hn_mlp_sched.cu", "hn_mlp_pack.cu", "hn_mlp_fwd.cu",
-           "hn_mlp_bwd.cu", "hn_mlp_wgrad.cu", "hn_precise.cu", "hn_fold.cu", "hn_render2d.cu", "hn_render.cu", "hn_train.cu", "hn_fine.cu"]
+           "hn_mlp_bwd.cu", "hn_mlp_wgrad.cu", "hn_precise.cu", "hn_fold.cu", "hn_render2d.cu", "hn_render.cu", "hn_train.cu", "hn_fine.cu", "hn_nr.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-DHN_BUILDING_DSO"]
 

@@ -1,18 +1,23 @@
 """NeuralRenderer — the consumer of the composited feature map (reference: NetWorks/neural_renderer.py:11-91,
 NetWorks/PixelShuffleUpsample.py:8-45).  Outside the CUDA hot path: modules whose parameter
 names, shapes and registration order reproduce the reference state dict (`neural_render.*` keys) and its seeded
-initialisation.  The 1x1 convolutions are library GEMMs; on CUDA tensors the memory-bound tails of the up-sampling
-blocks (leaky-relu + residual + pixel shuffle + blur; bilinear x2 + blur) run as single library kernels each way
-(ops.UpsampleTailFunction / ops.RgbUpsampleFunction, csrc/hn_render2d.cu) - `FUSED_TAILS = False` or CPU tensors
-take the plain PyTorch statement, which is also what the fused kernels are tested against.  The 3x3 binomial blur
-restates kornia.filters.filter2d(normalized=True, border 'reflect') with a depthwise convolution."""
+initialisation.  On CUDA fp32 tensors the whole forward (and its backward) is ONE library call (`FUSED_NET`,
+ops.NeuralRenderFunction -> hn_nr_fwd / hn_nr_bwd, csrc/hn_nr.cu): every 1x1 convolution with its LeakyReLU, RGB head,
+skip sum and the final sigmoid in a grouped tcgen05 tf32 GEMM kernel over the NCHW planes, the memory-bound tails of the
+up-sampling blocks (leaky-relu + residual + pixel shuffle + blur; bilinear x2 + blur) as single kernels
+(csrc/hn_render2d.cu).  `FUSED_NET = False` keeps the module-by-module statement with only the tails fused
+(ops.UpsampleTailFunction / ops.RgbUpsampleFunction); `FUSED_TAILS = False`, CPU tensors, deterministic-algorithms mode
+or an unsupported geometry take the plain PyTorch statement, which is also what the kernels are tested against (next to
+oracle.neural_render).  The 3x3 binomial blur restates kornia.filters.filter2d(normalized=True, border 'reflect') with a
+depthwise convolution."""
 from math import log2
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-FUSED_TAILS = True      # module-level switch (tests compare both paths)
+FUSED_TAILS = True      # module-level switches (tests compare the paths)
+FUSED_NET = True
 
 
 class Blur(nn.Module):
@@ -88,7 +93,40 @@ class NeuralRenderer(nn.Module):
             return ops.RgbUpsampleFunction.apply(rgb, self.rgb_upsample[1].taps())
         return self.rgb_upsample(rgb)
 
+    def fuse_grad_accumulation(self, enable=True):
+        """Opt-in: hn_nr_bwd accumulates the weight / bias gradients straight into the parameters' existing `.grad` buffers
+        (e.g. views of dist.GradBucket's flat buffer) instead of returning them through AccumulateGrad."""
+        self._fuse_grads = bool(enable)
+        return self
+
+    def fused_parameters(self):
+        """Parameters in the order ops.NeuralRenderFunction takes them."""
+        ps = []
+        for i in range(self.n_blocks):
+            up = self.feat_upsample_list[i]
+            ps += [up.layer_1.weight, up.layer_1.bias, up.layer_2.weight, up.layer_2.bias, self.feat_layers[i].weight, self.feat_layers[i].bias]
+        for conv in self.feat_2_rgb_list:
+            ps += [conv.weight, conv.bias]
+        return ps
+
+    def _fused_net(self, x):
+        if not (FUSED_NET and _fused(x)) or torch.are_deterministic_algorithms_enabled():
+            return False
+        widths = [max(self.n_feat // (2 ** i), self.min_feat) for i in range(self.n_blocks + 1)]
+        return (self.out_dim == 3 and 1 <= self.n_blocks <= 4 and x.dim() == 4 and x.shape[1] == self.n_feat and x.shape[2] == x.shape[3]
+                and all(w % 4 == 0 for w in widths) and all(w <= 256 for w in widths[1:]))
+
     def forward(self, x):
+        if self._fused_net(x):
+            from . import ops
+            ps = self.fused_parameters()
+            meta = {"n_blocks": self.n_blocks, "min_feat": self.min_feat, "final_actvn": self.final_actvn,
+                    "tail_taps": [up.blur_layer.taps() for up in self.feat_upsample_list], "rgb_taps": self.rgb_upsample[1].taps()}
+            if getattr(self, "_fuse_grads", False) and torch.is_grad_enabled():
+                if any(p.requires_grad and p.grad is None for p in ps):
+                    raise RuntimeError("fuse_grad_accumulation: every NeuralRenderer parameter needs an allocated .grad (e.g. dist.GradBucket)")
+                meta["grad_into"] = [p.grad if p.requires_grad else None for p in ps]
+            return ops.NeuralRenderFunction.apply(x, meta, *ps)
         rgb = self._rgb_up(self.feat_2_rgb_list[0](x))
         net = x
         for i in range(self.n_blocks):

@@ -763,6 +763,108 @@ class RgbUpsampleFunction(torch.autograd.Function):
         return dx, None
 
 
+_NR_STATUS = {}
+
+
+def _nr_status(dev):
+    """One persistent status word per device for the consumer's kernels (non-zero only after a pipeline fault)."""
+    st = _NR_STATUS.get(dev)
+    if st is None:
+        st = _NR_STATUS[dev] = torch.zeros(64, dtype=torch.int32, device=dev)
+    return st
+
+
+def _nr_args(x, ps, meta, saved, img, status):
+    nb = meta["n_blocks"]
+    a = L.NrFwd()
+    a.B, a.n_blocks, a.feat_nc, a.min_feat, a.featmap_size = x.shape[0], nb, x.shape[1], meta["min_feat"], x.shape[2]
+    a.final_actvn = 1 if meta["final_actvn"] else 0
+    a.x = _ptr(x)
+    for i in range(nb):
+        a.w1[i], a.b1[i], a.w2[i], a.b2[i], a.wf[i], a.bf[i] = (p.data_ptr() for p in ps[6 * i:6 * i + 6])
+        for k in range(3):
+            a.tail_taps[i][k] = float(meta["tail_taps"][i][k])
+    for j in range(nb + 1):
+        a.wrgb[j], a.brgb[j] = ps[6 * nb + 2 * j].data_ptr(), ps[6 * nb + 2 * j + 1].data_ptr()
+    for k in range(3):
+        a.rgb_taps[k] = float(meta["rgb_taps"][k])
+    a.saved, a.img, a.status = _ptr(saved), _ptr(img), _ptr(status)
+    return a
+
+
+class NeuralRenderFunction(torch.autograd.Function):
+    """(x [B,feat_nc,fs,fs], meta, parameters) -> images [B,3,fs << n_blocks,fs << n_blocks]: the whole NeuralRenderer
+    (NetWorks/neural_renderer.py:72-91, PixelShuffleUpsample.py:36-45) in one library call per direction (hn_nr_fwd / hn_nr_bwd,
+    csrc/hn_nr.cu).  Parameters: per block layer_1.weight, layer_1.bias, layer_2.weight, layer_2.bias, feat_layers.weight,
+    feat_layers.bias; then feat_2_rgb_list.j weight, bias.  meta: n_blocks, min_feat, final_actvn, tail_taps, rgb_taps and
+    optionally grad_into (a list parallel to the parameters: existing .grad buffers the kernels accumulate into)."""
+
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        lib = L.load()
+        nb = meta["n_blocks"]
+        if len(params) != 6 * nb + 2 * (nb + 1):
+            raise ValueError("NeuralRenderFunction: wrong number of parameters")
+        x = _dev_f32(x, "x", align=16)
+        ps = [_dev_f32(p.detach(), "parameter", align=16) for p in params]
+        B, C0, fs, fs2 = x.shape
+        n_saved = lib.hn_nr_saved_floats(B, nb, C0, meta["min_feat"], fs) if fs == fs2 else -1
+        if n_saved < 0:
+            raise ValueError("NeuralRenderFunction: unsupported geometry")
+        saved = torch.empty(n_saved, device=x.device)
+        img = torch.empty(B, 3, fs << nb, fs << nb, device=x.device)
+        status = _nr_status(x.device)
+        a = _nr_args(x, ps, meta, saved, img, status)
+        _call("hn_nr_fwd", lib.hn_nr_fwd, C.byref(a), _stream(), kernels=lib.hn_nr_launches(nb, 0))
+        FAULTS.watch(status, "hn_nr_fwd")
+        ctx.save_for_backward(x, saved, img, *ps)
+        ctx.meta, ctx.param_shapes = meta, [tuple(p.shape) for p in params]
+        return img
+
+    @staticmethod
+    def backward(ctx, g_img):
+        lib = L.load()
+        x, saved, img, *ps = ctx.saved_tensors
+        meta = ctx.meta
+        nb = meta["n_blocks"]
+        need = ctx.needs_input_grad
+        dev = x.device
+        g_img = _dev_f32(g_img, "g_img", align=16)
+        B, C0, fs, _ = x.shape
+        scratch = torch.empty(lib.hn_nr_scratch_floats(B, nb, C0, meta["min_feat"], fs), device=dev)
+        g_x = torch.empty_like(x) if need[0] else None
+        status = _nr_status(dev)
+        b = L.NrBwd()
+        b.f = _nr_args(x, ps, meta, saved, img, status)
+        b.g_img, b.scratch, b.g_x = _ptr(g_img), _ptr(scratch), _ptr(g_x)
+        # gradient destinations: the caller's accumulation buffers where given, else views of ONE zeroed buffer
+        into = meta.get("grad_into")
+        n_p = len(ps)
+        pair_need = [need[2 + 2 * k] or need[3 + 2 * k] for k in range(n_p // 2)]
+        dst = [_grad_dst(into, k, ps[k]) if need[2 + k] else None for k in range(n_p)]
+        own = [pair_need[k // 2] and dst[k] is None for k in range(n_p)]
+        zbuf = torch.zeros(sum((ps[k].numel() + 3) // 4 * 4 for k in range(n_p) if own[k]), device=dev)
+        off, buf = 0, list(dst)
+        for k in range(n_p):
+            if own[k]:
+                buf[k] = zbuf[off:off + ps[k].numel()]
+                off += (ps[k].numel() + 3) // 4 * 4
+        for i in range(nb):
+            if pair_need[3 * i]:
+                b.dw1[i], b.db1[i] = buf[6 * i].data_ptr(), buf[6 * i + 1].data_ptr()
+            if pair_need[3 * i + 1]:
+                b.dw2[i], b.db2[i] = buf[6 * i + 2].data_ptr(), buf[6 * i + 3].data_ptr()
+            if pair_need[3 * i + 2]:
+                b.dwf[i], b.dbf[i] = buf[6 * i + 4].data_ptr(), buf[6 * i + 5].data_ptr()
+        for j in range(nb + 1):
+            if pair_need[3 * nb + j]:
+                b.dwrgb[j], b.dbrgb[j] = buf[6 * nb + 2 * j].data_ptr(), buf[6 * nb + 2 * j + 1].data_ptr()
+        _call("hn_nr_bwd", lib.hn_nr_bwd, C.byref(b), _stream(), kernels=lib.hn_nr_launches(nb, 1))
+        FAULTS.watch(status, "hn_nr_bwd")
+        grads = [buf[k].view(ctx.param_shapes[k]) if (need[2 + k] and dst[k] is None) else None for k in range(n_p)]
+        return (g_x, None, *grads)
+
+
 # ---------------------------------------------------------------------------------------------------
 # debugging / test helpers: decode operand images (csrc/hn_tc.cuh layout) back to dense matrices
 # ---------------------------------------------------------------------------------------------------

@@ -58,8 +58,10 @@ def test_rgb_upsample_matches_pytorch(hn, B, H, W):
 
 @pytest.mark.parametrize("fs,S", [(8, 32), (16, 128), (32, 512)])
 def test_neural_renderer_fused_vs_plain(hn, fs, S):
-    """The whole consumer, fused tails against the plain modules: image and every gradient (input feature map, all parameters)."""
+    """The whole consumer, fused tails (library convolutions) against the plain modules: image and every gradient (input
+    feature map, all parameters).  The one-call renderer (FUSED_NET) has its own tests in test_gpu_nr.py."""
     nr = _nr(hn)
+    nr.FUSED_NET = False
     torch.manual_seed(fs)
     net = nr.NeuralRenderer(featmap_size=fs, img_size=S).to(DEV)
     x = torch.randn(2, 256, fs, fs, device=DEV)
@@ -72,7 +74,7 @@ def test_neural_renderer_fused_vs_plain(hn, fs, S):
         img = net(xi)
         ((img - tgt) ** 2).mean().backward()
         res.append((img.detach(), xi.grad, {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
-    nr.FUSED_TAILS = True
+    nr.FUSED_TAILS = nr.FUSED_NET = True
     (i0, g0, p0), (i1, g1, p1) = res
     assert (i0 - i1).abs().max() <= 2e-5
     assert (g0 - g1).abs().max() <= 1e-3 * g0.abs().max()

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(hn):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(hn._lib.EXPORTS) == declared
     lib.hn_abi_version.restype = ctypes.c_int
-    assert lib.hn_abi_version() == 3
+    assert lib.hn_abi_version() == 4
     lib.hn_packed_weights_bytes.restype = ctypes.c_size_t
     assert lib.hn_packed_weights_bytes() % 16384 == 0          # no GPU needed: host-side schedule only
 
