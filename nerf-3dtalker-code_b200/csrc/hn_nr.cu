@@ -117,6 +117,7 @@ struct NrShared {
     uint64_t stage_free[2], done;
     uint32_t tmem_base;
     float rgb_part[128 * 3];
+    float bias_s[kNrMaxN], wrgb_s[3][kNrMaxN];               // this tile's columns of the bias / RGB-head weights (zero beyond N)
 };
 
 // ---- fast loaders: the thread -> (row, chunk) map is fixed at compile time, so a block costs a handful of address adds
@@ -223,7 +224,7 @@ template <int ROWS> struct Ld<kModeGen, ROWS> {
 // The contraction loop of one output tile: two shared-memory stages; the loads of block kb + 1 are in flight while block kb is
 // issued.  Returns false when a barrier wait timed out.
 template <int AM, int BM>
-__device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k_len, int nkb, uint32_t smem, NrShared* sh, uint32_t tmem_base,
+__device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k_len, int nkb, uint32_t smem, NrShared* sh,
                                        uint32_t idesc, bool want_dbias, float (&bsum)[4], int tid) {
     bool ok = true;
     float4 ra[4], rb[8];
@@ -246,9 +247,11 @@ __device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k
             lb.load(rb, k_len - (kb + 1) * 32, tid);
         }
         fence_async_smem();
-        __syncthreads();
+        tc_fence_before_sync();
+        __syncthreads();                                      // (the first one also publishes the barriers and the TMEM address)
         if (tid == 0 && ok) {
             tc_fence_after_sync();
+            const uint32_t tmem_base = sh->tmem_base;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
                 umma_tf32(tmem_base, umma_desc_kmajor(stA, ks), umma_desc_kmajor(stB, ks), idesc, (kb | ks) ? 1u : 0u);
@@ -261,41 +264,92 @@ __device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k
 
 // Epilogue of a pixel-row tile for one 32-column piece, specialised at compile time (a generic version with run-time null checks
 // compiled into one dependent load -> use -> store chain per element, ~300 cycles each): the per-column vectors (bias, RGB-head
-// weights) are fetched once per piece, lane c holding column c, and broadcast with shuffles; the per-element operand (saved
-// activation for LeakyReLU', or the addend) is loaded for all 32 columns before the first use.
+// weights) were staged in shared memory while the contraction ran; the per-element operand (saved activation for LeakyReLU',
+// or the addend) is loaded for all 32 columns before the accumulator is waited for.
 enum { kAuxNone = 0, kAuxMask = 1, kAuxAdd = 2 };
 template <bool BIAS, bool LRELU, int AUX, bool RGB>
-__device__ __forceinline__ void epi_piece(const uint32_t (&v)[32], const NrProb& P, int n_first, bool row_ok, long long idx_first, long long plane,
-                                          int lane, float (&rgb)[3]) {
-    const int nv = P.N - n_first;                              // valid columns of this piece (>= 32 when full)
-    float bl = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f;
-    if (BIAS && lane < nv) bl = __ldg(P.bias + n_first + lane);
-    if (RGB && lane < nv) {
-        w0 = __ldg(P.wrgb + n_first + lane);
-        w1 = __ldg(P.wrgb + P.N + n_first + lane);
-        w2 = __ldg(P.wrgb + 2 * P.N + n_first + lane);
-    }
-    float aux[AUX == kAuxNone ? 1 : 32];
-    if (AUX != kAuxNone) {
-        const float* src = (AUX == kAuxMask ? P.mask_act : P.addend) + idx_first;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) aux[c] = (row_ok && c < nv) ? __ldg(src + c * plane) : 0.f;
-    }
-    float* out = P.out + idx_first;
+__device__ __forceinline__ void epi_piece(const uint32_t (&v)[32], const float (&aux)[32], const NrShared& sh, float* out, int col0, int nv, bool row_ok,
+                                          long long plane, float (&rgb)[3]) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
         float y = __uint_as_float(v[c]);
-        if (BIAS) y += __shfl_sync(0xffffffffu, bl, c);
+        if (BIAS) y += sh.bias_s[col0 + c];
         if (LRELU) y = fmaxf(y, y * kSlope);
         if (AUX == kAuxMask) y = aux[c] > 0.f ? y : y * kSlope;
         if (AUX == kAuxAdd) y += aux[c];
         if (row_ok && c < nv) out[c * plane] = y;
-        if (RGB) {                                              // columns beyond nv carry zero weights
-            rgb[0] = fmaf(__shfl_sync(0xffffffffu, w0, c), y, rgb[0]);
-            rgb[1] = fmaf(__shfl_sync(0xffffffffu, w1, c), y, rgb[1]);
-            rgb[2] = fmaf(__shfl_sync(0xffffffffu, w2, c), y, rgb[2]);
+        if (RGB) {                                              // columns beyond N carry zero weights
+            rgb[0] = fmaf(sh.wrgb_s[0][col0 + c], y, rgb[0]);
+            rgb[1] = fmaf(sh.wrgb_s[1][col0 + c], y, rgb[1]);
+            rgb[2] = fmaf(sh.wrgb_s[2][col0 + c], y, rgb[2]);
         }
     }
+}
+__device__ __forceinline__ void load_aux(float (&aux)[32], const float* src, int nv, bool row_ok, long long plane) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) aux[c] = (row_ok && c < nv) ? __ldg(src + c * plane) : 0.f;
+}
+
+// Epilogue of one pixel-row tile (all threads of the CTA): warp w drains TMEM lanes (w % 4) * 32 .. + 31, the two warp groups take
+// alternate 32-column pieces; the RGB head's two partial dot products meet in shared memory.
+__device__ __forceinline__ void epilogue_rows(const NrProb& P, NrShared& sh, uint32_t tmem_acc, int item, int m0, int n0, int n_tile,
+                                              const float (&rgb_prev)[3], bool ok, int warp, int lane) {
+    const int q = warp & 3, half = warp >> 2;
+    const int m = m0 + q * 32 + lane;
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const int n_pieces = (n_tile + 31) / 32;
+    float rgb[3] = {0.f, 0.f, 0.f};
+    const long long plane = P.M;
+    const float* wrgb = P.wrgb;
+    const bool row_ok = m < P.M;
+    const long long idx0 = item * P.out_item + m;
+    const int epi = P.epi;
+    const float* aux_src = epi == 4 ? P.mask_act : (epi == 5 ? P.addend : nullptr);
+    for (int pc = half; pc < n_pieces && ok; pc += 2) {
+        uint32_t v[32];
+        float aux[32];
+        const int n_first = n0 + pc * 32, nv = P.N - n_first;
+        const long long idx_first = idx0 + n_first * plane;
+        tmem_ld32(lane_addr + pc * 32, v);
+        if (aux_src) load_aux(aux, aux_src + idx_first, nv, row_ok, plane);
+        tmem_ld_wait();
+        float* out = P.out + idx_first;
+        switch (epi) {                                        // block-uniform
+            case 0: epi_piece<false, false, kAuxNone, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
+            case 1: epi_piece<true, false, kAuxNone, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
+            case 2: epi_piece<true, true, kAuxNone, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
+            case 3: epi_piece<true, true, kAuxNone, true>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
+            case 4: epi_piece<false, false, kAuxMask, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
+            default: epi_piece<false, false, kAuxAdd, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
+        }
+    }
+    if (wrgb) {                                               // block-uniform branch
+        if (half == 1) { sh.rgb_part[(q * 32 + lane) * 3 + 0] = rgb[0]; sh.rgb_part[(q * 32 + lane) * 3 + 1] = rgb[1]; sh.rgb_part[(q * 32 + lane) * 3 + 2] = rgb[2]; }
+        __syncthreads();
+        if (half == 0 && row_ok && ok) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const long long idx = item * 3 * plane + j * plane + m;
+                float y = rgb[j] + sh.rgb_part[(q * 32 + lane) * 3 + j] + __ldg(P.brgb + j) + rgb_prev[j];
+                if (P.sigmoid) y = 1.0f / (1.0f + __expf(-y));
+                P.rgb_out[idx] = y;
+            }
+        }
+    }
+}
+
+// per-column vectors of the epilogue: fetched at CTA start, used after the contraction
+__device__ __forceinline__ void stage_columns(const NrProb& P, NrShared& sh, int n0, int tid) {
+    const int n = n0 + tid;
+    sh.bias_s[tid] = (P.bias && n < P.N) ? __ldg(P.bias + n) : 0.f;
+    if (P.wrgb) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sh.wrgb_s[j][tid] = n < P.N ? __ldg(P.wrgb + j * P.N + n) : 0.f;
+    }
+}
+__device__ __forceinline__ void load_rgb_prev(float (&r)[3], const NrProb& P, int item, int m, bool active) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[j] = (active && P.rgb_in && m < P.M) ? __ldg(P.rgb_in + item * 3ll * P.M + (long long)j * P.M + m) : 0.f;
 }
 
 __global__ void __launch_bounds__(kNrThreads, 2) nr_gemm_kernel(const __grid_constant__ NrLaunch L) {
@@ -315,131 +369,85 @@ __global__ void __launch_bounds__(kNrThreads, 2) nr_gemm_kernel(const __grid_con
         mbar_init(smem_u32(&sh.done), 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc<256>(smem_u32(&sh.tmem_base));
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = sh.tmem_base;
-#ifdef HN_NR_TRACE
-    long long tr[5];
-    const bool tracer = tid == 0 && (int)gridDim.x == HN_NR_TRACE && blockIdx.x == gridDim.x - 1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[0]));
-#endif
-
-    // ---- which tile
-    int t = (int)blockIdx.x - P.tile0;
-    const int mt = t % P.m_tiles; t /= P.m_tiles;
-    const int nt = t % P.n_tiles; t /= P.n_tiles;
-    int item, k0;
-    if (P.kind == 0) { item = t; k0 = 0; }
-    else { item = t / P.k_chunks; k0 = (t % P.k_chunks) * P.k_chunk; }
-    const int m0 = mt * 128, n0 = nt * P.n_tile;
-    const int k_len = min(P.k_chunk, P.K - k0);
-    const int nkb = (k_len + 31) / 32;
-    const int n_tile = min(P.n_tile, ((P.N - n0) + 15) & ~15);
-
-    Operand A, B;
-    A.base = P.a + item * P.a_item + (long long)m0 * P.a_rs + (long long)k0 * P.a_ks;
-    A.rs = P.a_rs; A.ks = P.a_ks; A.rows_valid = P.M - m0; A.rows_tile = 128;
-    A.vec = P.a_ks == 1 && (k_len & 3) == 0 && (P.a_rs & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.base) & 15) == 0);
-    B.base = P.b + item * P.b_item + (long long)n0 * P.b_rs + (long long)k0 * P.b_ks;
-    B.rs = P.b_rs; B.ks = P.b_ks; B.rows_valid = P.N - n0; B.rows_tile = n_tile;
-    B.vec = P.b_ks == 1 && (k_len & 3) == 0 && (P.b_rs & 3) == 0 && ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0);
-
-    const uint32_t idesc = umma_idesc(128, (uint32_t)n_tile, 2u, 2u, 0, 0);      // 2 = tf32 operands, f32 accumulator
-    const bool want_dbias = P.kind == 1 && P.dbias != nullptr && nt == 0;
-    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    if (warp == 0) tmem_alloc<256>(smem_u32(&sh.tmem_base));   // published by the first __syncthreads of the contraction loop
     bool ok = true;
-    const bool a_rc = P.a_rs == 1 && (P.a_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.base) & 15) == 0) && (A.rows_valid >= 128 || (A.rows_valid & 3) == 0);
-    const bool b_rc = P.b_rs == 1 && (P.b_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0) && (B.rows_valid >= n_tile || (B.rows_valid & 3) == 0);
-    if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV>(A, B, k_len, nkb, smem, &sh, tmem_base, idesc, want_dbias, bsum, tid);
-    else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC>(A, B, k_len, nkb, smem, &sh, tmem_base, idesc, want_dbias, bsum, tid);
-    else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV>(A, B, k_len, nkb, smem, &sh, tmem_base, idesc, want_dbias, bsum, tid);
-    else ok = k_loop<kModeGen, kModeGen>(A, B, k_len, nkb, smem, &sh, tmem_base, idesc, want_dbias, bsum, tid);
-#ifdef HN_NR_TRACE
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
-#endif
-    if (ok) ok = mbar_wait(smem_u32(&sh.done), 0);
-#ifdef HN_NR_TRACE
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[2]));
-#endif
-    tc_fence_after_sync();
-    if (!ok && tid == 0) atomicCAS(L.status, 0, 801);
 
-    // ---- epilogue: warp w drains TMEM lanes (w % 4) * 32 .. + 31, the two warp groups take alternate 32-column pieces
-    const int q = warp & 3, half = warp >> 2;
-    const int m = m0 + q * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int n_pieces = (n_tile + 31) / 32;
-    if (P.kind == 0) {
-        float rgb[3] = {0.f, 0.f, 0.f};
-        const long long plane = P.M;
-        const float* wrgb = P.wrgb;
-        const bool row_ok = m < P.M;
-        const long long idx0 = item * P.out_item + m;
-        const int epi = P.epi;
-        for (int pc = half; pc < n_pieces && ok; pc += 2) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + pc * 32, v);
-            tmem_ld_wait();
-            const int n_first = n0 + pc * 32;
-            const long long idx_first = idx0 + n_first * plane;
-            switch (epi) {                                    // block-uniform
-                case 0: epi_piece<false, false, kAuxNone, false>(v, P, n_first, row_ok, idx_first, plane, lane, rgb); break;
-                case 1: epi_piece<true, false, kAuxNone, false>(v, P, n_first, row_ok, idx_first, plane, lane, rgb); break;
-                case 2: epi_piece<true, true, kAuxNone, false>(v, P, n_first, row_ok, idx_first, plane, lane, rgb); break;
-                case 3: epi_piece<true, true, kAuxNone, true>(v, P, n_first, row_ok, idx_first, plane, lane, rgb); break;
-                case 4: epi_piece<false, false, kAuxMask, false>(v, P, n_first, row_ok, idx_first, plane, lane, rgb); break;
-                default: epi_piece<false, false, kAuxAdd, false>(v, P, n_first, row_ok, idx_first, plane, lane, rgb); break;
-            }
+    {
+        // ---- one output tile per CTA
+        int t = (int)blockIdx.x - P.tile0;
+        const int mt = t % P.m_tiles; t /= P.m_tiles;
+        const int nt = t % P.n_tiles; t /= P.n_tiles;
+        int item, k0;
+        if (P.kind == 0) { item = t; k0 = 0; }
+        else { item = t / P.k_chunks; k0 = (t % P.k_chunks) * P.k_chunk; }
+        const int m0 = mt * 128, n0 = nt * P.n_tile;
+        const int k_len = min(P.k_chunk, P.K - k0);
+        const int nkb = (k_len + 31) / 32;
+        const int n_tile = min(P.n_tile, ((P.N - n0) + 15) & ~15);
+
+        Operand A, B;
+        A.base = P.a + item * P.a_item + (long long)m0 * P.a_rs + (long long)k0 * P.a_ks;
+        A.rs = P.a_rs; A.ks = P.a_ks; A.rows_valid = P.M - m0; A.rows_tile = 128;
+        A.vec = P.a_ks == 1 && (k_len & 3) == 0 && (P.a_rs & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.base) & 15) == 0);
+        B.base = P.b + item * P.b_item + (long long)n0 * P.b_rs + (long long)k0 * P.b_ks;
+        B.rs = P.b_rs; B.ks = P.b_ks; B.rows_valid = P.N - n0; B.rows_tile = n_tile;
+        B.vec = P.b_ks == 1 && (k_len & 3) == 0 && (P.b_rs & 3) == 0 && ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0);
+
+        const int q = warp & 3, half = warp >> 2;
+        const int m = m0 + q * 32 + lane;
+        float rgb_prev[3] = {0.f, 0.f, 0.f};
+        if (P.kind == 0) {
+            stage_columns(P, sh, n0, tid);
+            if (P.wrgb) load_rgb_prev(rgb_prev, P, item, m, half == 0);
         }
-        if (wrgb) {                                           // block-uniform branch
-            if (half == 1) { sh.rgb_part[(q * 32 + lane) * 3 + 0] = rgb[0]; sh.rgb_part[(q * 32 + lane) * 3 + 1] = rgb[1]; sh.rgb_part[(q * 32 + lane) * 3 + 2] = rgb[2]; }
-            __syncthreads();
-            if (half == 0 && row_ok && ok) {
+        const uint32_t idesc = umma_idesc(128, (uint32_t)n_tile, 2u, 2u, 0, 0);      // 2 = tf32 operands, f32 accumulator
+        const bool want_dbias = P.kind == 1 && P.dbias != nullptr && nt == 0;
+        float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool a_rc = P.a_rs == 1 && (P.a_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.base) & 15) == 0) && (A.rows_valid >= 128 || (A.rows_valid & 3) == 0);
+        const bool b_rc = P.b_rs == 1 && (P.b_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0) && (B.rows_valid >= n_tile || (B.rows_valid & 3) == 0);
+        if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV>(A, B, k_len, nkb, smem, &sh, idesc, want_dbias, bsum, tid);
+        else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC>(A, B, k_len, nkb, smem, &sh, idesc, want_dbias, bsum, tid);
+        else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV>(A, B, k_len, nkb, smem, &sh, idesc, want_dbias, bsum, tid);
+        else ok = k_loop<kModeGen, kModeGen>(A, B, k_len, nkb, smem, &sh, idesc, want_dbias, bsum, tid);
+        if (ok) ok = mbar_wait(smem_u32(&sh.done), 0);
+        tc_fence_after_sync();
+        if (!ok && tid == 0) atomicCAS(L.status, 0, 801);
+
+        const uint32_t tmem_base = sh.tmem_base;
+        if (P.kind == 0) {
+            epilogue_rows(P, sh, tmem_base, item, m0, n0, n_tile, rgb_prev, ok, warp, lane);
+        } else {
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int n_pieces = (n_tile + 31) / 32;
+            float* out = P.out + (long long)m * P.out_ld;
+            const int N = P.N;
+            const bool row_ok = m < P.M;
+            for (int pc = half; pc < n_pieces && ok; pc += 2) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + pc * 32, v);
+                tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const long long idx = item * 3 * plane + j * plane + m;
-                    float y = rgb[j] + sh.rgb_part[(q * 32 + lane) * 3 + j] + __ldg(P.brgb + j);
-                    if (P.rgb_in) y += __ldg(P.rgb_in + idx);
-                    if (P.sigmoid) y = 1.0f / (1.0f + __expf(-y));
-                    P.rgb_out[idx] = y;
+                for (int c = 0; c < 32; ++c) {
+                    const int n = n0 + pc * 32 + c;
+                    if (row_ok && n < N) atomicAdd(out + n, __uint_as_float(v[c]));
                 }
             }
-        }
-    } else {
-        float* out = P.out + (long long)m * P.out_ld;
-        const int N = P.N;
-        const bool row_ok = m < P.M;
-        for (int pc = half; pc < n_pieces && ok; pc += 2) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + pc * 32, v);
-            tmem_ld_wait();
+            if (want_dbias && ok) {                           // k-contiguous A: thread = (row tid/8 + 32 j, chunk tid % 8)
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int n = n0 + pc * 32 + c;
-                if (row_ok && n < N) atomicAdd(out + n, __uint_as_float(v[c]));
-            }
-        }
-        if (want_dbias && ok) {                               // k-contiguous A: thread = (row tid/8 + 32 j, chunk tid % 8)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float sum = bsum[j];
-                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-                const int row = (tid >> 3) + 32 * j;
-                if ((tid & 7) == 0 && m0 + row < P.M) atomicAdd(P.dbias + m0 + row, sum);
+                for (int j = 0; j < 4; ++j) {
+                    float sum = bsum[j];
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                    const int row = (tid >> 3) + 32 * j;
+                    if ((tid & 7) == 0 && m0 + row < P.M) atomicAdd(P.dbias + m0 + row, sum);
+                }
             }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-#ifdef HN_NR_TRACE
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[3]));
-    if (tracer) { for (int i = 0; i < 4; ++i) reinterpret_cast<long long*>(L.status + 16)[i] = tr[i]; L.status[32] = nkb; L.status[33] = n_tile; L.status[34] = pi; }
-#endif
-    if (warp == 0) tmem_free<256>(tmem_base);
+    if (warp == 0) tmem_free<256>(sh.tmem_base);
 }
 
 // Gradient entering a block's feat_layers convolution (neural_renderer.py:83-87 backwards): the RGB head adds W_rgb^T g_rgb to
