@@ -3,7 +3,8 @@
 // direction.  Every 1x1 convolution, its LeakyReLU, the RGB heads with their skip sums and the final sigmoid run in one
 // grouped tensor-core GEMM kernel (tcgen05 kind::tf32, fp32 accumulation in tensor memory) that reads and writes the NCHW
 // planes directly; the memory-bound tails (leaky-relu + residual + pixel shuffle + blur, bilinear x2 + blur) are the kernels
-// of hn_render2d.cu.  A Reso32HR training step issues 35 launches for the whole renderer, both directions, from two C calls.
+// of hn_render2d.cu.  With n blocks the forward call issues 5 n kernels and the backward call 6 n + 1 (Reso32HR, four blocks up
+// to 512 x 512: 45 launches for the whole renderer, both directions, from two C calls).
 //
 // One GEMM problem:  D[m, n] = sum_k A(m, k) * B(n, k), both operands fetched element-wise as base[row * rs + k * ks]:
 //   pixel rows   (forward / data gradient): A = an NCHW activation (m = pixel: rs = 1, ks = plane stride), B = the weight
@@ -14,8 +15,13 @@
 //   weight gradient: A = the pre-activation gradient (m = out channel, k = pixel: rs = plane stride, ks = 1), B = the layer
 //                input (n = in channel), contraction over the pixels of all items split across CTAs; partial products are
 //                added to the gradient buffer with atomics; the bias gradient is the row sum of A, taken while loading it.
-// Operands are rounded to tf32 (cvt.rna) on their way into the canonical SWIZZLE_128B K-major shared-memory layout (128-byte
-// rows of 32 tf32); the same two-stage ring feeds four K = 8 MMAs per block.
+// Operands pass through registers on their way into the canonical SWIZZLE_128B K-major shared-memory layout (128-byte rows of
+// 32 tf32): NCHW planes with rows = pixels are transposed there (float4 loads along the pixels, 4 x 4 register transpose, 16-byte
+// row chunks), rounded to tf32 with one integer add; a two-stage ring feeds four K = 8 MMAs per 32-wide block.
+// Measured (profiles/r02_nr_*): the whole renderer forward + backward at Reso32HR, batch 2: 2.1 ms (the module-by-module cuDNN
+// path: 3.3 ms incl. its launch gaps).  What bounds it: the low-resolution layers are chains of 8-16 dependent global-memory
+// round trips on 48-128 CTAs; the high-resolution layers run ~5.5 us per 128-pixel tile with two CTAs per SM (registers);
+// a multi-tile streaming variant was measured and brought nothing once its register prefetch spilled.
 #include <algorithm>
 #include <vector>
 #include "hn_api.h"

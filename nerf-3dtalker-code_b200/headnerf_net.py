@@ -148,10 +148,12 @@ class HeadNeRFNet(nn.Module):
         return ws, self._packed_hl
 
     def fuse_grad_accumulation(self, enable=True):
-        """Opt-in: the kernels accumulate fg_CD_predictor's weight and bias gradients straight into the parameters' existing
-        `.grad` buffers (e.g. the views of dist.GradBucket's flat all-reduce buffer) instead of returning them through
-        autograd's AccumulateGrad - no per-parameter zero-fill and add kernels.  Every parameter needs a `.grad` beforehand."""
+        """Opt-in: the kernels accumulate fg_CD_predictor's and NeuralRenderer's weight and bias gradients straight into the
+        parameters' existing `.grad` buffers (e.g. the views of dist.GradBucket's flat all-reduce buffer) instead of returning
+        them through autograd's AccumulateGrad - no per-parameter zero-fill and add kernels.  Every parameter needs a `.grad`
+        beforehand."""
         self._fuse_grads = bool(enable)
+        self.neural_render.fuse_grad_accumulation(enable)
         return self
 
     def _grad_into(self):
