@@ -34,6 +34,9 @@ extern "C" int hn_rgb_upsample_bwd(const float*, const float*, float*, int, int,
 
 namespace hn {
 
+#ifndef HN_NR_MIN_CTAS
+#define HN_NR_MIN_CTAS 2
+#endif
 constexpr int kNrThreads = 256;
 constexpr int kNrMaxN = 256;
 constexpr uint32_t kNrStageA = 128 * 128;                    // 128 rows x 32 tf32
@@ -57,7 +60,7 @@ struct NrProb {
     int lrelu, sigmoid, epi;
     int tile0, tiles;
 };
-struct NrLaunch { NrProb p[kNrMaxProblems]; int n; int* status; };
+struct NrLaunch { NrProb p[kNrMaxProblems]; int n; int tmem_cols; uint32_t stage_bytes; int* status; };   // tmem_cols / stage_bytes: sized for the widest tile of the launch
 
 // fp32 -> tf32 operand bits: the tensor core reads the upper 19 bits of the word, so adding half an ulp of the 10-bit mantissa
 // rounds to nearest (ties away) in ONE integer add; cvt.rna.tf32.f32 compiles to four instructions per element on sm_100a,
@@ -230,7 +233,7 @@ template <int ROWS> struct Ld<kModeGen, ROWS> {
 // The contraction loop of one output tile: two shared-memory stages; the loads of block kb + 1 are in flight while block kb is
 // issued.  Returns false when a barrier wait timed out.
 template <int AM, int BM>
-__device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k_len, int nkb, uint32_t smem, NrShared* sh,
+__device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k_len, int nkb, uint32_t smem, uint32_t stage_bytes, NrShared* sh,
                                        uint32_t idesc, bool want_dbias, float (&bsum)[4], int tid) {
     bool ok = true;
     float4 ra[4], rb[8];
@@ -240,7 +243,7 @@ __device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k
     lb.load(rb, k_len, tid);
     for (int kb = 0; kb < nkb; ++kb) {
         const uint32_t s = kb & 1;
-        const uint32_t stA = smem + s * kNrStage, stB = stA + kNrStageA;
+        const uint32_t stA = smem + s * stage_bytes, stB = stA + kNrStageA;
         if (kb >= 2 && ok) ok = mbar_wait(smem_u32(&sh->stage_free[s]), ((kb >> 1) - 1) & 1);
         if (want_dbias) {
 #pragma unroll
@@ -358,7 +361,7 @@ __device__ __forceinline__ void load_rgb_prev(float (&r)[3], const NrProb& P, in
     for (int j = 0; j < 3; ++j) r[j] = (active && P.rgb_in && m < P.M) ? __ldg(P.rgb_in + item * 3ll * P.M + (long long)j * P.M + m) : 0.f;
 }
 
-__global__ void __launch_bounds__(kNrThreads, 2) nr_gemm_kernel(const __grid_constant__ NrLaunch L) {
+__global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(const __grid_constant__ NrLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ NrShared sh;
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -375,7 +378,10 @@ __global__ void __launch_bounds__(kNrThreads, 2) nr_gemm_kernel(const __grid_con
         mbar_init(smem_u32(&sh.done), 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc<256>(smem_u32(&sh.tmem_base));   // published by the first __syncthreads of the contraction loop
+    if (warp == 0) {                                           // published by the first __syncthreads of the contraction loop
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)), "r"(L.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     bool ok = true;
 
     {
@@ -411,10 +417,10 @@ __global__ void __launch_bounds__(kNrThreads, 2) nr_gemm_kernel(const __grid_con
         float bsum[4] = {0.f, 0.f, 0.f, 0.f};
         const bool a_rc = P.a_rs == 1 && (P.a_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.base) & 15) == 0) && (A.rows_valid >= 128 || (A.rows_valid & 3) == 0);
         const bool b_rc = P.b_rs == 1 && (P.b_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0) && (B.rows_valid >= n_tile || (B.rows_valid & 3) == 0);
-        if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV>(A, B, k_len, nkb, smem, &sh, idesc, want_dbias, bsum, tid);
-        else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC>(A, B, k_len, nkb, smem, &sh, idesc, want_dbias, bsum, tid);
-        else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV>(A, B, k_len, nkb, smem, &sh, idesc, want_dbias, bsum, tid);
-        else ok = k_loop<kModeGen, kModeGen>(A, B, k_len, nkb, smem, &sh, idesc, want_dbias, bsum, tid);
+        if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+        else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+        else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+        else ok = k_loop<kModeGen, kModeGen>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
         if (ok) ok = mbar_wait(smem_u32(&sh.done), 0);
         tc_fence_after_sync();
         if (!ok && tid == 0) atomicCAS(L.status, 0, 801);
@@ -453,7 +459,7 @@ __global__ void __launch_bounds__(kNrThreads, 2) nr_gemm_kernel(const __grid_con
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_free<256>(sh.tmem_base);
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "r"(L.tmem_cols) : "memory");
 }
 
 // Gradient entering a block's feat_layers convolution (neural_renderer.py:83-87 backwards): the RGB head adds W_rgb^T g_rgb to
@@ -600,7 +606,11 @@ static int launch_group(std::vector<NrProb>& ps, int* status, cudaStream_t st) {
     ps.clear();
     if (!L.n) return 0;
     L.status = status;
-    nr_gemm_kernel<<<total, kNrThreads, kNrSmem, st>>>(L);
+    int widest = 16;
+    for (int i = 0; i < L.n; ++i) widest = std::max(widest, L.p[i].n_tile);
+    L.tmem_cols = widest <= 32 ? 32 : (widest <= 64 ? 64 : (widest <= 128 ? 128 : 256));
+    L.stage_bytes = kNrStageA + (uint32_t)((widest * 128 + 1023) & ~1023);
+    nr_gemm_kernel<<<total, kNrThreads, 2 * L.stage_bytes + 1024, st>>>(L);
     return check_launch("hn_nr (grouped tf32 GEMM)");
 }
 

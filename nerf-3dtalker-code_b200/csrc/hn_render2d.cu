@@ -23,57 +23,75 @@ __device__ __forceinline__ float shuffled(const float* __restrict__ z2, const fl
     return lrelu(__ldg(z2 + ((size_t)b * 4 * C + k) * H * W + pix), slope) + __ldg(x + ((size_t)b * C + (k % C)) * H * W + pix);
 }
 
-// Block = one (item, channel) plane x one tile of 32 x 32 output pixels (16 x 16 input pixels).  The shuffled tensor
-// s = pixel_shuffle(leaky_relu(z2) + repeat(x, 4)) of the tile plus a one-pixel halo (reflected at the image border) is
-// built ONCE in shared memory - 2.3 global loads per output instead of 18 - and the 3 x 3 filter runs from there.
-constexpr int kT = 32;                                            // output tile edge
+// Forward tail, one CTA = one (item, channel) plane x a tile of 32 x 8 INPUT pixels (64 x 16 outputs), one thread per input pixel.
+// An input pixel owns a 2 x 2 quad of the shuffled tensor s = pixel_shuffle(leaky_relu(z2) + repeat(x, 4)) (its four sub-channels
+// 4c .. 4c+3): phase A builds the quads of the tile plus one quad of margin in shared memory (8 coalesced plane loads per quad,
+// no per-element index arithmetic), phase B mirrors the rows / columns next to the image border (reflect padding: s[-1] = s[1],
+// s[n] = s[n-2]), then every thread filters its own quad from a 4 x 4 window: 16 shared loads and 36 FMAs for four outputs,
+// stored as two float2.
+constexpr int kQW = 32, kQH = 8;                                   // input-pixel tile
+constexpr int kSW = 2 * kQW + 4, kSH = 2 * kQH + 4;                // shared tile: outputs Y0 - 2 .. Y0 + 2 kQH + 1
 __global__ void __launch_bounds__(256) upsample_tail_fwd_kernel(const float* __restrict__ z2, const float* __restrict__ x, Taps3 f,
                                                                 float* __restrict__ y, int B, int C, int H, int W, float slope) {
-    __shared__ float s[kT + 2][kT + 3];
+    __shared__ float s[kSH][kSW + 1];
     const int H2 = 2 * H, W2 = 2 * W;
-    const int tiles_x = (W2 + kT - 1) / kT;
-    const int X0 = (blockIdx.x % tiles_x) * kT, Y0 = (blockIdx.x / tiles_x) * kT;
+    const int tiles_x = (W + kQW - 1) / kQW;
+    const int j0 = (blockIdx.x % tiles_x) * kQW, i0 = (blockIdx.x / tiles_x) * kQH;
     const int c = blockIdx.y, b = blockIdx.z;
-    for (int e = threadIdx.x; e < (kT + 2) * (kT + 2); e += 256) {
-        const int sy = e / (kT + 2), sx = e % (kT + 2);
-        const int Y = Y0 - 1 + sy, X = X0 - 1 + sx;
-        float v = 0.f;
-        if (Y <= H2 && X <= W2) v = shuffled(z2, x, b, c, reflect_idx(Y, H2), reflect_idx(X, W2), C, H, W, slope);   // (<=: row n - 1 needs the reflected row n)
-        s[sy][sx] = v;
+    const size_t HW = (size_t)H * W;
+    const float* zq = z2 + ((size_t)b * 4 * C + 4 * c) * HW;       // sub-channel q at zq + q * HW
+    const float* xb = x + (size_t)b * C * HW;
+    int xm[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xm[q] = (4 * c + q) % C;
+    // phase A: quads (i0 - 1 + qi, j0 - 1 + qj), qi < kQH + 2, qj < kQW + 2
+    for (int e = threadIdx.x; e < (kQH + 2) * (kQW + 2); e += 256) {
+        const int qi = e / (kQW + 2), qj = e - qi * (kQW + 2);
+        const int i = i0 - 1 + qi, j = j0 - 1 + qj;
+        if (i < 0 || i >= H || j < 0 || j >= W) continue;
+        const size_t pix = (size_t)i * W + j;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = lrelu(__ldg(zq + q * HW + pix), slope) + __ldg(xb + xm[q] * HW + pix);
+        s[2 * qi][2 * qj] = v[0]; s[2 * qi][2 * qj + 1] = v[1];
+        s[2 * qi + 1][2 * qj] = v[2]; s[2 * qi + 1][2 * qj + 1] = v[3];
     }
     __syncthreads();
-    const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;
+    // phase B: reflect.  Shared row r holds output row Y0 - 2 + r (Y0 = 2 i0); rows first (all columns), then columns (all rows)
+    const int Y0 = 2 * i0, X0 = 2 * j0;
+    if (Y0 == 0)
+        for (int t = threadIdx.x; t < kSW; t += 256) s[1][t] = s[3][t];                               // Y = -1 <- Y = 1
+    if (H2 - Y0 + 2 < kSH && H2 - Y0 + 2 >= 2)
+        for (int t = threadIdx.x; t < kSW; t += 256) s[H2 - Y0 + 2][t] = s[H2 - Y0][t];               // Y = H2 <- Y = H2 - 2
+    __syncthreads();
+    if (X0 == 0)
+        for (int t = threadIdx.x; t < kSH; t += 256) s[t][1] = s[t][3];
+    if (W2 - X0 + 2 < kSW && W2 - X0 + 2 >= 2)
+        for (int t = threadIdx.x; t < kSH; t += 256) s[t][W2 - X0 + 2] = s[t][W2 - X0];
+    __syncthreads();
+    const int tj = threadIdx.x & 31, ti = threadIdx.x >> 5;
+    const int i = i0 + ti, j = j0 + tj;
+    if (i >= H || j >= W) return;
+    float w[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) w[r][t] = s[2 * ti + 1 + r][2 * tj + 1 + t];
     float* plane = y + ((size_t)b * C + c) * H2 * W2;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int ty = ty0 + 8 * r, Y = Y0 + ty, X = X0 + tx;
-        if (Y >= H2 || X >= W2) continue;
-        float acc = 0.f;
+    for (int dy = 0; dy < 2; ++dy) {
+        float o[2];
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
+        for (int dx = 0; dx < 2; ++dx) {
+            float acc = 0.f;
 #pragma unroll
-            for (int e = 0; e < 3; ++e) acc = fmaf(f.w[a] * f.w[e], s[ty + a][tx + e], acc);
-        plane[(size_t)Y * W2 + X] = acc;
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) acc = fmaf(f.w[a] * f.w[e], w[dy + a][dx + e], acc);
+            o[dx] = acc;
+        }
+        *reinterpret_cast<float2*>(plane + (size_t)(2 * i + dy) * W2 + 2 * j) = make_float2(o[0], o[1]);
     }
-}
-
-// adjoint of the reflect-padded 3-tap filter along one axis: positions P and weights with reflect(P + a) == Y
-struct AdjTaps { int p[4]; float w[4]; int n; };
-__device__ __forceinline__ AdjTaps adjoint_taps(int Y, int n, const Taps3& f) {
-    AdjTaps t; t.n = 0;
-    if (Y + 1 < n) { t.p[t.n] = Y + 1; t.w[t.n++] = f.w[0]; }     // a = -1
-    t.p[t.n] = Y; t.w[t.n++] = f.w[1];                            // a = 0
-    if (Y - 1 >= 0) { t.p[t.n] = Y - 1; t.w[t.n++] = f.w[2]; }    // a = +1
-    if (Y == 1) { t.p[t.n] = 0; t.w[t.n++] = f.w[0]; }            // P + a = -1 reflects onto 1
-    if (Y == n - 2) { t.p[t.n] = n - 1; t.w[t.n++] = f.w[2]; }    // P + a = n reflects onto n - 2
-    return t;
-}
-__device__ __forceinline__ float blur_adjoint_at(const float* __restrict__ dy_plane, int Y, int X, int H2, int W2, const Taps3& f) {
-    const AdjTaps ty = adjoint_taps(Y, H2, f), tx = adjoint_taps(X, W2, f);
-    float acc = 0.f;
-    for (int a = 0; a < ty.n; ++a)
-        for (int e = 0; e < tx.n; ++e) acc = fmaf(ty.w[a] * tx.w[e], __ldg(dy_plane + (size_t)ty.p[a] * W2 + tx.p[e]), acc);
-    return acc;
 }
 
 // Backward: block = one (item, channel) plane x 64 x 16 output pixels (32 x 8 input pixels, one per thread, a full warp along
@@ -81,47 +99,70 @@ __device__ __forceinline__ float blur_adjoint_at(const float* __restrict__ dy_pl
 // again a 3-tap filter whose outer weights pick up the reflected tap next to the border (position 1 also receives what row -1
 // read, position n-2 what row n read), so ds needs no index lists: 9 shared-memory taps per output position.
 // dz2 = ds * leaky_relu'(z2) for the pixel's four sub-channels; ds is added to the x channel it came from (x[m] feeds the four
-// shuffled channels m, m+C, m+2C, m+3C: atomics, dx zero-initialised).
+// shuffled channels m, m+C, m+2C, m+3C; dx accumulates).
 constexpr int kBX = 64, kBY = 16;
 __device__ __forceinline__ void adjoint_weights(int Y, int n, const Taps3& f, float* cm, float* c0, float* cp) {
     *cm = f.w[2] + (Y == 1 ? f.w[0] : 0.f);          // coefficient of dy[Y - 1]
     *c0 = f.w[1];
     *cp = f.w[0] + (Y == n - 2 ? f.w[2] : 0.f);      // coefficient of dy[Y + 1]
 }
+// GROUPED = true (C % 4 == 0): blockIdx.y = c0 < C / 4 and the CTA walks the four planes c0 + r C / 4, whose sub-channels
+// 4 c + q = 4 c0 + q + r C are exactly the four shuffled channels fed by x channel 4 c0 + q - so dx is owned by one thread and
+// needs no atomics.  GROUPED = false: one plane per CTA, dx with atomics.
+template <bool GROUPED>
 __global__ void __launch_bounds__(256) upsample_tail_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z2, Taps3 f,
                                                                 float* __restrict__ dz2, float* __restrict__ dx, int B, int C, int H, int W, float slope) {
     __shared__ float g[kBY + 2][kBX + 3];
     const int H2 = 2 * H, W2 = 2 * W;
     const int tiles_x = (W2 + kBX - 1) / kBX;
     const int X0 = (blockIdx.x % tiles_x) * kBX, Y0 = (blockIdx.x / tiles_x) * kBY;
-    const int c = blockIdx.y, b = blockIdx.z;
-    const float* plane = dy + ((size_t)b * C + c) * H2 * W2;
-    for (int e = threadIdx.x; e < (kBY + 2) * (kBX + 2); e += 256) {
-        const int sy = e / (kBX + 2), sx = e % (kBX + 2);
-        const int Y = Y0 - 1 + sy, X = X0 - 1 + sx;
-        g[sy][sx] = (Y >= 0 && Y < H2 && X >= 0 && X < W2) ? __ldg(plane + (size_t)Y * W2 + X) : 0.f;
-    }
-    __syncthreads();
+    const int b = blockIdx.z;
     const int lj = threadIdx.x & 31, li = threadIdx.x >> 5;
     const int j = (X0 >> 1) + lj, i = (Y0 >> 1) + li;
-    if (i >= H || j >= W) return;
+    const bool inside = i < H && j < W;
     const size_t pix = (size_t)i * W + j;
+    float wy[2][3], wx[2][3];                                 // adjoint weights of this thread's two output rows / columns
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int ly = 2 * li + (q >> 1), lx = 2 * lj + (q & 1);     // position inside the tile; shared-memory index = +1
-        float ym, y0, yp, xm, x0, xp;
-        adjoint_weights(Y0 + ly, H2, f, &ym, &y0, &yp);
-        adjoint_weights(X0 + lx, W2, f, &xm, &x0, &xp);
-        const float r0 = xm * g[ly][lx] + x0 * g[ly][lx + 1] + xp * g[ly][lx + 2];
-        const float r1 = xm * g[ly + 1][lx] + x0 * g[ly + 1][lx + 1] + xp * g[ly + 1][lx + 2];
-        const float r2 = xm * g[ly + 2][lx] + x0 * g[ly + 2][lx + 1] + xp * g[ly + 2][lx + 2];
-        const float ds = ym * r0 + y0 * r1 + yp * r2;
-        const int k = 4 * c + q;
-        if (dz2) {
-            const size_t zi = ((size_t)b * 4 * C + k) * H * W + pix;
-            dz2[zi] = __ldg(z2 + zi) > 0.f ? ds : ds * slope;
+    for (int d = 0; d < 2; ++d) {
+        adjoint_weights(Y0 + 2 * li + d, H2, f, &wy[d][0], &wy[d][1], &wy[d][2]);
+        adjoint_weights(X0 + 2 * lj + d, W2, f, &wx[d][0], &wx[d][1], &wx[d][2]);
+    }
+    float dxacc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int n_planes = GROUPED ? 4 : 1;
+    for (int r = 0; r < n_planes; ++r) {
+        const int c = GROUPED ? (int)blockIdx.y + r * (C >> 2) : (int)blockIdx.y;
+        const float* plane = dy + ((size_t)b * C + c) * H2 * W2;
+        if (r) __syncthreads();
+        for (int e = threadIdx.x; e < (kBY + 2) * (kBX + 2); e += 256) {
+            const int sy = e / (kBX + 2), sx = e % (kBX + 2);
+            const int Y = Y0 - 1 + sy, X = X0 - 1 + sx;
+            g[sy][sx] = (Y >= 0 && Y < H2 && X >= 0 && X < W2) ? __ldg(plane + (size_t)Y * W2 + X) : 0.f;
         }
-        if (dx) atomicAdd(dx + ((size_t)b * C + (k % C)) * H * W + pix, ds);
+        __syncthreads();
+        if (!inside) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int dyq = q >> 1, dxq = q & 1;
+            const int ly = 2 * li + dyq, lx = 2 * lj + dxq;   // position inside the tile; shared-memory index = +1
+            const float r0 = wx[dxq][0] * g[ly][lx] + wx[dxq][1] * g[ly][lx + 1] + wx[dxq][2] * g[ly][lx + 2];
+            const float r1 = wx[dxq][0] * g[ly + 1][lx] + wx[dxq][1] * g[ly + 1][lx + 1] + wx[dxq][2] * g[ly + 1][lx + 2];
+            const float r2 = wx[dxq][0] * g[ly + 2][lx] + wx[dxq][1] * g[ly + 2][lx + 1] + wx[dxq][2] * g[ly + 2][lx + 2];
+            const float ds = wy[dyq][0] * r0 + wy[dyq][1] * r1 + wy[dyq][2] * r2;
+            const int k = 4 * c + q;
+            if (dz2) {
+                const size_t zi = ((size_t)b * 4 * C + k) * H * W + pix;
+                dz2[zi] = __ldg(z2 + zi) > 0.f ? ds : ds * slope;
+            }
+            if (GROUPED) dxacc[q] += ds;
+            else if (dx) atomicAdd(dx + ((size_t)b * C + (k % C)) * H * W + pix, ds);
+        }
+    }
+    if (GROUPED && dx && inside) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float* d = dx + ((size_t)b * C + 4 * blockIdx.y + q) * H * W + pix;
+            *d += dxacc[q];                                   // accumulate semantics without atomics: this thread owns the element
+        }
     }
 }
 
@@ -133,47 +174,90 @@ __device__ __forceinline__ void bilinear_src(int Y, int n_in, int* i0, int* i1, 
     *i1 = *i0 + 1 < n_in ? *i0 + 1 : n_in - 1;
     *l = s - (float)*i0;
 }
-__device__ __forceinline__ float upsampled(const float* __restrict__ plane, int Y, int X, int H, int W) {
-    int y0, y1, x0, x1; float ly, lx;
-    bilinear_src(Y, H, &y0, &y1, &ly);
-    bilinear_src(X, W, &x0, &x1, &lx);
-    const float top = (1.f - lx) * __ldg(plane + (size_t)y0 * W + x0) + lx * __ldg(plane + (size_t)y0 * W + x1);
-    const float bot = (1.f - lx) * __ldg(plane + (size_t)y1 * W + x0) + lx * __ldg(plane + (size_t)y1 * W + x1);
-    return (1.f - ly) * top + ly * bot;
+// blur(bilinear x2) along one axis is a fixed linear map with at most three input taps per output: output Y (input index
+// i = Y / 2) reads inputs i - 1, i, i + 1.  w[t] = weight of input i - 1 + t: the three blur taps at the reflected positions
+// Y - 1, Y, Y + 1, each spread over its two (clamped) bilinear sources.
+__device__ __forceinline__ void up_weights(int Y, int n_in, const Taps3& f, float (&w)[3]) {
+    const int i = Y >> 1;
+    w[0] = w[1] = w[2] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        int i0, i1; float l;
+        bilinear_src(reflect_idx(Y + a - 1, 2 * n_in), n_in, &i0, &i1, &l);
+        const int t0 = i0 - (i - 1), t1 = i1 - (i - 1);
+        const float a0 = f.w[a] * (1.f - l), a1 = f.w[a] * l;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) w[t] += (t == t0 ? a0 : 0.f) + (t == t1 ? a1 : 0.f);
+    }
 }
+__device__ __forceinline__ int clampi(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
 
+// one thread per INPUT pixel: its 3 x 3 neighbourhood gives the 2 x 2 outputs above it
 __global__ void __launch_bounds__(256) rgb_upsample_fwd_kernel(const float* __restrict__ x, Taps3 f, float* __restrict__ y, int planes, int H, int W) {
-    const int H2 = 2 * H, W2 = 2 * W;
-    const size_t n = (size_t)planes * H2 * W2;
+    const int W2 = 2 * W;
+    const size_t n = (size_t)planes * H * W;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const int X = (int)(t % W2), Y = (int)((t / W2) % H2), p = (int)(t / ((size_t)W2 * H2));
+        const int j = (int)(t % W), i = (int)((t / W) % H), p = (int)(t / ((size_t)W * H));
         const float* plane = x + (size_t)p * H * W;
-        float acc = 0.f;
+        float v[3][3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const int yy = reflect_idx(Y + a - 1, H2);
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) acc = fmaf(f.w[a] * f.w[e], upsampled(plane, yy, reflect_idx(X + e - 1, W2), H, W), acc);
+            for (int e = 0; e < 3; ++e) v[a][e] = __ldg(plane + (size_t)clampi(i - 1 + a, H) * W + clampi(j - 1 + e, W));
+        float wy[2][3], wx[2][3];
+        up_weights(2 * i, H, f, wy[0]); up_weights(2 * i + 1, H, f, wy[1]);
+        up_weights(2 * j, W, f, wx[0]); up_weights(2 * j + 1, W, f, wx[1]);
+        float* out = y + (size_t)p * 4 * H * W;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            float o[2];
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float acc = 0.f;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) acc = fmaf(wy[dy][a], wx[dx][0] * v[a][0] + wx[dx][1] * v[a][1] + wx[dx][2] * v[a][2], acc);
+                o[dx] = acc;
+            }
+            *reinterpret_cast<float2*>(out + (size_t)(2 * i + dy) * W2 + 2 * j) = make_float2(o[0], o[1]);
         }
-        y[t] = acc;
     }
 }
 
-// one thread per up-sampled pixel: gradient through the blur (gather), then scattered onto its four bilinear sources
+// adjoint as a gather, one thread per INPUT pixel (p, q): the outputs that read input row p are Y = 2 p - 2 .. 2 p + 3 (their
+// input index Y / 2 is p - 1, p or p + 1), with weight up_weights(Y)[p - (Y / 2 - 1)]; same along the columns.  No atomics.
+__device__ __forceinline__ void adjoint_up_weights(int p, int n_in, const Taps3& f, float (&c)[6]) {
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        const int Y = 2 * p - 2 + t;
+        float w[3] = {0.f, 0.f, 0.f};
+        if (Y >= 0 && Y < 2 * n_in) up_weights(Y, n_in, f, w);
+        const int slot = p - ((Y >> 1) - 1);                   // 2, 2, 1, 1, 0, 0 for t = 0 .. 5
+        c[t] = slot == 0 ? w[0] : (slot == 1 ? w[1] : w[2]);
+    }
+}
 __global__ void __launch_bounds__(256) rgb_upsample_bwd_kernel(const float* __restrict__ dy, Taps3 f, float* __restrict__ dx, int planes, int H, int W) {
     const int H2 = 2 * H, W2 = 2 * W;
-    const size_t n = (size_t)planes * H2 * W2;
+    const size_t n = (size_t)planes * H * W;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const int X = (int)(t % W2), Y = (int)((t / W2) % H2), p = (int)(t / ((size_t)W2 * H2));
-        const float g = blur_adjoint_at(dy + (size_t)p * H2 * W2, Y, X, H2, W2, f);
-        int y0, y1, x0, x1; float ly, lx;
-        bilinear_src(Y, H, &y0, &y1, &ly);
-        bilinear_src(X, W, &x0, &x1, &lx);
-        float* plane = dx + (size_t)p * H * W;
-        atomicAdd(plane + (size_t)y0 * W + x0, g * (1.f - ly) * (1.f - lx));
-        atomicAdd(plane + (size_t)y0 * W + x1, g * (1.f - ly) * lx);
-        atomicAdd(plane + (size_t)y1 * W + x0, g * ly * (1.f - lx));
-        atomicAdd(plane + (size_t)y1 * W + x1, g * ly * lx);
+        const int q = (int)(t % W), p = (int)((t / W) % H), pl = (int)(t / ((size_t)W * H));
+        float cy[6], cx[6];
+        adjoint_up_weights(p, H, f, cy);
+        adjoint_up_weights(q, W, f, cx);
+        const float* g = dy + (size_t)pl * H2 * W2;
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const int Y = 2 * p - 2 + a;
+            if (Y < 0 || Y >= H2) continue;
+            float row = 0.f;
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+                const int X = 2 * q - 2 + e;
+                if (X >= 0 && X < W2) row = fmaf(cx[e], __ldg(g + (size_t)Y * W2 + X), row);
+            }
+            acc = fmaf(cy[a], row, acc);
+        }
+        dx[t] += acc;                                          // accumulate semantics; this thread owns the element
     }
 }
 
@@ -195,7 +279,7 @@ extern "C" int hn_upsample_tail_fwd(const float* z2, const float* x, const float
     Taps3 t;
     if (!z2 || !x || !y || !f3_host || B <= 0 || C <= 0 || H < 2 || W < 2 || !taps_from(f3_host, &t)) return set_error(HN_E_BADARG, "hn_upsample_tail_fwd: bad argument");
     if (C > 65535 || B > 65535) return set_error(HN_E_UNSUPPORTED, "hn_upsample_tail_fwd: more than 65535 channels or items");
-    const dim3 grid((unsigned)(((2 * W + kT - 1) / kT) * ((2 * H + kT - 1) / kT)), (unsigned)C, (unsigned)B);
+    const dim3 grid((unsigned)(((W + kQW - 1) / kQW) * ((H + kQH - 1) / kQH)), (unsigned)C, (unsigned)B);
     upsample_tail_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z2, x, t, y, B, C, H, W, 0.2f);
     return check_launch("hn_upsample_tail_fwd");
 }
@@ -204,22 +288,23 @@ extern "C" int hn_upsample_tail_bwd(const float* dy, const float* z2, const floa
     Taps3 t;
     if (!dy || !z2 || !f3_host || B <= 0 || C <= 0 || H < 2 || W < 2 || !taps_from(f3_host, &t)) return set_error(HN_E_BADARG, "hn_upsample_tail_bwd: bad argument");
     if (C > 65535 || B > 65535) return set_error(HN_E_UNSUPPORTED, "hn_upsample_tail_bwd: more than 65535 channels or items");
-    const dim3 grid((unsigned)(((2 * W + kBX - 1) / kBX) * ((2 * H + kBY - 1) / kBY)), (unsigned)C, (unsigned)B);
-    upsample_tail_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
+    const unsigned tiles = (unsigned)(((2 * W + kBX - 1) / kBX) * ((2 * H + kBY - 1) / kBY));
+    if (C % 4 == 0) upsample_tail_bwd_kernel<true><<<dim3(tiles, (unsigned)(C / 4), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
+    else upsample_tail_bwd_kernel<false><<<dim3(tiles, (unsigned)C, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
     return check_launch("hn_upsample_tail_bwd");
 }
 extern "C" int hn_rgb_upsample_fwd(const float* x, const float* f3_host, float* y, int planes, int H, int W, void* stream) {
     using namespace hn;
     Taps3 t;
     if (!x || !y || !f3_host || planes <= 0 || H < 2 || W < 2 || !taps_from(f3_host, &t)) return set_error(HN_E_BADARG, "hn_rgb_upsample_fwd: bad argument");
-    rgb_upsample_fwd_kernel<<<grid_for((size_t)planes * 4 * H * W), 256, 0, (cudaStream_t)stream>>>(x, t, y, planes, H, W);
+    rgb_upsample_fwd_kernel<<<grid_for((size_t)planes * H * W), 256, 0, (cudaStream_t)stream>>>(x, t, y, planes, H, W);
     return check_launch("hn_rgb_upsample_fwd");
 }
 extern "C" int hn_rgb_upsample_bwd(const float* dy, const float* f3_host, float* dx_zeroed, int planes, int H, int W, void* stream) {
     using namespace hn;
     Taps3 t;
     if (!dy || !dx_zeroed || !f3_host || planes <= 0 || H < 2 || W < 2 || !taps_from(f3_host, &t)) return set_error(HN_E_BADARG, "hn_rgb_upsample_bwd: bad argument");
-    rgb_upsample_bwd_kernel<<<grid_for((size_t)planes * 4 * H * W), 256, 0, (cudaStream_t)stream>>>(dy, t, dx_zeroed, planes, H, W);
+    rgb_upsample_bwd_kernel<<<grid_for((size_t)planes * H * W), 256, 0, (cudaStream_t)stream>>>(dy, t, dx_zeroed, planes, H, W);
     return check_launch("hn_rgb_upsample_bwd");
 }
 
