@@ -466,30 +466,49 @@ __global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(con
 // the gradient arriving from the next block, then LeakyReLU'.  For the last block g_rgb itself comes from the image gradient
 // through the sigmoid.  One thread per pixel and group of 16 channels (coalesced across the warp).
 constexpr int kHeadChannels = 16;
+template <int V>                                                // V = pixels per thread (4: float4 along the plane, needs P % 4 == 0)
 __global__ void __launch_bounds__(256) nr_head_bwd_kernel(const float* __restrict__ g_img, const float* __restrict__ img, int sigmoid,
                                                           float* __restrict__ g_rgb, const float* __restrict__ g_net, const float* __restrict__ net,
                                                           const float* __restrict__ wrgb, float* __restrict__ g_pre, int Cn, long long P, int items) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V;
     if (t >= P * items) return;
     const int item = (int)(t / P);
     const long long p = t % P;
-    float gr[3];
+    float gr[3][V];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const long long idx = ((long long)item * 3 + j) * P + p;
-        if (g_img) {
-            float g = __ldg(g_img + idx);
-            if (sigmoid) { const float s = __ldg(img + idx); g *= s * (1.0f - s); }
-            if (blockIdx.y == 0) g_rgb[idx] = g;
-            gr[j] = g;
-        } else gr[j] = g_rgb[idx];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            if (g_img) {
+                float g = __ldg(g_img + idx + e);
+                if (sigmoid) { const float s = __ldg(img + idx + e); g *= s * (1.0f - s); }
+                if (blockIdx.y == 0) g_rgb[idx + e] = g;
+                gr[j][e] = g;
+            } else gr[j][e] = g_rgb[idx + e];
+        }
     }
     const int c_end = min(Cn, (int)(blockIdx.y + 1) * kHeadChannels);
     for (int c = blockIdx.y * kHeadChannels; c < c_end; ++c) {
         const long long idx = ((long long)item * Cn + c) * P + p;
-        float v = fmaf(__ldg(wrgb + c), gr[0], fmaf(__ldg(wrgb + Cn + c), gr[1], __ldg(wrgb + 2 * Cn + c) * gr[2]));
-        if (g_net) v += __ldg(g_net + idx);
-        g_pre[idx] = __ldg(net + idx) > 0.f ? v : v * kSlope;
+        const float w0 = __ldg(wrgb + c), w1 = __ldg(wrgb + Cn + c), w2 = __ldg(wrgb + 2 * Cn + c);
+        float a[V], gn[V], o[V];
+        if (V == 4) {
+            const float4 av = __ldg(reinterpret_cast<const float4*>(net + idx));
+            a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+            if (g_net) { const float4 gv = __ldg(reinterpret_cast<const float4*>(g_net + idx)); gn[0] = gv.x; gn[1] = gv.y; gn[2] = gv.z; gn[3] = gv.w; }
+        } else {
+            a[0] = __ldg(net + idx);
+            if (g_net) gn[0] = __ldg(g_net + idx);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            float v = fmaf(w0, gr[0][e], fmaf(w1, gr[1][e], w2 * gr[2][e]));
+            if (g_net) v += gn[e];
+            o[e] = a[e] > 0.f ? v : v * kSlope;
+        }
+        if (V == 4) *reinterpret_cast<float4*>(g_pre + idx) = make_float4(o[0], o[1], o[2], o[3]);
+        else g_pre[idx] = o[0];
     }
 }
 
@@ -728,9 +747,16 @@ extern "C" int hn_nr_bwd(const hn_nr_bwd_t* b, void* stream) {
         float* gR = sc + T.gR[i + 1];
         {   // gradient entering feat_layers[i]'s pre-activation
             const long long n = d.P[i + 1] * B;
-            nr_head_bwd_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)((Cn + kHeadChannels - 1) / kHeadChannels)), 256, 0, st>>>(last ? b->g_img : nullptr, a->img, last && a->final_actvn, gR,
-                                                                            last ? nullptr : sc + T.dxs[i + 1], sv + S.net[i], a->wrgb[i + 1],
-                                                                            sc + T.gpre_f, Cn, d.P[i + 1], B);
+            const dim3 cg((unsigned)((Cn + kHeadChannels - 1) / kHeadChannels));
+            const float* gimg = last ? b->g_img : nullptr;
+            const float* gnet = last ? nullptr : sc + T.dxs[i + 1];
+            const bool v4 = d.P[i + 1] % 4 == 0 && (reinterpret_cast<uintptr_t>(b->g_img) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->img) & 15) == 0;
+            if (v4)
+                nr_head_bwd_kernel<4><<<dim3((unsigned)((n / 4 + 255) / 256), cg.x), 256, 0, st>>>(gimg, a->img, last && a->final_actvn, gR, gnet, sv + S.net[i],
+                                                                                                    a->wrgb[i + 1], sc + T.gpre_f, Cn, d.P[i + 1], B);
+            else
+                nr_head_bwd_kernel<1><<<dim3((unsigned)((n + 255) / 256), cg.x), 256, 0, st>>>(gimg, a->img, last && a->final_actvn, gR, gnet, sv + S.net[i],
+                                                                                                a->wrgb[i + 1], sc + T.gpre_f, Cn, d.P[i + 1], B);
             if (int rc = check_launch("hn_nr_bwd (RGB head)")) return rc;
         }
         g.push_back(pixel_rows(sc + T.gpre_f, Cn, d.P[i + 1], B, a->wf[i], C, true, C, sc + T.g_y));

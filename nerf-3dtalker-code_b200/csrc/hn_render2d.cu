@@ -129,24 +129,44 @@ __global__ void __launch_bounds__(256) upsample_tail_bwd_kernel(const float* __r
     }
     float dxacc[4] = {0.f, 0.f, 0.f, 0.f};
     const int n_planes = GROUPED ? 4 : 1;
+    const bool vec_rows = (W2 & 3) == 0 && X0 + kBX <= W2 && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
     for (int r = 0; r < n_planes; ++r) {
         const int c = GROUPED ? (int)blockIdx.y + r * (C >> 2) : (int)blockIdx.y;
         const float* plane = dy + ((size_t)b * C + c) * H2 * W2;
         if (r) __syncthreads();
-        for (int e = threadIdx.x; e < (kBY + 2) * (kBX + 2); e += 256) {
-            const int sy = e / (kBX + 2), sx = e % (kBX + 2);
-            const int Y = Y0 - 1 + sy, X = X0 - 1 + sx;
-            g[sy][sx] = (Y >= 0 && Y < H2 && X >= 0 && X < W2) ? __ldg(plane + (size_t)Y * W2 + X) : 0.f;
+        if (vec_rows) {                                       // 64 interior columns as float4 (one row = 16 lanes), the two halo columns apart
+            for (int e = threadIdx.x; e < (kBY + 2) * (kBX / 4); e += 256) {
+                const int sy = e / (kBX / 4), c4 = e % (kBX / 4);
+                const int Y = Y0 - 1 + sy;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (Y >= 0 && Y < H2) v = __ldg(reinterpret_cast<const float4*>(plane + (size_t)Y * W2 + X0) + c4);
+                g[sy][1 + 4 * c4] = v.x; g[sy][2 + 4 * c4] = v.y; g[sy][3 + 4 * c4] = v.z; g[sy][4 + 4 * c4] = v.w;
+            }
+            for (int e = threadIdx.x; e < 2 * (kBY + 2); e += 256) {
+                const int sy = e >> 1, sx = (e & 1) ? kBX + 1 : 0;
+                const int Y = Y0 - 1 + sy, X = X0 - 1 + sx;
+                g[sy][sx] = (Y >= 0 && Y < H2 && X >= 0 && X < W2) ? __ldg(plane + (size_t)Y * W2 + X) : 0.f;
+            }
+        } else {
+            for (int e = threadIdx.x; e < (kBY + 2) * (kBX + 2); e += 256) {
+                const int sy = e / (kBX + 2), sx = e % (kBX + 2);
+                const int Y = Y0 - 1 + sy, X = X0 - 1 + sx;
+                g[sy][sx] = (Y >= 0 && Y < H2 && X >= 0 && X < W2) ? __ldg(plane + (size_t)Y * W2 + X) : 0.f;
+            }
         }
         __syncthreads();
         if (!inside) continue;
+        float win[4][4];                                      // dy at rows Y - 1 .. Y + 2, columns X - 1 .. X + 2 of this thread's quad origin
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) win[a][e] = g[2 * li + a][2 * lj + e];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int dyq = q >> 1, dxq = q & 1;
-            const int ly = 2 * li + dyq, lx = 2 * lj + dxq;   // position inside the tile; shared-memory index = +1
-            const float r0 = wx[dxq][0] * g[ly][lx] + wx[dxq][1] * g[ly][lx + 1] + wx[dxq][2] * g[ly][lx + 2];
-            const float r1 = wx[dxq][0] * g[ly + 1][lx] + wx[dxq][1] * g[ly + 1][lx + 1] + wx[dxq][2] * g[ly + 1][lx + 2];
-            const float r2 = wx[dxq][0] * g[ly + 2][lx] + wx[dxq][1] * g[ly + 2][lx + 1] + wx[dxq][2] * g[ly + 2][lx + 2];
+            const float r0 = wx[dxq][0] * win[dyq][dxq] + wx[dxq][1] * win[dyq][dxq + 1] + wx[dxq][2] * win[dyq][dxq + 2];
+            const float r1 = wx[dxq][0] * win[dyq + 1][dxq] + wx[dxq][1] * win[dyq + 1][dxq + 1] + wx[dxq][2] * win[dyq + 1][dxq + 2];
+            const float r2 = wx[dxq][0] * win[dyq + 2][dxq] + wx[dxq][1] * win[dyq + 2][dxq + 1] + wx[dxq][2] * win[dyq + 2][dxq + 2];
             const float ds = wy[dyq][0] * r0 + wy[dyq][1] * r1 + wy[dyq][2] * r2;
             const int k = 4 * c + q;
             if (dz2) {
