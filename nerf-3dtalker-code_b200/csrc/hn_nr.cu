@@ -18,11 +18,12 @@
 // Operands pass through registers on their way into the canonical SWIZZLE_128B K-major shared-memory layout (128-byte rows of
 // 32 tf32): NCHW planes with rows = pixels are transposed there (float4 loads along the pixels, 4 x 4 register transpose, 16-byte
 // row chunks), rounded to tf32 with one integer add; a two-stage ring feeds four K = 8 MMAs per 32-wide block.
-// Measured (profiles/r02_nr_*): the whole renderer forward + backward at Reso32HR, batch 2: 2.1 ms (the module-by-module cuDNN
+// Measured (profiles/r02_nr_*): the whole renderer forward + backward at Reso32HR, batch 2: 1.9 ms (the module-by-module cuDNN
 // path: 3.3 ms incl. its launch gaps).  What bounds it: the low-resolution layers are chains of 8-16 dependent global-memory
 // round trips on 48-128 CTAs; the high-resolution layers run ~5.5 us per 128-pixel tile with two CTAs per SM (registers);
 // a multi-tile streaming variant was measured and brought nothing once its register prefetch spilled.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "hn_api.h"
 #include "hn_tc.cuh"
@@ -60,7 +61,7 @@ struct NrProb {
     int lrelu, sigmoid, epi;
     int tile0, tiles;
 };
-struct NrLaunch { NrProb p[kNrMaxProblems]; int n; int tmem_cols; uint32_t stage_bytes; int* status; };   // tmem_cols / stage_bytes: sized for the widest tile of the launch
+struct NrLaunch { NrProb p[kNrMaxProblems]; int n; int tmem_cols; int async_loads; uint32_t stage_bytes, window_bytes; int* status; };   // tmem_cols / stage_bytes: sized for the widest tile of the launch
 
 // fp32 -> tf32 operand bits: the tensor core reads the upper 19 bits of the word, so adding half an ulp of the 10-bit mantissa
 // rounds to nearest (ties away) in ONE integer add; cvt.rna.tf32.f32 compiles to four instructions per element on sm_100a,
@@ -123,7 +124,7 @@ __device__ __forceinline__ void sstore(const float4 (&r)[NJ], const Operand& o, 
 }
 
 struct NrShared {
-    uint64_t stage_free[2], done;
+    uint64_t stage_free[4], done;
     uint32_t tmem_base;
     float rgb_part[128 * 3];
     float bias_s[kNrMaxN], wrgb_s[3][kNrMaxN];               // this tile's columns of the bias / RGB-head weights (zero beyond N)
@@ -271,6 +272,78 @@ __device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k
     return ok;
 }
 
+// ---- asynchronous contraction loop of the weight-gradient problems (both operands k-contiguous NCHW planes): cp.async
+// (LDGSTS, 16 bytes) writes every chunk straight to its place in the K-major SWIZZLE_128B tile, no registers in between, so LA
+// K blocks are in flight per CTA behind a ring of 2-4 stages (a weight-gradient CTA walks 16-64 K blocks; through registers
+// every block cost a full global-memory round trip).  Values are not rounded on the way: the tensor core truncates to tf32.
+// Chunk map as in the KCV loader: rows tid / 8 + 32 j, chunk tid % 8.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int bytes = valid ? 16 : 0;                           // 0 = fill the 16 bytes with zeros, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NJ>
+__device__ __forceinline__ void issue_kmajor(const Operand& o, int kb, int k_len, uint32_t stage, int tid) {
+    const int hi = tid >> 3, c = tid & 7;
+    const bool kv = kb * 32 + 4 * c < k_len;
+    const float* src = o.base + hi * o.rs + kb * 32 + 4 * c;
+    const uint32_t dst = stage + (hi >> 3) * 1024 + (hi & 7) * 128 + ((c ^ (hi & 7)) << 4);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int row = hi + 32 * j;
+        if (row < o.rows_tile) cp_async16(dst + j * 4096, src + j * 32 * o.rs, kv && row < o.rows_valid);
+    }
+}
+template <int LA>                                               // LA = K blocks in flight beyond the one being consumed
+__device__ __forceinline__ bool k_loop_async(const Operand& A, const Operand& B, int k_len, int nkb, uint32_t smem, int n_stages, uint32_t stage_bytes,
+                                             NrShared* sh, uint32_t idesc, bool want_dbias, float (&bsum)[4], int tid) {
+    bool ok = true;
+#pragma unroll
+    for (int b = 0; b < LA; ++b) {
+        if (b < nkb) {
+            issue_kmajor<4>(A, b, k_len, smem + b * stage_bytes, tid);
+            issue_kmajor<8>(B, b, k_len, smem + b * stage_bytes + kNrStageA, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int nx = kb + LA;
+        if (nx < nkb) {
+            const int sn = nx % n_stages;
+            if (nx >= n_stages && ok) ok = mbar_wait(smem_u32(&sh->stage_free[sn]), ((nx / n_stages) - 1) & 1);   // its previous tenant's MMAs retired
+            issue_kmajor<4>(A, nx, k_len, smem + sn * stage_bytes, tid);
+            issue_kmajor<8>(B, nx, k_len, smem + sn * stage_bytes + kNrStageA, tid);
+        }
+        cp_async_commit();
+        cp_async_wait<LA>();                                    // this thread's chunks of block kb have landed
+        const int s = kb % n_stages;
+        const uint32_t stA = smem + s * stage_bytes, stB = stA + kNrStageA;
+        if (want_dbias) {                                       // row sums of this thread's own chunks (rows tid / 8 + 32 j)
+            const int hi = tid >> 3, c = tid & 7;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 v = ld_shared_v4(stA + ((hi >> 3) + 4 * j) * 1024 + (hi & 7) * 128 + ((c ^ (hi & 7)) << 4));
+                bsum[j] += (__uint_as_float(v.x) + __uint_as_float(v.y)) + (__uint_as_float(v.z) + __uint_as_float(v.w));
+            }
+        }
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();                                        // (the first one also publishes the barriers and the TMEM address)
+        if (tid == 0 && ok) {
+            tc_fence_after_sync();
+            const uint32_t tmem_base = sh->tmem_base;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                umma_tf32(tmem_base, umma_desc_kmajor(stA, ks), umma_desc_kmajor(stB, ks), idesc, (kb | ks) ? 1u : 0u);
+            umma_commit(smem_u32(&sh->stage_free[s]));
+            if (kb == nkb - 1) umma_commit(smem_u32(&sh->done));
+        }
+    }
+    return ok;
+}
+
 // Epilogue of a pixel-row tile for one 32-column piece, specialised at compile time (a generic version with run-time null checks
 // compiled into one dependent load -> use -> store chain per element, ~300 cycles each): the per-column vectors (bias, RGB-head
 // weights) were staged in shared memory while the contraction ran; the per-element operand (saved activation for LeakyReLU',
@@ -373,8 +446,8 @@ __global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(con
     const NrProb& P = L.p[pi];
 
     if (tid == 0) {
-        mbar_init(smem_u32(&sh.stage_free[0]), 1);
-        mbar_init(smem_u32(&sh.stage_free[1]), 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&sh.stage_free[i]), 1);
         mbar_init(smem_u32(&sh.done), 1);
         mbar_fence_init();
     }
@@ -419,6 +492,12 @@ __global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(con
         const bool b_rc = P.b_rs == 1 && (P.b_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0) && (B.rows_valid >= n_tile || (B.rows_valid & 3) == 0);
         if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
         else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+        else if (A.vec && B.vec && L.async_loads && nkb >= 4) {
+            const uint32_t sb = kNrStageA + (uint32_t)((n_tile * 128 + 1023) & ~1023);          // this tile's stage: as many as fit the launch's window
+            const int n_stages = min(4, (int)(L.window_bytes / sb));
+            if (n_stages >= 4) ok = k_loop_async<2>(A, B, k_len, nkb, smem, n_stages, sb, &sh, idesc, want_dbias, bsum, tid);
+            else ok = k_loop_async<1>(A, B, k_len, nkb, smem, n_stages, sb, &sh, idesc, want_dbias, bsum, tid);
+        }
         else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
         else ok = k_loop<kModeGen, kModeGen>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
         if (ok) ok = mbar_wait(smem_u32(&sh.done), 0);
@@ -610,7 +689,21 @@ static NrProb weight_grad(const float* g, int M, const float* x, int N, long lon
     return p;
 }
 
+static bool async_enabled() {
+    static const bool on = [] { const char* e = getenv("HN_NR_ASYNC"); return !(e && e[0] == '0'); }();
+    return on;
+}
 static int launch_group(std::vector<NrProb>& ps, int* status, cudaStream_t st) {
+    static const bool split = [] { const char* e = getenv("HN_NR_SPLIT"); return e && e[0] == '1'; }();      // diagnostic: one launch per problem
+    if (split && ps.size() > 1) {
+        std::vector<NrProb> all;
+        all.swap(ps);
+        for (auto& p : all) {
+            std::vector<NrProb> one{p};
+            if (int rc = launch_group(one, status, st)) return rc;
+        }
+        return 0;
+    }
     NrLaunch L{};
     int total = 0;
     L.n = 0;
@@ -625,11 +718,18 @@ static int launch_group(std::vector<NrProb>& ps, int* status, cudaStream_t st) {
     ps.clear();
     if (!L.n) return 0;
     L.status = status;
+    L.async_loads = async_enabled() ? 1 : 0;
     int widest = 16;
     for (int i = 0; i < L.n; ++i) widest = std::max(widest, L.p[i].n_tile);
     L.tmem_cols = widest <= 32 ? 32 : (widest <= 64 ? 64 : (widest <= 128 ? 128 : 256));
     L.stage_bytes = kNrStageA + (uint32_t)((widest * 128 + 1023) & ~1023);
-    nr_gemm_kernel<<<total, kNrThreads, 2 * L.stage_bytes + 1024, st>>>(L);
+    L.window_bytes = 2 * L.stage_bytes;                       // two stages of the widest tile; four of the widest weight-gradient tile if that fits 96 KiB
+    for (int i = 0; i < L.n; ++i)
+        if (L.p[i].kind == 1 && L.async_loads) {
+            const uint32_t sb = kNrStageA + (uint32_t)((L.p[i].n_tile * 128 + 1023) & ~1023);
+            L.window_bytes = std::max(L.window_bytes, std::min(4 * sb, 2 * kNrStage));
+        }
+    nr_gemm_kernel<<<total, kNrThreads, L.window_bytes + 1024, st>>>(L);
     return check_launch("hn_nr (grouped tf32 GEMM)");
 }
 
