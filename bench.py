@@ -456,7 +456,7 @@ def run_config3(args):
                    "ms_per_step": round(ms_e2e / args.steps, 4)},
            "sustained": sustained, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
            "library_ms_per_step": round(sum(v["ms_avg"] * v["n"] / args.steps for v in kern.values()), 4), "hot_path_ms_per_step": round(hot, 4),
-           "roofline": {"kernel": "whole step (launch-bound at this size: 131 072 ray*samples per GPU)", "bound": "tensor",
+           "roofline": {"kernel": "whole step: hot-path FLOPs (section 8d) over the step time; ~60 % of the step is the 512x512 NeuralRenderer (memory-bound tf32 convolutions + tails, DESIGN.md 5b)", "bound": "tensor",
                         "achieved": round(FLOP_STEP * M_rank / (ms_step * 1e-3) / 1e12, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                         "frac": round(FLOP_STEP * M_rank / (ms_step * 1e-3) / 1e12 / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["src"]},
            "kernels": {k: {"launches_per_step": v["n"] / args.steps, "ms_avg": round(v["ms_avg"], 4)} for k, v in kern.items()}, "clocks": clocks}
@@ -553,7 +553,7 @@ def run_config4(args):
                    "note": "inputs of the loop are device-resident by definition (one image, fitted for 500 iterations); the per-iteration loss is read back"},
            "gpu_launches": launches, "gpu_launches_per_step": launches / iters,
            "library_ms_per_step": round(sum(v["ms_avg"] * v["n"] / iters for v in kern.values()), 4),
-           "roofline": {"kernel": "whole iteration (launch-bound: 65 536 ray*samples)", "bound": "tensor", "achieved": round(flop_iter / (ms_it * 1e-3) / 1e12, 1),
+           "roofline": {"kernel": "whole iteration: hot-path FLOPs (section 8d) over the iteration time; the split-operand kernels issue 3x those FLOPs (DESIGN.md 6)", "bound": "tensor", "achieved": round(flop_iter / (ms_it * 1e-3) / 1e12, 1),
                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(flop_iter / (ms_it * 1e-3) / 1e12 / peaks["tflops"], 4), "traffic": None,
                         "peak_source": peaks["src"]},
            "kernels": {k: {"launches_per_step": v["n"] / iters, "ms_avg": round(v["ms_avg"], 4)} for k, v in kern.items()}, "clocks": clocks}
