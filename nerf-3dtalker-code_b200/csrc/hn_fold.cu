@@ -212,55 +212,79 @@ namespace hn {
 // db_R0 is delivered through RGB_layer_0's (otherwise unused) entries of item 0's bias-row gradient, from where hn_fold_bias_bwd
 // picks it up like every other bias gradient.  dW_R1a contracts over the CONTIGUOUS index of both operands: one warp per element,
 // lanes along k (coalesced rows, shuffle reduction); dW_R0 and db_R0: one thread per element, consecutive threads on consecutive k.
-__global__ void __launch_bounds__(256) unfuse_r1_kernel(const hn_unfuse_t a) {
-    const int wid = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (wid >= HN_RGB1 * HN_HIDDEN) return;
-    const int n = wid / HN_HIDDEN, c = wid % HN_HIDDEN;
-    float acc = 0.f;
-    for (int k = lane; k < HN_HIDDEN; k += 32) acc = fmaf(__ldg(a.dwf + (size_t)n * HN_HIDDEN + k), __ldg(a.wr0 + (size_t)c * a.ldr0 + k), acc);
-    float g = 0.f;                                                  // the items' bias-row gradients: lanes in parallel, folded with acc
-    for (int b = lane; b < a.B; b += 32) g += a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R1 + n];
-    acc = warp_sum(fmaf(g, __ldg(a.b_r0 + c), acc));
-    if (lane == 0) a.dwr1[(size_t)n * a.ldr1 + c] += acc;
-}
-
-__global__ void __launch_bounds__(256) unfuse_r0_kernel(const hn_unfuse_t a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= HN_HIDDEN * HN_HIDDEN) return;
-    const int c = t / HN_HIDDEN, k = t % HN_HIDDEN;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int n = 0; n < HN_RGB1; ++n) acc = fmaf(__ldg(a.wr1 + (size_t)n * a.ldr1 + c), __ldg(a.dwf + (size_t)n * HN_HIDDEN + k), acc);
-    a.dwr0[(size_t)c * a.ldr0 + k] += acc;
-}
-
-// db_R0 = W_R1a^T g: one block; g (192 sums over the items) goes through shared memory first - 384 threads each re-deriving it with
-// dependent global loads took 0.1 ms
-__global__ void __launch_bounds__(HN_HIDDEN) unfuse_b0_kernel(const hn_unfuse_t a) {
-    __shared__ float g[HN_RGB1];
-    const int t = threadIdx.x;
-    if (t < HN_RGB1) {
-        float s = 0.f;
-        for (int b = 0; b < a.B; ++b) s += a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R1 + t];
-        g[t] = s;
+// Both products and the bias vector in ONE launch, the products as 32 x 32 output tiles (blocks [0, 72): dW_R1 = dW_f W_R0^T + g b_R0^T, 6 x 12 tiles, K = 384;
+// blocks [72, 216): dW_R0 = W_R1a^T dW_f, 12 x 12 tiles, K = 192): 32-wide K chunks through shared memory, 4 outputs per thread.
+// (Round 2's first version - a warp per output element straight from L2 - took 75 us for these 85 MFLOP.)
+constexpr int kUnfuseTilesR1 = (HN_RGB1 / 32) * (HN_HIDDEN / 32), kUnfuseTilesR0 = (HN_HIDDEN / 32) * (HN_HIDDEN / 32);
+__global__ void __launch_bounds__(256) unfuse_gemm_kernel(const hn_unfuse_t a) {
+    __shared__ float As[32][33], Bs[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // ty 0..7
+    if ((int)blockIdx.x == kUnfuseTilesR1 + kUnfuseTilesR0) {        // last block: db_R0 = W_R1a^T g, g = the items' summed RGB_layer_1 bias-row gradients
+        float* g = &As[0][0];
+        for (int t = threadIdx.x; t < HN_RGB1; t += 256) {
+            float sum = 0.f;
+            for (int b = 0; b < a.B; ++b) sum += a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R1 + t];
+            g[t] = sum;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < HN_HIDDEN; t += 256) {
+            float acc = 0.f;
+#pragma unroll 16                                                   // keep 16 independent loads in flight
+            for (int n = 0; n < HN_RGB1; ++n) acc = fmaf(__ldg(a.wr1 + (size_t)n * a.ldr1 + t), g[n], acc);
+            a.dbias_eff[HN_BIAS_OFF_R0 + t] = acc;
+            for (int b = 1; b < a.B; ++b) a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R0 + t] = 0.f;
+        }
+        return;
     }
-    __syncthreads();
-    float acc = 0.f;
-#pragma unroll 16                                                   // one block: keep 16 independent loads in flight
-    for (int n = 0; n < HN_RGB1; ++n) acc = fmaf(__ldg(a.wr1 + (size_t)n * a.ldr1 + t), g[n], acc);
-    a.dbias_eff[HN_BIAS_OFF_R0 + t] = acc;
-    for (int b = 1; b < a.B; ++b) a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R0 + t] = 0.f;
+    const bool r1 = (int)blockIdx.x < kUnfuseTilesR1;
+    if (r1 ? !a.dwr1 : !a.dwr0) return;
+    const int t = r1 ? (int)blockIdx.x : (int)blockIdx.x - kUnfuseTilesR1;
+    const int m0 = (t / (HN_HIDDEN / 32)) * 32, n0 = (t % (HN_HIDDEN / 32)) * 32;   // output rows m0.., columns n0..
+    const int K = r1 ? HN_HIDDEN : HN_RGB1;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};                              // outputs (m0 + ty + 8 r, n0 + tx)
+    for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = ty + 8 * r;
+            if (r1) {       // A[m, k] = dwf[m, k];  B[n, k] = wr0[n, k]      (both k-contiguous)
+                As[row][tx] = __ldg(a.dwf + (size_t)(m0 + row) * HN_HIDDEN + k0 + tx);
+                Bs[row][tx] = __ldg(a.wr0 + (size_t)(n0 + row) * a.ldr0 + k0 + tx);
+            } else {        // A[m, k] = wr1[k, m] (m-contiguous: As[k][m]);  B[n, k] = dwf[k, n] (n-contiguous: Bs[k][n])
+                As[row][tx] = __ldg(a.wr1 + (size_t)(k0 + row) * a.ldr1 + m0 + tx);
+                Bs[row][tx] = __ldg(a.dwf + (size_t)(k0 + row) * HN_HIDDEN + n0 + tx);
+            }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float bv = r1 ? Bs[tx][k] : Bs[k][tx];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(r1 ? As[ty + 8 * r][k] : As[k][ty + 8 * r], bv, acc[r]);
+        }
+        __syncthreads();
+    }
+    if (r1) {
+        float br = __ldg(a.b_r0 + n0 + tx);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int n = m0 + ty + 8 * r;
+            float g = 0.f;                                            // the items' bias-row gradients of RGB_layer_1 output n
+            for (int b = 0; b < a.B; ++b) g += a.dbias_eff[(size_t)b * HN_BIAS_STRIDE + HN_BIAS_OFF_R1 + n];
+            a.dwr1[(size_t)n * a.ldr1 + n0 + tx] += fmaf(g, br, acc[r]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a.dwr0[(size_t)(m0 + ty + 8 * r) * a.ldr0 + n0 + tx] += acc[r];
+    }
 }
+
 }  // namespace hn
 
 extern "C" int hn_unfuse_r0r1(const hn_unfuse_t* a, void* stream) {
     using namespace hn;
     if (!a || !a->wr0 || !a->wr1 || !a->b_r0 || !a->dwf || !a->dbias_eff || a->B <= 0 || a->ldr0 < HN_HIDDEN || a->ldr1 < HN_HIDDEN)
         return set_error(HN_E_BADARG, "hn_unfuse_r0r1: null pointer or inconsistent dimensions");
-    // (the R0 kernel writes RGB_layer_0's bias-row entries, which the R1 kernel does not read: any order)
-    if (a->dwr1) unfuse_r1_kernel<<<(HN_RGB1 * HN_HIDDEN * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
-    if (a->dwr0) unfuse_r0_kernel<<<(HN_HIDDEN * HN_HIDDEN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
-    unfuse_b0_kernel<<<1, HN_HIDDEN, 0, (cudaStream_t)stream>>>(*a);
+    unfuse_gemm_kernel<<<kUnfuseTilesR1 + kUnfuseTilesR0 + 1, 256, 0, (cudaStream_t)stream>>>(*a);
     return check_launch("hn_unfuse_r0r1");
 }
 
