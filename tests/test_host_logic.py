@@ -37,6 +37,40 @@ def test_ctypes_structs_match_header_constants(hn):
     assert L.Camera.xy.offset == 24 and ctypes.sizeof(L.Camera) == 64
 
 
+def test_ctypes_struct_layouts_match_the_header(hn, tmp_path):
+    """Every argument struct of include/headnerf_b200.h, compiled as plain C, has the size - and every field the offset - of
+    its ctypes twin in _lib.py (a silent mismatch would shift pointers inside a library call)."""
+    import shutil
+    import subprocess
+    L = hn._lib
+    pairs = {"hn_weights_t": L.Weights, "hn_camera_t": L.Camera, "hn_mlp_fwd_t": L.MlpFwd, "hn_composite_fwd_t": L.CompositeFwd,
+             "hn_composite_bwd_t": L.CompositeBwd, "hn_mlp_bwd_data_t": L.MlpBwdData, "hn_mlp_bwd_weights_t": L.MlpBwdWeights,
+             "hn_fold_t": L.Fold, "hn_fold_grads_t": L.FoldGrads, "hn_unfuse_t": L.Unfuse, "hn_mlp_fwd_precise_t": L.MlpFwdPrecise,
+             "hn_mlp_bwd_data_precise_t": L.MlpBwdDataPrecise, "hn_render_fwd_t": L.RenderFwd, "hn_render_bwd_t": L.RenderBwd,
+             "hn_photo_loss_t": L.PhotoLoss, "hn_adam_t": L.Adam, "hn_fine_sample_t": L.FineSample, "hn_nr_fwd_t": L.NrFwd, "hn_nr_bwd_t": L.NrBwd}
+    header = open(os.path.join(ROOT, "include", "headnerf_b200.h")).read()
+    declared = set(re.findall(r"^} (hn_[a-z0-9_]+_t);", header, flags=re.M))
+    assert declared == set(pairs), declared ^ set(pairs)
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "headnerf_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True, capture_output=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), (cname, out[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
 @pytest.mark.parametrize("fs,S", [(32, 256), (32, 512), (64, 512)])
 def test_state_dict_layout_matches_reference(hn, fs, S):
     opt = O.OracleOptions(featmap_size=fs, pred_img_size=S)
