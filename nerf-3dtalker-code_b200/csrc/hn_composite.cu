@@ -9,7 +9,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include "hn_api.h"
-#include "hn_tc.cuh"
+#include "hn_mlp_common.cuh"
 
 namespace hn {
 
@@ -119,8 +119,13 @@ __device__ __forceinline__ float transpose_reduce8(float (&part)[8], int lane) {
     return v;
 }
 
+// resident CTAs per SM: measured 2 / 3 / 4 / 5 / 6 / 8 -> 0.170 / 0.192 / 0.158 / 0.201 / 0.210 / 0.177 ms (Reso64 batch 2): four
+// (64 registers, a few spilled words) hides the most latency
+#ifndef HN_COMP_BWD_CTAS
+#define HN_COMP_BWD_CTAS 4
+#endif
 template <int NS, int CV>
-__global__ void __launch_bounds__(kCompThreads, 3) composite_bwd_kernel(hn_composite_bwd_t a, int n_tiles) {
+__global__ void __launch_bounds__(kCompThreads, HN_COMP_BWD_CTAS) composite_bwd_kernel(hn_composite_bwd_t a, int n_tiles) {
     constexpr int SPL = NS / 32, C = CV * 128;
     const int lane = threadIdx.x & 31;
     const int ray = blockIdx.x * (kCompThreads / 32) + (threadIdx.x >> 5);
@@ -166,8 +171,8 @@ __global__ void __launch_bounds__(kCompThreads, 3) composite_bwd_kernel(hn_compo
                         uint8_t* dst = (uint8_t*)a.dfeat_image + ((size_t)kb * n_tiles + (m >> 7)) * kBlockBytes +
                                        image_offset((uint32_t)(m & 127), col);
                         uint2 pk;
-                        pk.x = pack_h2(fminf(fmaxf(wsc * g[k].x, -65504.f), 65504.f), fminf(fmaxf(wsc * g[k].y, -65504.f), 65504.f));
-                        pk.y = pack_h2(fminf(fmaxf(wsc * g[k].z, -65504.f), 65504.f), fminf(fmaxf(wsc * g[k].w, -65504.f), 65504.f));
+                        pk.x = pack_sat(wsc * g[k].x, wsc * g[k].y);          // one saturating conversion per pair (+-65504)
+                        pk.y = pack_sat(wsc * g[k].z, wsc * g[k].w);
                         *reinterpret_cast<uint2*>(dst) = pk;
                     }
                 }
