@@ -416,12 +416,42 @@ def run_config3(args):
         adam.step(grad_scale=1.0 / world)
         return loss
 
+    copy_in = torch.cuda.Stream(device=dev)
+    e2e_state = {"next": None, "pending": [], "count": 0, "last_loss": None}
+    loss_slots = [torch.zeros(1).pin_memory() for _ in range(2)]
+
+    def prefetch():
+        """Next step's inputs (8.4 MB: images, masks, codes, cameras) travel on a copy stream while the current step computes."""
+        with torch.cuda.stream(copy_in):
+            x = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_in)
+        return x, ev
+
     def step_e2e():
-        x = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        """The training step from HOST buffers, as a prefetching loader + asynchronous logging would drive it: every step's inputs are
+        copied from pinned memory and its loss is read back inside the timed region (talker_trainer.py:1069 logs it); the copy of
+        step i+1 overlaps step i, and the host waits for step i-1's loss after step i is queued.  timed_region() drains the tail."""
+        main = torch.cuda.current_stream()
+        if e2e_state["next"] is None:
+            e2e_state["next"] = prefetch()
+        x, ev = e2e_state["next"]
+        main.wait_event(ev)
+        for t in x.values():
+            t.record_stream(main)
+        e2e_state["next"] = prefetch()
         loss = step(x)
-        loss_host[:1].copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()     # the step's loss is on the host (as the trainer's logging reads it, talker_trainer.py:1069)
-        return float(loss_host[0])
+        slot = loss_slots[e2e_state["count"] & 1]
+        e2e_state["count"] += 1
+        slot.copy_(loss.detach().reshape(1), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        e2e_state["pending"].append((done, slot))
+        if len(e2e_state["pending"]) > 1:
+            d_ev, d_slot = e2e_state["pending"].pop(0)
+            d_ev.synchronize()
+            e2e_state["last_loss"] = float(d_slot[0])
+        return e2e_state["last_loss"]
 
     sampler = ClockSampler(local)
     if rank == 0:
