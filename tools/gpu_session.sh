@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box session of round 2 (run through gpurun): parity tests, the bench, A/B variants of the weight-gradient kernel and one
+# One GPU-box session of round 2 (run through gpurun): parity tests, the bench, A/B switches of the weight-gradient kernel and one
 # ncu --set full capture of the MLP kernels.   usage: bash tools/gpu_session.sh <tag>
 tag=${1:-r2c}
 out=gpurun_out/$tag
@@ -7,9 +7,6 @@ mkdir -p $out
 python -m pytest tests -m gpu -q --timeout 900 > $out/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $out/pytest.log
 B="python bench.py --no-high --warmup 5"
 $B --steps 30 --sustain-s 1.5 > $out/bench_c2.json 2> $out/bench_c2.err; echo "bench rc=$?"
-for v in W8 W1 W2; do
-  HN_LIB_PATH=build/libhn_$v.so $B --steps 15 --sustain-s 0.2 > $out/bench_$v.json 2> $out/bench_$v.err; echo "$v rc=$?"
-done
 HN_WGRAD_DUOS=0 $B --steps 15 --sustain-s 0.2 > $out/bench_noduo.json 2> $out/bench_noduo.err; echo "noduo rc=$?"
 HN_WGRAD_SIDE=0 $B --steps 15 --sustain-s 0.2 > $out/bench_noside.json 2> $out/bench_noside.err; echo "noside rc=$?"
 export HN_WGRAD_SIDE=0
