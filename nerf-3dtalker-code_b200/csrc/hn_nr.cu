@@ -349,11 +349,19 @@ __device__ __forceinline__ bool k_loop_async(const Operand& A, const Operand& B,
 // weights) were staged in shared memory while the contraction ran; the per-element operand (saved activation for LeakyReLU',
 // or the addend) is loaded for all 32 columns before the accumulator is waited for.
 enum { kAuxNone = 0, kAuxMask = 1, kAuxAdd = 2 };
+constexpr int kPiece = 16;                                      // accumulator columns per epilogue piece (a 32-column tile keeps both warp groups busy)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
 template <bool BIAS, bool LRELU, int AUX, bool RGB>
-__device__ __forceinline__ void epi_piece(const uint32_t (&v)[32], const float (&aux)[32], const NrShared& sh, float* out, int col0, int nv, bool row_ok,
+__device__ __forceinline__ void epi_piece(const uint32_t (&v)[kPiece], const float (&aux)[kPiece], const NrShared& sh, float* out, int col0, int nv, bool row_ok,
                                           long long plane, float (&rgb)[3]) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < kPiece; ++c) {
         float y = __uint_as_float(v[c]);
         if (BIAS) y += sh.bias_s[col0 + c];
         if (LRELU) y = fmaxf(y, y * kSlope);
@@ -367,19 +375,19 @@ __device__ __forceinline__ void epi_piece(const uint32_t (&v)[32], const float (
         }
     }
 }
-__device__ __forceinline__ void load_aux(float (&aux)[32], const float* src, int nv, bool row_ok, long long plane) {
+__device__ __forceinline__ void load_aux(float (&aux)[kPiece], const float* src, int nv, bool row_ok, long long plane) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) aux[c] = (row_ok && c < nv) ? __ldg(src + c * plane) : 0.f;
+    for (int c = 0; c < kPiece; ++c) aux[c] = (row_ok && c < nv) ? __ldg(src + c * plane) : 0.f;
 }
 
 // Epilogue of one pixel-row tile (all threads of the CTA): warp w drains TMEM lanes (w % 4) * 32 .. + 31, the two warp groups take
-// alternate 32-column pieces; the RGB head's two partial dot products meet in shared memory.
+// alternate 16-column pieces; the RGB head's two partial dot products meet in shared memory.
 __device__ __forceinline__ void epilogue_rows(const NrProb& P, NrShared& sh, uint32_t tmem_acc, int item, int m0, int n0, int n_tile,
                                               const float (&rgb_prev)[3], bool ok, int warp, int lane) {
     const int q = warp & 3, half = warp >> 2;
     const int m = m0 + q * 32 + lane;
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(q * 32) << 16);
-    const int n_pieces = (n_tile + 31) / 32;
+    const int n_pieces = (n_tile + kPiece - 1) / kPiece;
     float rgb[3] = {0.f, 0.f, 0.f};
     const long long plane = P.M;
     const float* wrgb = P.wrgb;
@@ -388,21 +396,21 @@ __device__ __forceinline__ void epilogue_rows(const NrProb& P, NrShared& sh, uin
     const int epi = P.epi;
     const float* aux_src = epi == 4 ? P.mask_act : (epi == 5 ? P.addend : nullptr);
     for (int pc = half; pc < n_pieces && ok; pc += 2) {
-        uint32_t v[32];
-        float aux[32];
-        const int n_first = n0 + pc * 32, nv = P.N - n_first;
+        uint32_t v[kPiece];
+        float aux[kPiece];
+        const int n_first = n0 + pc * kPiece, nv = P.N - n_first;
         const long long idx_first = idx0 + n_first * plane;
-        tmem_ld32(lane_addr + pc * 32, v);
+        tmem_ld16(lane_addr + pc * kPiece, v);
         if (aux_src) load_aux(aux, aux_src + idx_first, nv, row_ok, plane);
         tmem_ld_wait();
         float* out = P.out + idx_first;
         switch (epi) {                                        // block-uniform
-            case 0: epi_piece<false, false, kAuxNone, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
-            case 1: epi_piece<true, false, kAuxNone, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
-            case 2: epi_piece<true, true, kAuxNone, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
-            case 3: epi_piece<true, true, kAuxNone, true>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
-            case 4: epi_piece<false, false, kAuxMask, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
-            default: epi_piece<false, false, kAuxAdd, false>(v, aux, sh, out, pc * 32, nv, row_ok, plane, rgb); break;
+            case 0: epi_piece<false, false, kAuxNone, false>(v, aux, sh, out, pc * kPiece, nv, row_ok, plane, rgb); break;
+            case 1: epi_piece<true, false, kAuxNone, false>(v, aux, sh, out, pc * kPiece, nv, row_ok, plane, rgb); break;
+            case 2: epi_piece<true, true, kAuxNone, false>(v, aux, sh, out, pc * kPiece, nv, row_ok, plane, rgb); break;
+            case 3: epi_piece<true, true, kAuxNone, true>(v, aux, sh, out, pc * kPiece, nv, row_ok, plane, rgb); break;
+            case 4: epi_piece<false, false, kAuxMask, false>(v, aux, sh, out, pc * kPiece, nv, row_ok, plane, rgb); break;
+            default: epi_piece<false, false, kAuxAdd, false>(v, aux, sh, out, pc * kPiece, nv, row_ok, plane, rgb); break;
         }
     }
     if (wrgb) {                                               // block-uniform branch
