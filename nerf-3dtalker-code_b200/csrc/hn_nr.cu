@@ -551,8 +551,8 @@ __global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(con
 
 // Gradient entering a block's feat_layers convolution (neural_renderer.py:83-87 backwards): the RGB head adds W_rgb^T g_rgb to
 // the gradient arriving from the next block, then LeakyReLU'.  For the last block g_rgb itself comes from the image gradient
-// through the sigmoid.  One thread per pixel and group of 16 channels (coalesced across the warp).
-constexpr int kHeadChannels = 16;
+// through the sigmoid.  One thread per 4 pixels and group of 8 channels (coalesced across the warp).
+constexpr int kHeadChannels = 8;
 template <int V>                                                // V = pixels per thread (4: float4 along the plane, needs P % 4 == 0)
 __global__ void __launch_bounds__(256) nr_head_bwd_kernel(const float* __restrict__ g_img, const float* __restrict__ img, int sigmoid,
                                                           float* __restrict__ g_rgb, const float* __restrict__ g_net, const float* __restrict__ net,
@@ -575,24 +575,35 @@ __global__ void __launch_bounds__(256) nr_head_bwd_kernel(const float* __restric
             } else gr[j][e] = g_rgb[idx + e];
         }
     }
-    const int c_end = min(Cn, (int)(blockIdx.y + 1) * kHeadChannels);
-    for (int c = blockIdx.y * kHeadChannels; c < c_end; ++c) {
-        const long long idx = ((long long)item * Cn + c) * P + p;
-        const float w0 = __ldg(wrgb + c), w1 = __ldg(wrgb + Cn + c), w2 = __ldg(wrgb + 2 * Cn + c);
-        float a[V], gn[V], o[V];
+    // fixed trip count, fully unrolled: the read-only loads of all 8 channels are issued before the first store (a run-time bounded
+    // loop exposed one global round trip per channel: ncu long-scoreboard stall 28 of 31 cycles per issue)
+    const int c0 = blockIdx.y * kHeadChannels;
+    float a[kHeadChannels][V], gn[kHeadChannels][V];
+#pragma unroll
+    for (int k = 0; k < kHeadChannels; ++k) {
+        const int c = c0 + k;
+        const long long idx = ((long long)item * Cn + (c < Cn ? c : Cn - 1)) * P + p;
         if (V == 4) {
             const float4 av = __ldg(reinterpret_cast<const float4*>(net + idx));
-            a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
-            if (g_net) { const float4 gv = __ldg(reinterpret_cast<const float4*>(g_net + idx)); gn[0] = gv.x; gn[1] = gv.y; gn[2] = gv.z; gn[3] = gv.w; }
+            a[k][0] = av.x; a[k][1] = av.y; a[k][2] = av.z; a[k][3] = av.w;
+            if (g_net) { const float4 gv = __ldg(reinterpret_cast<const float4*>(g_net + idx)); gn[k][0] = gv.x; gn[k][1] = gv.y; gn[k][2] = gv.z; gn[k][3] = gv.w; }
         } else {
-            a[0] = __ldg(net + idx);
-            if (g_net) gn[0] = __ldg(g_net + idx);
+            a[k][0] = __ldg(net + idx);
+            if (g_net) gn[k][0] = __ldg(g_net + idx);
         }
+    }
+#pragma unroll
+    for (int k = 0; k < kHeadChannels; ++k) {
+        const int c = c0 + k;
+        if (c >= Cn) break;
+        const long long idx = ((long long)item * Cn + c) * P + p;
+        const float w0 = __ldg(wrgb + c), w1 = __ldg(wrgb + Cn + c), w2 = __ldg(wrgb + 2 * Cn + c);
+        float o[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             float v = fmaf(w0, gr[0][e], fmaf(w1, gr[1][e], w2 * gr[2][e]));
-            if (g_net) v += gn[e];
-            o[e] = a[e] > 0.f ? v : v * kSlope;
+            if (g_net) v += gn[k][e];
+            o[e] = a[k][e] > 0.f ? v : v * kSlope;
         }
         if (V == 4) *reinterpret_cast<float4*>(g_pre + idx) = make_float4(o[0], o[1], o[2], o[3]);
         else g_pre[idx] = o[0];

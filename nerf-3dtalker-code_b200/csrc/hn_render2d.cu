@@ -186,6 +186,90 @@ __global__ void __launch_bounds__(256) upsample_tail_bwd_kernel(const float* __r
     }
 }
 
+// Software-pipelined form of the grouped kernel for full-width, 16-byte aligned tiles (W2 % 64 == 0): while plane r is filtered,
+// the dy tile and the z2 values of plane r + 1 are already in flight in registers (double-buffered shared tile, one barrier
+// per plane).  The plain kernel above exposed two global round trips per plane - ncu: 22 of 33 stall cycles on the long scoreboard.
+__global__ void __launch_bounds__(256) upsample_tail_bwd_pipe_kernel(const float* __restrict__ dy, const float* __restrict__ z2, Taps3 f,
+                                                                     float* __restrict__ dz2, float* __restrict__ dx, int B, int C, int H, int W, float slope) {
+    __shared__ float g[2][kBY + 2][kBX + 4];
+    const int H2 = 2 * H, W2 = 2 * W;
+    const int tiles_x = W2 / kBX;
+    const int X0 = (blockIdx.x % tiles_x) * kBX, Y0 = (blockIdx.x / tiles_x) * kBY;
+    const int b = blockIdx.z, tid = threadIdx.x;
+    const int lj = tid & 31, li = tid >> 5;
+    const int j = (X0 >> 1) + lj, i = (Y0 >> 1) + li;
+    const bool inside = i < H && j < W;
+    const size_t pix = (size_t)i * W + j, HW = (size_t)H * W;
+    float wy[2][3], wx[2][3];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        adjoint_weights(Y0 + 2 * li + d, H2, f, &wy[d][0], &wy[d][1], &wy[d][2]);
+        adjoint_weights(X0 + 2 * lj + d, W2, f, &wx[d][0], &wx[d][1], &wx[d][2]);
+    }
+    // this thread's share of a tile fill: float4 (row tid / 16, columns 4 (tid % 16) ..), for tid < 32 also rows 16 / 17, for tid < 36 a halo element
+    const int sy0 = tid >> 4, c4 = tid & 15, sy1 = 16 + (tid >> 4), syh = tid >> 1, sxh = (tid & 1) ? kBX + 1 : 0;
+    float4 f0, f1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float fh = 0.f, zv[4] = {1.f, 1.f, 1.f, 1.f};
+    auto load_plane = [&](int r) {
+        const int c = (int)blockIdx.y + r * (C >> 2);
+        const float* plane = dy + ((size_t)b * C + c) * H2 * W2;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        int Y = Y0 - 1 + sy0;
+        f0 = (Y >= 0 && Y < H2) ? __ldg(reinterpret_cast<const float4*>(plane + (size_t)Y * W2 + X0) + c4) : zero;
+        if (tid < 32) {
+            Y = Y0 - 1 + sy1;
+            f1 = (Y >= 0 && Y < H2) ? __ldg(reinterpret_cast<const float4*>(plane + (size_t)Y * W2 + X0) + c4) : zero;
+        }
+        if (tid < 2 * (kBY + 2)) {
+            Y = Y0 - 1 + syh;
+            const int X = X0 - 1 + sxh;
+            fh = (Y >= 0 && Y < H2 && X >= 0 && X < W2) ? __ldg(plane + (size_t)Y * W2 + X) : 0.f;
+        }
+        if (inside && dz2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) zv[q] = __ldg(z2 + ((size_t)b * 4 * C + 4 * c + q) * HW + pix);
+        }
+    };
+    load_plane(0);
+    float dxacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float (*gb)[kBX + 4] = g[r & 1];
+        gb[sy0][1 + 4 * c4] = f0.x; gb[sy0][2 + 4 * c4] = f0.y; gb[sy0][3 + 4 * c4] = f0.z; gb[sy0][4 + 4 * c4] = f0.w;
+        if (tid < 32) { gb[sy1][1 + 4 * c4] = f1.x; gb[sy1][2 + 4 * c4] = f1.y; gb[sy1][3 + 4 * c4] = f1.z; gb[sy1][4 + 4 * c4] = f1.w; }
+        if (tid < 2 * (kBY + 2)) gb[syh][sxh] = fh;
+        float zc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) zc[q] = zv[q];
+        const int c = (int)blockIdx.y + r * (C >> 2);
+        if (r + 1 < 4) load_plane(r + 1);                     // travels while this plane is filtered
+        __syncthreads();
+        if (!inside) continue;
+        float win[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) win[a][e] = gb[2 * li + a][2 * lj + e];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int dyq = q >> 1, dxq = q & 1;
+            const float r0 = wx[dxq][0] * win[dyq][dxq] + wx[dxq][1] * win[dyq][dxq + 1] + wx[dxq][2] * win[dyq][dxq + 2];
+            const float r1 = wx[dxq][0] * win[dyq + 1][dxq] + wx[dxq][1] * win[dyq + 1][dxq + 1] + wx[dxq][2] * win[dyq + 1][dxq + 2];
+            const float r2 = wx[dxq][0] * win[dyq + 2][dxq] + wx[dxq][1] * win[dyq + 2][dxq + 1] + wx[dxq][2] * win[dyq + 2][dxq + 2];
+            const float ds = wy[dyq][0] * r0 + wy[dyq][1] * r1 + wy[dyq][2] * r2;
+            if (dz2) dz2[((size_t)b * 4 * C + 4 * c + q) * HW + pix] = zc[q] > 0.f ? ds : ds * slope;
+            dxacc[q] += ds;
+        }
+    }
+    if (dx && inside) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float* d = dx + ((size_t)b * C + 4 * blockIdx.y + q) * HW + pix;
+            *d += dxacc[q];
+        }
+    }
+}
+
 // bilinear x2 (align_corners = False) source rows / weight of destination index Y
 __device__ __forceinline__ void bilinear_src(int Y, int n_in, int* i0, int* i1, float* l) {
     float s = (Y + 0.5f) * 0.5f - 0.5f;
@@ -309,7 +393,9 @@ extern "C" int hn_upsample_tail_bwd(const float* dy, const float* z2, const floa
     if (!dy || !z2 || !f3_host || B <= 0 || C <= 0 || H < 2 || W < 2 || !taps_from(f3_host, &t)) return set_error(HN_E_BADARG, "hn_upsample_tail_bwd: bad argument");
     if (C > 65535 || B > 65535) return set_error(HN_E_UNSUPPORTED, "hn_upsample_tail_bwd: more than 65535 channels or items");
     const unsigned tiles = (unsigned)(((2 * W + kBX - 1) / kBX) * ((2 * H + kBY - 1) / kBY));
-    if (C % 4 == 0) upsample_tail_bwd_kernel<true><<<dim3(tiles, (unsigned)(C / 4), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
+    if (C % 4 == 0 && (2 * W) % kBX == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0)
+        upsample_tail_bwd_pipe_kernel<<<dim3(tiles, (unsigned)(C / 4), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
+    else if (C % 4 == 0) upsample_tail_bwd_kernel<true><<<dim3(tiles, (unsigned)(C / 4), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
     else upsample_tail_bwd_kernel<false><<<dim3(tiles, (unsigned)C, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(dy, z2, t, dz2, dx, B, C, H, W, 0.2f);
     return check_launch("hn_upsample_tail_bwd");
 }
