@@ -18,7 +18,7 @@
 // Operands pass through registers on their way into the canonical SWIZZLE_128B K-major shared-memory layout (128-byte rows of
 // 32 tf32): NCHW planes with rows = pixels are transposed there (float4 loads along the pixels, 4 x 4 register transpose, 16-byte
 // row chunks), rounded to tf32 with one integer add; a two-stage ring feeds four K = 8 MMAs per 32-wide block.
-// Measured (profiles/r02_nr_*): the whole renderer forward + backward at Reso32HR, batch 2: 1.9 ms (the module-by-module cuDNN
+// Measured (profiles/r02_nr_*): the whole renderer forward + backward at Reso32HR, batch 2: 1.8 ms (the module-by-module cuDNN
 // path: 3.3 ms incl. its launch gaps).  What bounds it: the low-resolution layers are chains of 8-16 dependent global-memory
 // round trips on 48-128 CTAs; the high-resolution layers run ~5.5 us per 128-pixel tile with two CTAs per SM (registers);
 // a multi-tile streaming variant was measured and brought nothing once its register prefetch spilled.
