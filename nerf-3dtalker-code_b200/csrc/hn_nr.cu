@@ -18,6 +18,8 @@
 // Operands pass through registers on their way into the canonical SWIZZLE_128B K-major shared-memory layout (128-byte rows of
 // 32 tf32): NCHW planes with rows = pixels are transposed there (float4 loads along the pixels, 4 x 4 register transpose, 16-byte
 // row chunks), rounded to tf32 with one integer add; a two-stage ring feeds four K = 8 MMAs per 32-wide block.
+// (kind::tf32 accepts K-major operands only - with either major bit set the accumulator comes back all zero, tools/probe_tf32.cu -
+// so the row-contiguous planes cannot be handed to the tensor core as they lie in memory.)
 // Measured (profiles/r02_nr_*): the whole renderer forward + backward at Reso32HR, batch 2: 1.8 ms (the module-by-module cuDNN
 // path: 3.3 ms incl. its launch gaps).  What bounds it: the low-resolution layers are chains of 8-16 dependent global-memory
 // round trips on 48-128 CTAs; the high-resolution layers run ~5.5 us per 128-pixel tile with two CTAs per SM (registers);
