@@ -71,6 +71,24 @@ def test_ctypes_struct_layouts_match_the_header(hn, tmp_path):
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
+def test_renderer_workspace_sizes(hn):
+    """hn_nr_saved_floats / hn_nr_scratch_floats / hn_nr_launches: host-side geometry only (no GPU): the saved buffer holds exactly the
+    four activations of every block plus the RGB chain, unsupported geometries are refused."""
+    lib = hn._lib.load()
+    B, nb, nc, mf, fs = 2, 4, 256, 32, 32                     # Reso32HR: 32 x 32 x 256 -> 512 x 512
+    C = [max(nc >> i, mf) for i in range(nb + 1)]
+    P = [(fs << i) ** 2 for i in range(nb + 1)]
+    pad = lambda n: (n + 63) // 64 * 64
+    want = sum(pad(B * 2 * C[i] * P[i]) + pad(B * 4 * C[i] * P[i]) + pad(B * C[i] * P[i + 1]) + pad(B * C[i + 1] * P[i + 1]) for i in range(nb))
+    want += pad(B * 3 * P[0]) + sum(2 * pad(B * 3 * P[l]) for l in range(1, nb + 1))
+    assert lib.hn_nr_saved_floats(B, nb, nc, mf, fs) == want
+    assert lib.hn_nr_scratch_floats(B, nb, nc, mf, fs) > 0
+    assert lib.hn_nr_saved_floats(2 * B, nb, nc, mf, fs) > want
+    assert lib.hn_nr_launches(nb, 0) == 5 * nb and lib.hn_nr_launches(nb, 1) == 6 * nb + 1
+    for bad in [(0, nb, nc, mf, fs), (B, 0, nc, mf, fs), (B, 5, nc, mf, fs), (B, nb, 258, mf, fs), (B, nb, 1024, 512, fs), (B, nb, nc, mf, 1)]:
+        assert lib.hn_nr_saved_floats(*bad) == -1 and lib.hn_nr_scratch_floats(*bad) == -1, bad
+
+
 @pytest.mark.parametrize("fs,S", [(32, 256), (32, 512), (64, 512)])
 def test_state_dict_layout_matches_reference(hn, fs, S):
     opt = O.OracleOptions(featmap_size=fs, pred_img_size=S)
