@@ -334,8 +334,9 @@ class HeadNeRFNet(nn.Module):
 
     def capture_consumer_graph(self, batch_size):
         """Opt-in: capture NeuralRenderer's forward and backward over `batch_size` + 1 feature maps (the merged maps and the
-        background map, see _forward) into CUDA graphs (torch.cuda.make_graphed_callables).  The consumer is ~130 small launches per
-        training step and bound by the host's launch rate; replaying two graphs removes that.  Only calls with exactly the captured
+        background map, see _forward) into CUDA graphs (torch.cuda.make_graphed_callables).  Useful for the module-by-module path
+        (`neural_renderer.FUSED_NET = False`, deterministic mode: ~130 small launches per step, bound by the host's launch rate);
+        the default one-call renderer (hn_nr_fwd / hn_nr_bwd, 45 kernels from two C calls) is GPU-bound without it.  Only calls with exactly the captured
         input shape, autograd enabled and the captured training mode replay the graphs; every other call (validation under
         no_grad, other batch sizes, the background map alone) runs the eager module.  The module tree, its state_dict keys and
         the parameters are untouched; `release_consumer_graph()` restores plain eager launches."""
