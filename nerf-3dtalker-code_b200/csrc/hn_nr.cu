@@ -40,7 +40,8 @@ namespace hn {
 #ifndef HN_NR_MIN_CTAS
 #define HN_NR_MIN_CTAS 2
 #endif
-constexpr int kNrThreads = 256;
+constexpr int kNrThreads = 256;                              // loader / epilogue threads (8 warps); a ninth warp issues the MMAs
+constexpr int kNrCtaThreads = kNrThreads + 32;
 constexpr int kNrMaxN = 256;
 constexpr uint32_t kNrStageA = 128 * 128;                    // 128 rows x 32 tf32
 constexpr uint32_t kNrStageB = kNrMaxN * 128;
@@ -126,7 +127,7 @@ __device__ __forceinline__ void sstore(const float4 (&r)[NJ], const Operand& o, 
 }
 
 struct NrShared {
-    uint64_t stage_free[4], done;
+    uint64_t stage_free[4], stage_full[4], done;
     uint32_t tmem_base;
     float rgb_part[128 * 3];
     float bias_s[kNrMaxN], wrgb_s[3][kNrMaxN];               // this tile's columns of the bias / RGB-head weights (zero beyond N)
@@ -259,17 +260,32 @@ __device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k
             lb.load(rb, k_len - (kb + 1) * 32, tid);
         }
         fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();                                      // (the first one also publishes the barriers and the TMEM address)
-        if (tid == 0 && ok) {
-            tc_fence_after_sync();
-            const uint32_t tmem_base = sh->tmem_base;
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(smem_u32(&sh->stage_full[s]));      // one arrival per loader warp; the MMA warp does the rest
+    }
+    return ok;
+}
+
+// The ninth warp: waits for a stage to be full, issues its four K = 8 MMAs, and hands the stage back when they retire.  With the
+// issue on its own thread the loaders never wait for it (before, thread 0 did both and its 0.4 us of descriptor building + issue
+// per block sat on everybody's critical path: 64-block weight-gradient CTA, measured 67 us = 18 wait-free + 14 cp.async issue +
+// 6 row sums + 28 MMA issue).
+__device__ __forceinline__ bool mma_loop(int nkb, uint32_t smem, int n_stages, uint32_t stage_bytes, NrShared* sh, uint32_t idesc, int lane) {
+    bool ok = true;
+    const uint32_t tmem_base = sh->tmem_base;
+    for (int kb = 0; kb < nkb && ok; ++kb) {
+        const int s = kb % n_stages;
+        ok = mbar_wait(smem_u32(&sh->stage_full[s]), (kb / n_stages) & 1);
+        tc_fence_after_sync();
+        if (lane == 0 && ok) {
+            const uint32_t stA = smem + s * stage_bytes, stB = stA + kNrStageA;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
                 umma_tf32(tmem_base, umma_desc_kmajor(stA, ks), umma_desc_kmajor(stB, ks), idesc, (kb | ks) ? 1u : 0u);
             umma_commit(smem_u32(&sh->stage_free[s]));
             if (kb == nkb - 1) umma_commit(smem_u32(&sh->done));
         }
+        __syncwarp();
     }
     return ok;
 }
@@ -331,17 +347,8 @@ __device__ __forceinline__ bool k_loop_async(const Operand& A, const Operand& B,
             }
         }
         fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();                                        // (the first one also publishes the barriers and the TMEM address)
-        if (tid == 0 && ok) {
-            tc_fence_after_sync();
-            const uint32_t tmem_base = sh->tmem_base;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-                umma_tf32(tmem_base, umma_desc_kmajor(stA, ks), umma_desc_kmajor(stB, ks), idesc, (kb | ks) ? 1u : 0u);
-            umma_commit(smem_u32(&sh->stage_free[s]));
-            if (kb == nkb - 1) umma_commit(smem_u32(&sh->done));
-        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(smem_u32(&sh->stage_full[s]));
     }
     return ok;
 }
@@ -417,7 +424,7 @@ __device__ __forceinline__ void epilogue_rows(const NrProb& P, NrShared& sh, uin
     }
     if (wrgb) {                                               // block-uniform branch
         if (half == 1) { sh.rgb_part[(q * 32 + lane) * 3 + 0] = rgb[0]; sh.rgb_part[(q * 32 + lane) * 3 + 1] = rgb[1]; sh.rgb_part[(q * 32 + lane) * 3 + 2] = rgb[2]; }
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;" ::"n"(kNrThreads) : "memory");      // the eight epilogue warps only
         if (half == 0 && row_ok && ok) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -444,7 +451,7 @@ __device__ __forceinline__ void load_rgb_prev(float (&r)[3], const NrProb& P, in
     for (int j = 0; j < 3; ++j) r[j] = (active && P.rgb_in && m < P.M) ? __ldg(P.rgb_in + item * 3ll * P.M + (long long)j * P.M + m) : 0.f;
 }
 
-__global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(const __grid_constant__ NrLaunch L) {
+__global__ void __launch_bounds__(kNrCtaThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(const __grid_constant__ NrLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ NrShared sh;
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -457,14 +464,17 @@ __global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(con
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&sh.stage_free[i]), 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sh.stage_free[i]), 1); mbar_init(smem_u32(&sh.stage_full[i]), kNrThreads / 32); }
         mbar_init(smem_u32(&sh.done), 1);
         mbar_fence_init();
     }
-    if (warp == 0) {                                           // published by the first __syncthreads of the contraction loop
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)), "r"(L.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    tc_fence_before_sync();
+    __syncthreads();                                           // barriers and the TMEM address are visible to all nine warps
+    tc_fence_after_sync();
     bool ok = true;
 
     {
@@ -488,28 +498,37 @@ __global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(con
         B.rs = P.b_rs; B.ks = P.b_ks; B.rows_valid = P.N - n0; B.rows_tile = n_tile;
         B.vec = P.b_ks == 1 && (k_len & 3) == 0 && (P.b_rs & 3) == 0 && ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0);
 
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, half = (warp >> 2) & 1;
         const int m = m0 + q * 32 + lane;
         float rgb_prev[3] = {0.f, 0.f, 0.f};
-        if (P.kind == 0) {
-            stage_columns(P, sh, n0, tid);
-            if (P.wrgb) load_rgb_prev(rgb_prev, P, item, m, half == 0);
-        }
         const uint32_t idesc = umma_idesc(128, (uint32_t)n_tile, 2u, 2u, 0, 0);      // 2 = tf32 operands, f32 accumulator
         const bool want_dbias = P.kind == 1 && P.dbias != nullptr && nt == 0;
         float bsum[4] = {0.f, 0.f, 0.f, 0.f};
         const bool a_rc = P.a_rs == 1 && (P.a_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.base) & 15) == 0) && (A.rows_valid >= 128 || (A.rows_valid & 3) == 0);
         const bool b_rc = P.b_rs == 1 && (P.b_ks & 3) == 0 && ((reinterpret_cast<uintptr_t>(B.base) & 15) == 0) && (B.rows_valid >= n_tile || (B.rows_valid & 3) == 0);
-        if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
-        else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
-        else if (A.vec && B.vec && L.async_loads && nkb >= 4) {
-            const uint32_t sb = kNrStageA + (uint32_t)((n_tile * 128 + 1023) & ~1023);          // this tile's stage: as many as fit the launch's window
-            const int n_stages = min(4, (int)(L.window_bytes / sb));
-            if (n_stages >= 4) ok = k_loop_async<2>(A, B, k_len, nkb, smem, n_stages, sb, &sh, idesc, want_dbias, bsum, tid);
-            else ok = k_loop_async<1>(A, B, k_len, nkb, smem, n_stages, sb, &sh, idesc, want_dbias, bsum, tid);
+        const bool use_async = !(a_rc && (B.vec || b_rc)) && A.vec && B.vec && L.async_loads && nkb >= 4;
+        const uint32_t sb_async = kNrStageA + (uint32_t)((n_tile * 128 + 1023) & ~1023);       // this tile's stage: as many as fit the launch's window
+        const int n_stages = use_async ? min(4, (int)(L.window_bytes / sb_async)) : 2;
+        const uint32_t stage_bytes = use_async ? sb_async : L.stage_bytes;
+        if (warp == kNrThreads / 32) {
+            ok = mma_loop(nkb, smem, n_stages, stage_bytes, &sh, idesc, lane);
+        } else {
+            if (P.kind == 0) {
+                stage_columns(P, sh, n0, tid);
+                if (P.wrgb) load_rgb_prev(rgb_prev, P, item, m, half == 0);
+            }
+            if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+            else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+            else if (use_async) {
+                if (n_stages >= 4) ok = k_loop_async<2>(A, B, k_len, nkb, smem, n_stages, sb_async, &sh, idesc, want_dbias, bsum, tid);
+                else ok = k_loop_async<1>(A, B, k_len, nkb, smem, n_stages, sb_async, &sh, idesc, want_dbias, bsum, tid);
+            }
+            else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+            else ok = k_loop<kModeGen, kModeGen>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
         }
-        else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
-        else ok = k_loop<kModeGen, kModeGen>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+        if (warp == kNrThreads / 32) {
+            if (!ok && lane == 0) atomicCAS(L.status, 0, 803);
+        } else {
         if (ok) ok = mbar_wait(smem_u32(&sh.done), 0);
         tc_fence_after_sync();
         if (!ok && tid == 0) atomicCAS(L.status, 0, 801);
@@ -544,6 +563,7 @@ __global__ void __launch_bounds__(kNrThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(con
                     if ((tid & 7) == 0 && m0 + row < P.M) atomicAdd(P.dbias + m0 + row, sum);
                 }
             }
+        }
         }
     }
     tc_fence_before_sync();
@@ -750,7 +770,7 @@ static int launch_group(std::vector<NrProb>& ps, int* status, cudaStream_t st) {
             const uint32_t sb = kNrStageA + (uint32_t)((L.p[i].n_tile * 128 + 1023) & ~1023);
             L.window_bytes = std::max(L.window_bytes, std::min(4 * sb, 2 * kNrStage));
         }
-    nr_gemm_kernel<<<total, kNrThreads, L.window_bytes + 1024, st>>>(L);
+    nr_gemm_kernel<<<total, kNrCtaThreads, L.window_bytes + 1024, st>>>(L);
     return check_launch("hn_nr (grouped tf32 GEMM)");
 }
 
