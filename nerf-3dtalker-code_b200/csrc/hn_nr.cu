@@ -78,6 +78,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// split-descriptor form (hn_tc.cuh): high word constant, low word = (address >> 4) | (LBO >> 4) << 16; a K = 8 tf32 step is 32 bytes (+2)
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+
 struct Operand { const float* base; long long rs, ks; int rows_valid, rows_tile; bool vec; };
 
 // chunk i of a [rows_tile x 32] block = 4 consecutive k of one row; k-contiguous operands put 8 lanes on one 128-byte row,
@@ -278,10 +288,9 @@ __device__ __forceinline__ bool mma_loop(int nkb, uint32_t smem, int n_stages, u
         ok = mbar_wait(smem_u32(&sh->stage_full[s]), (kb / n_stages) & 1);
         tc_fence_after_sync();
         if (lane == 0 && ok) {
-            const uint32_t stA = smem + s * stage_bytes, stB = stA + kNrStageA;
+            const uint32_t a_lo = desc_lo(smem + s * stage_bytes, 16), b_lo = a_lo + (kNrStageA >> 4);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-                umma_tf32(tmem_base, umma_desc_kmajor(stA, ks), umma_desc_kmajor(stB, ks), idesc, (kb | ks) ? 1u : 0u);
+            for (uint32_t ks = 0; ks < 4; ++ks) umma_tf32_lohi(tmem_base, a_lo + 2 * ks, b_lo + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
             umma_commit(smem_u32(&sh->stage_free[s]));
             if (kb == nkb - 1) umma_commit(smem_u32(&sh->done));
         }
