@@ -140,7 +140,7 @@ struct NrShared {
     uint64_t stage_free[4], stage_full[4], done;
     uint32_t tmem_base;
     float rgb_part[128 * 3];
-    float bias_s[kNrMaxN], wrgb_s[3][kNrMaxN];               // this tile's columns of the bias / RGB-head weights (zero beyond N)
+    float bias_s[kNrMaxN], wrgb_s[3][kNrMaxN], brgb_s[4];               // this tile's columns of the bias / RGB-head weights (zero beyond N)
 };
 
 // ---- fast loaders: the thread -> (row, chunk) map is fixed at compile time, so a block costs a handful of address adds
@@ -438,7 +438,7 @@ __device__ __forceinline__ void epilogue_rows(const NrProb& P, NrShared& sh, uin
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const long long idx = item * 3 * plane + j * plane + m;
-                float y = rgb[j] + sh.rgb_part[(q * 32 + lane) * 3 + j] + __ldg(P.brgb + j) + rgb_prev[j];
+                float y = rgb[j] + sh.rgb_part[(q * 32 + lane) * 3 + j] + sh.brgb_s[j] + rgb_prev[j];
                 if (P.sigmoid) y = 1.0f / (1.0f + __expf(-y));
                 P.rgb_out[idx] = y;
             }
@@ -453,6 +453,7 @@ __device__ __forceinline__ void stage_columns(const NrProb& P, NrShared& sh, int
     if (P.wrgb) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) sh.wrgb_s[j][tid] = n < P.N ? __ldg(P.wrgb + j * P.N + n) : 0.f;
+        if (tid < 3) sh.brgb_s[tid] = __ldg(P.brgb + tid);
     }
 }
 __device__ __forceinline__ void load_rgb_prev(float (&r)[3], const NrProb& P, int item, int m, bool active) {
