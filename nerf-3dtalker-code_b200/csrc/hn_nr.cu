@@ -246,13 +246,13 @@ template <int ROWS> struct Ld<kModeGen, ROWS> {
 
 // The contraction loop of one output tile: two shared-memory stages; the loads of block kb + 1 are in flight while block kb is
 // issued.  Returns false when a barrier wait timed out.
-template <int AM, int BM>
+template <int AM, int BM, int BROWS>
 __device__ __forceinline__ bool k_loop(const Operand& A, const Operand& B, int k_len, int nkb, uint32_t smem, uint32_t stage_bytes, NrShared* sh,
                                        uint32_t idesc, bool want_dbias, float (&bsum)[4], int tid) {
     bool ok = true;
-    float4 ra[4], rb[8];
+    float4 ra[4], rb[BROWS / 32];
     Ld<AM, 128> la(A, tid);
-    Ld<BM, 256> lb(B, tid);
+    Ld<BM, BROWS> lb(B, tid);
     la.load(ra, k_len, tid);
     lb.load(rb, k_len, tid);
     for (int kb = 0; kb < nkb; ++kb) {
@@ -323,7 +323,7 @@ __device__ __forceinline__ void issue_kmajor(const Operand& o, int kb, int k_len
         if (row < o.rows_tile) cp_async16(dst + j * 4096, src + j * 32 * o.rs, kv && row < o.rows_valid);
     }
 }
-template <int LA>                                               // LA = K blocks in flight beyond the one being consumed
+template <int LA, int BROWS>                                    // LA = K blocks in flight beyond the one being consumed
 __device__ __forceinline__ bool k_loop_async(const Operand& A, const Operand& B, int k_len, int nkb, uint32_t smem, int n_stages, uint32_t stage_bytes,
                                              NrShared* sh, uint32_t idesc, bool want_dbias, float (&bsum)[4], int tid) {
     bool ok = true;
@@ -331,7 +331,7 @@ __device__ __forceinline__ bool k_loop_async(const Operand& A, const Operand& B,
     for (int b = 0; b < LA; ++b) {
         if (b < nkb) {
             issue_kmajor<4>(A, b, k_len, smem + b * stage_bytes, tid);
-            issue_kmajor<8>(B, b, k_len, smem + b * stage_bytes + kNrStageA, tid);
+            issue_kmajor<BROWS / 32>(B, b, k_len, smem + b * stage_bytes + kNrStageA, tid);
         }
         cp_async_commit();
     }
@@ -341,7 +341,7 @@ __device__ __forceinline__ bool k_loop_async(const Operand& A, const Operand& B,
             const int sn = nx % n_stages;
             if (nx >= n_stages && ok) ok = mbar_wait(smem_u32(&sh->stage_free[sn]), ((nx / n_stages) - 1) & 1);   // its previous tenant's MMAs retired
             issue_kmajor<4>(A, nx, k_len, smem + sn * stage_bytes, tid);
-            issue_kmajor<8>(B, nx, k_len, smem + sn * stage_bytes + kNrStageA, tid);
+            issue_kmajor<BROWS / 32>(B, nx, k_len, smem + sn * stage_bytes + kNrStageA, tid);
         }
         cp_async_commit();
         cp_async_wait<LA>();                                    // this thread's chunks of block kb have landed
@@ -461,7 +461,11 @@ __device__ __forceinline__ void load_rgb_prev(float (&r)[3], const NrProb& P, in
     for (int j = 0; j < 3; ++j) r[j] = (active && P.rgb_in && m < P.M) ? __ldg(P.rgb_in + item * 3ll * P.M + (long long)j * P.M + m) : 0.f;
 }
 
-__global__ void __launch_bounds__(kNrCtaThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(const __grid_constant__ NrLaunch L) {
+// BROWS = rows of the B tile the loaders are compiled for: launches whose widest tile has <= 128 columns (every layer from the
+// second block on) run the 128-row instantiation - 16 registers fewer per thread, three CTAs per SM instead of two (ncu: the
+// kernel sits at 14-27 % of the warp slots, bound by latency, not by any pipe).
+template <int BROWS, int MIN_CTAS>
+__global__ void __launch_bounds__(kNrCtaThreads, MIN_CTAS) nr_gemm_kernel(const __grid_constant__ NrLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ NrShared sh;
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -527,14 +531,14 @@ __global__ void __launch_bounds__(kNrCtaThreads, HN_NR_MIN_CTAS) nr_gemm_kernel(
                 stage_columns(P, sh, n0, tid);
                 if (P.wrgb) load_rgb_prev(rgb_prev, P, item, m, half == 0);
             }
-            if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
-            else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+            if (a_rc && B.vec) ok = k_loop<kModeRC, kModeKCV, BROWS>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+            else if (a_rc && b_rc) ok = k_loop<kModeRC, kModeRC, BROWS>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
             else if (use_async) {
-                if (n_stages >= 4) ok = k_loop_async<2>(A, B, k_len, nkb, smem, n_stages, sb_async, &sh, idesc, want_dbias, bsum, tid);
-                else ok = k_loop_async<1>(A, B, k_len, nkb, smem, n_stages, sb_async, &sh, idesc, want_dbias, bsum, tid);
+                if (n_stages >= 4) ok = k_loop_async<2, BROWS>(A, B, k_len, nkb, smem, n_stages, sb_async, &sh, idesc, want_dbias, bsum, tid);
+                else ok = k_loop_async<1, BROWS>(A, B, k_len, nkb, smem, n_stages, sb_async, &sh, idesc, want_dbias, bsum, tid);
             }
-            else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
-            else ok = k_loop<kModeGen, kModeGen>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+            else if (A.vec && B.vec) ok = k_loop<kModeKCV, kModeKCV, BROWS>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
+            else ok = k_loop<kModeGen, kModeGen, BROWS>(A, B, k_len, nkb, smem, L.stage_bytes, &sh, idesc, want_dbias, bsum, tid);
         }
         if (warp == kNrThreads / 32) {
             if (!ok && lane == 0) atomicCAS(L.status, 0, 803);
@@ -774,13 +778,15 @@ static int launch_group(std::vector<NrProb>& ps, int* status, cudaStream_t st) {
     for (int i = 0; i < L.n; ++i) widest = std::max(widest, L.p[i].n_tile);
     L.tmem_cols = widest <= 32 ? 32 : (widest <= 64 ? 64 : (widest <= 128 ? 128 : 256));
     L.stage_bytes = kNrStageA + (uint32_t)((widest * 128 + 1023) & ~1023);
-    L.window_bytes = 2 * L.stage_bytes;                       // two stages of the widest tile; four of the widest weight-gradient tile if that fits 96 KiB
+    const bool small = widest <= 128;                         // the 128-row instantiation: three CTAs per SM, so at most 64 KiB of stages each
+    L.window_bytes = 2 * L.stage_bytes;                       // two stages of the widest tile; four of the widest weight-gradient tile if that fits
     for (int i = 0; i < L.n; ++i)
         if (L.p[i].kind == 1 && L.async_loads) {
             const uint32_t sb = kNrStageA + (uint32_t)((L.p[i].n_tile * 128 + 1023) & ~1023);
-            L.window_bytes = std::max(L.window_bytes, std::min(4 * sb, 2 * kNrStage));
+            L.window_bytes = std::max(L.window_bytes, std::min(4 * sb, small ? 64u * 1024u : 2 * kNrStage));
         }
-    nr_gemm_kernel<<<total, kNrCtaThreads, L.window_bytes + 1024, st>>>(L);
+    if (small) nr_gemm_kernel<128, 3><<<total, kNrCtaThreads, L.window_bytes + 1024, st>>>(L);
+    else nr_gemm_kernel<256, 2><<<total, kNrCtaThreads, L.window_bytes + 1024, st>>>(L);
     return check_launch("hn_nr (grouped tf32 GEMM)");
 }
 
@@ -789,7 +795,8 @@ static int nr_prepare() {
     cudaGetDevice(&dev);
     static bool ready[64] = {};
     if (dev < 64 && !ready[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(nr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNrSmem);
+        cudaError_t e = cudaFuncSetAttribute(nr_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNrSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nr_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNrSmem);
         if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
         ready[dev] = true;
     }
