@@ -22,7 +22,7 @@
 // so the row-contiguous planes cannot be handed to the tensor core as they lie in memory.)
 // Measured (profiles/r02_nr_*): the whole renderer forward + backward at Reso32HR, batch 2: 1.7 ms (the module-by-module cuDNN
 // path: 3.3 ms incl. its launch gaps).  What bounds it: the low-resolution layers are chains of 8-16 dependent global-memory
-// round trips on 48-128 CTAs; the high-resolution layers run ~5.5 us per 128-pixel tile with two CTAs per SM (registers);
+// round trips on 48-128 CTAs; the high-resolution layers run ~5 us per 128-pixel tile with three CTAs per SM (registers);
 // a multi-tile streaming variant was measured and brought nothing once its register prefetch spilled.
 #include <algorithm>
 #include <cstdlib>
